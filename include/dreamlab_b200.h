@@ -1,0 +1,139 @@
+/* dreamlab_b200 — C-ABI of the B200-native LCM denoise + VAE-decode hot path.
+ *
+ * This is the drop-in boundary below the `b200` worker (backends/b200_worker.py), which itself
+ * implements the reference's `PipelineWorker` protocol (reference `backends/base.py:29-39`).
+ * The reference has NO native interface for this path: its CUDA worker makes one call into the
+ * third-party diffusers pipeline (reference `backends/cuda_worker.py:221-229`), which in turn
+ * dispatches to cuDNN/cuBLAS/SDPA through torch.  Each entry point below therefore cites the
+ * diffusers module / reference line whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless noted;
+ *   - activations are NHWC bf16, statistics / time embeddings / latents fp32;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns
+ *     0 on success; non-zero -> text in dl_last_error().  Nothing allocates or synchronises,
+ *     so every call is CUDA-graph capturable;
+ *   - there is no CPU fallback: without a CUDA device / sm_100a every call fails.
+ */
+#ifndef DREAMLAB_B200_H
+#define DREAMLAB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL_ABI_VERSION 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int dl_abi_version(void);
+const char* dl_last_error(void);           /* thread-local text of the last failure          */
+int dl_device_sm_count(void);              /* SM count of the current device (148 on B200)   */
+
+/* ---- implicit-GEMM conv / linear (tcgen05 + TMEM + TMA) ---------------------------------- *
+ * Replaces torch.nn.Conv2d(3x3,s1,p1 | 1x1) and torch.nn.Linear inside diffusers'
+ * ResnetBlock2D / Transformer2DModel / Attention projections / FeedForward(GEGLU) /
+ * Upsample2D / AutoencoderKL decoder convs, reached from reference
+ * `backends/cuda_worker.py:222` (UNet call mirrored at `backends/rknnlcm.py:588-593`,
+ * VAE decode at `backends/rknnlcm.py:618`).                                                  */
+enum {
+  DL_EPI_BF16 = 0,      /* out bf16 [pixels, ldo]: acc*alpha + bias + rowadd + residual      */
+  DL_EPI_GEGLU = 1,     /* weights interleaved (value,gate): out[:, j] = v_j * gelu(g_j)      */
+  DL_EPI_F32 = 2,       /* out fp32 [pixels, ldo] (UNet conv_out -> noise_pred)               */
+  DL_EPI_U8_IMAGE = 3   /* VaeImageProcessor tail fused: clamp(x/2+.5,0,1)*255 -> u8 NHWC
+                           (reference `backends/rknnlcm.py:220-235`)                          */
+};
+
+typedef struct dl_igemm_desc {
+  const void* a0;            /* source 0: NHWC bf16, channels [0,c0)                          */
+  long long a0_pix_stride;   /* elements between consecutive pixels of a0 (>= c0)             */
+  int c0;                    /* multiple of 64                                                */
+  const void* a1;            /* optional source 1 (skip-concat partner), channels [c0,c0+c1)  */
+  long long a1_pix_stride;
+  int c1;                    /* 0 or multiple of 64                                           */
+  int nimg, h, w;            /* activation extent; Linear over M rows: nimg=1, h=1, w=M       */
+  int taps;                  /* 9: conv3x3 stride 1 pad 1;  1: conv1x1 / Linear               */
+  const void* wgt;           /* bf16 [n, taps*(c0+c1)], K index = tap*(c0+c1) + channel       */
+  long long ldw;             /* weight row stride in elements; 0 = dense                      */
+  int n;                     /* output channels                                               */
+  void* out;
+  long long ldo;             /* output row stride in elements                                 */
+  const float* bias;         /* [n] or NULL                                                   */
+  const float* rowadd;       /* [nimg, ld_rowadd] per-image channel add (time emb) or NULL    */
+  int ld_rowadd;
+  const void* residual;      /* bf16 [pixels, ldr] or NULL (DL_EPI_BF16 only)                 */
+  long long ldr;
+  int mode;                  /* DL_EPI_*                                                      */
+  float alpha;               /* accumulator scale (0 -> 1)                                    */
+  int bn;                    /* N tile (multiple of 16, <=256); 0 = auto                      */
+} dl_igemm_desc;
+
+int dl_igemm(const dl_igemm_desc* desc, void* stream);
+
+/* ---- GroupNorm (+SiLU), NHWC bf16, optional two-source concat ---------------------------- *
+ * Replaces torch.nn.GroupNorm + F.silu in ResnetBlock2D.norm1/norm2, conv_norm_out,
+ * Transformer2DModel.norm and the VAE attention group_norm.  With x1 != NULL
+ * the normalised output is the channel concat [x0 | x1] (UNet up-block `torch.cat`, K10).
+ * `workspace` holds per-chunk partial statistics: >= dl_groupnorm_workspace_bytes().          */
+size_t dl_groupnorm_workspace_bytes(int nimg, int groups);
+int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
+                 float eps, const float* gamma, const float* beta, int apply_silu, void* out,
+                 void* workspace, void* stream);
+
+/* ---- LayerNorm over the channel dim, bf16 rows (BasicTransformerBlock.norm1/2/3, K8) ------ */
+int dl_layernorm(const void* x, long long rows, int c, float eps, const float* gamma,
+                 const float* beta, void* out, void* stream);
+
+/* ---- attention (diffusers Attention / AttnProcessor2_0, K5/K6) ---------------------------- *
+ * q: bf16 [batch*sq, ldq]  head h at columns [h*dh_stride, h*dh_stride+d); k, v likewise over
+ * [batch*skv, ld].  out: bf16 [batch*sq, ldo], head h at columns [h*d, (h+1)*d).
+ * impl: DL_ATTN_TC = tcgen05 flash kernel (product path), DL_ATTN_SIMT = CUDA-core checker.   */
+enum { DL_ATTN_TC = 0, DL_ATTN_SIMT = 1 };
+int dl_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                 long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
+                 int skv, int heads, int d, float scale, int impl, void* stream);
+
+/* ---- time / guidance embedding pieces (diffusers Timesteps + TimestepEmbedding, K9) ------- */
+/* out[b, :] = [cos(t_b f_i), sin(t_b f_i)], f_i = exp(-ln(1e4) i/half)  (flip_sin_to_cos)     */
+int dl_timestep_sinusoid(const float* t, int batch, int dim, float* out, void* stream);
+/* out[m, n] = act_out( sum_k act_in(x[m,k]) * w[n,k] + bias[n] + add[m,n] ), x/out fp32,
+ * w bf16 [n,k]; silu flags select the activations.  For the tiny (M <= 64) time-MLP GEMMs.    */
+int dl_small_linear(const float* x, int m, int k, const void* w, const float* bias,
+                    const float* add, int n, int silu_in, int silu_out, float* out, void* stream);
+
+/* ---- data movement (K10): nearest-2x upsample, stride-2 im2col, latent packing ------------ */
+int dl_upsample2x(const void* x, int nimg, int h, int w, int c, void* out, void* stream);
+/* cols[n*ho*wo, 9*c] for conv3x3 stride 2 pad 1 (Downsample2D); K index = tap*c + channel     */
+int dl_im2col_s2(const void* x, int nimg, int h, int w, int c, void* cols, void* stream);
+/* bf16 [npix, cpad] <- mat . (fp32 NHWC [npix, cin] * scale) + vec, zero-padded to cpad channels
+ * (feeds conv_in).  mat/vec: optional fp32 [cin,cin] / [cin] = the VAE post_quant_conv 1x1 and the
+ * `latents / scaling_factor` of reference `backends/rknnlcm.py:614` (K13); NULL = identity.     */
+int dl_pack_latent(const float* x, long long npix, int cin, int cpad, float scale,
+                   const float* mat, const float* vec, void* out, void* stream);
+/* fp32 scores [rows, cols] -> bf16 softmax rows (VAE mid-block attention, heads=1, d=512: the
+ * QK^T / PV contractions run through dl_igemm)                                                  */
+int dl_softmax_rows(const float* scores, long long rows, int cols, void* out, void* stream);
+int dl_nchw_to_nhwc_f32(const float* x, int nimg, int c, int hw, float* out, void* stream);
+int dl_nhwc_to_nchw_f32(const float* x, int nimg, int c, int hw, float* out, void* stream);
+
+/* ---- LCM scheduler step (diffusers LCMScheduler.step, K11; call site mirrored at reference
+ * `backends/rknnlcm.py:596-598`) -------------------------------------------------------------
+ * x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); den = c_out x0 + c_skip x;
+ * x' = sqrt(a_prev) den + sqrt(1-a_prev) noise   (noise == NULL on the final step: x' = den)  */
+typedef struct dl_lcm_coeffs {
+  float sqrt_alpha_t, sqrt_beta_t, c_skip, c_out, sqrt_alpha_prev, sqrt_beta_prev;
+} dl_lcm_coeffs;
+int dl_lcm_step(const float* eps, const float* x, const float* noise, float* x_next,
+                float* denoised, long long n, const dl_lcm_coeffs* coeffs /* host */, void* stream);
+
+/* ---- run_job_with_latents tail: fp32 adaptive_avg_pool2d -> (8,8) -> fp16 NCHW ------------- *
+ * (reference `backends/cuda_worker.py:297-304`).  lat: fp32 NHWC [nimg,h,w,c]; out: fp16
+ * [nimg,c,8,8].  h, w multiples of 8.                                                         */
+int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DREAMLAB_B200_H */

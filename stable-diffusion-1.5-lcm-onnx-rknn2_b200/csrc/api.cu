@@ -1,0 +1,115 @@
+// Host-side plumbing of the C-ABI: error text, driver entry points, tensor-map encoding.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "dreamlab_b200.h"
+
+namespace dl {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  return 0;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver / no GPU): %s",
+              cudaGetErrorString(e));
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) return 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor map: base pointer %p not 16-byte aligned", base);
+    return 1;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) {
+      set_error("tensor map: box[%d]=%u out of range", i, box[i]);
+      return 1;
+    }
+  }
+  for (int i = 0; i < rank - 1; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (gstr[i] % 16 != 0) {
+      set_error("tensor map: stride[%d]=%llu not a multiple of 16 bytes", i,
+                (unsigned long long)gstr[i]);
+      return 1;
+    }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                   gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,%llu,%llu] "
+              "box=[%u,%u,%u,%u]",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+              box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 1;
+  }
+  return 0;
+}
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cached[dev & 63] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)
+      v = 148;
+    cached[dev & 63] = v;
+  }
+  return cached[dev & 63];
+}
+
+}  // namespace dl
+
+extern "C" {
+int dl_abi_version(void) { return DL_ABI_VERSION; }
+const char* dl_last_error(void) { return dl::last_error(); }
+int dl_device_sm_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    dl::set_error("no CUDA device");
+    return -1;
+  }
+  return dl::num_sms();
+}
+}

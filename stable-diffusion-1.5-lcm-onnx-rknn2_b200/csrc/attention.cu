@@ -1,0 +1,335 @@
+// Fused flash-style attention for sm_100a (tcgen05 + TMEM + TMA), SURVEY.md K5/K6.
+// Replaces diffusers' Attention / AttnProcessor2_0 (F.scaled_dot_product_attention) inside
+// BasicTransformerBlock.attn1 (self) and .attn2 (cross, S_kv = 77), reached from reference
+// `backends/cuda_worker.py:222`.
+//
+// One CTA per (128-query tile, head, batch element); 6 warps:
+//   warp 0  TMA producer   Q once, then K_j / V_j tiles (128 keys) through an mbarrier ring
+//   warp 1  MMA issuer     S_j = Q K_j^T  (SS, M=128 N=128 K=d16)   -> TMEM S[j&1]
+//                          O  += P_j V_j  (TS: A = P_j in TMEM, B = V_j MN-major smem)
+//   warps 2-5 softmax      one query row per thread: tcgen05.ld S row, online softmax in fp32
+//                          (exp2, scale*log2e folded), P_j written back to TMEM as packed bf16
+//                          over the S_j columns it was read from, O rescaled in TMEM when the
+//                          running max moved; final O / l -> bf16 global.
+// S is double-buffered so the tensor core computes S_{j+1} while the softmax warps work on
+// S_j.  Head dims that are not a multiple of 16 (SD1.5: 40) are laid out by the QKV projection
+// with a zero-padded per-head stride (dh_stride = 48), so the padded K-steps contribute 0.
+#include "common.cuh"
+#include "dreamlab_b200.h"
+
+namespace dl {
+
+int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                     long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
+                     int skv, int heads, int d, float scale, cudaStream_t stream);
+
+constexpr int AT_THREADS = 192;
+constexpr int AT_TILE = 128;                 // queries per CTA and keys per KV tile
+constexpr int AT_CHUNK_BYTES = AT_TILE * 128;   // one [128 rows x 64 bf16] swizzled block
+
+struct AttnParams {
+  CUtensorMap tmQ, tmK, tmV;
+  __nv_bfloat16* out;
+  long long ldo;
+  int sq, skv, d, d16, nchunk, dh_stride;
+  int stages;
+  float scale_log2;
+};
+
+// TMEM column map (512 columns allocated): S0 [0,128) S1 [128,256) O [256, 256+d16)
+constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int q_bytes = p.nchunk * AT_CHUNK_BYTES;
+  const int kv_bytes = 2 * q_bytes;                       // K tile + V tile
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + q_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * kv_bytes);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // [stages]
+  uint64_t* kv_empty = kv_full + p.stages; // [stages]
+  uint64_t* s_full = kv_empty + p.stages;  // [2]
+  uint64_t* p_ready = s_full + 2;          // [2]
+  uint64_t* pv_done = p_ready + 2;         // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * AT_TILE;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (p.skv + AT_TILE - 1) / AT_TILE;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      const int col0 = h * p.dh_stride;
+      mbar_expect_tx(q_full, (uint32_t)q_bytes);
+      for (int c = 0; c < p.nchunk; ++c)
+        tma_load_2d(sQ + c * AT_CHUNK_BYTES, &p.tmQ, q_full, col0 + c * 64, b * p.sq + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sK = sKV + (size_t)stage * kv_bytes;
+        uint8_t* sV = sK + q_bytes;
+        mbar_expect_tx(&kv_full[stage], (uint32_t)kv_bytes);
+        const int row = b * p.skv + j * AT_TILE;
+        for (int c = 0; c < p.nchunk; ++c) {
+          tma_load_2d(sK + c * AT_CHUNK_BYTES, &p.tmK, &kv_full[stage], col0 + c * 64, row);
+          tma_load_2d(sV + c * AT_CHUNK_BYTES, &p.tmV, &kv_full[stage], col0 + c * 64, row);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);              // Q K^T
+      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.d16, 0, 1);  // P V (B MN-major)
+      const int ksteps = p.d16 / 16;
+      const uint32_t sq_addr = smem_u32(sQ);
+      auto issue_s = [&](int j, int stage) {
+        const uint32_t sk_addr = smem_u32(sKV + (size_t)stage * kv_bytes);
+        const uint32_t d_tmem = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * AT_CHUNK_BYTES + (ks & 3) * 32);
+          umma_ss(d_tmem, umma_desc_kmajor_sw128(sq_addr + off, 1024),
+                  umma_desc_kmajor_sw128(sk_addr + off, 1024), idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+        if (p.stages >= 2 && j + 1 < n_tiles) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(j + 1, nstage);
+        }
+        mbar_wait(&p_ready[j & 1], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        {
+          const uint32_t sv_addr = smem_u32(sKV + (size_t)stage * kv_bytes + q_bytes);
+          const uint32_t p_tmem = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
+          const uint32_t o_tmem = tmem_base + TM_O;
+          for (int ks = 0; ks < AT_TILE / 16; ++ks) {
+            // 16 keys = two 8-row swizzle atoms = 2048 B; P advances 8 packed columns
+            umma_ts(o_tmem, p_tmem + (uint32_t)(ks * 8),
+                    umma_desc_mnmajor_sw128(sv_addr + (uint32_t)(ks * 2048), AT_CHUNK_BYTES, 1024),
+                    idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[stage]);
+          umma_commit(pv_done);
+        }
+        if (p.stages < 2 && j + 1 < n_tiles) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(j + 1, nstage);
+        }
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ============================ softmax + epilogue ============================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t s_tmem = tmem_base + lane_off + ((j & 1) ? TM_S1 : TM_S0);
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const int kbase = j * AT_TILE;
+      // pass 1: row max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(s_tmem + (uint32_t)(c * 32), rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (kbase + c * 32 + i < p.skv) mx = fmaxf(mx, __uint_as_float(rr[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const float corr = fast_exp2(m_run - m_new);
+      l_run *= corr;
+      // pass 2: p = exp2(s*scale - m), write packed bf16 P over the S columns already consumed
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(s_tmem + (uint32_t)(c * 32), rr);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k0 = kbase + c * 32 + 2 * i;
+          float p0 = fast_exp2(__uint_as_float(rr[2 * i]) * p.scale_log2 - m_new);
+          float p1 = fast_exp2(__uint_as_float(rr[2 * i + 1]) * p.scale_log2 - m_new);
+          if (k0 >= p.skv) p0 = 0.f;
+          if (k0 + 1 >= p.skv) p1 = 0.f;
+          // sum what the tensor core will actually multiply (bf16-rounded P)
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          const float2 pf = __bfloat1622float2(pb);
+          lsum += pf.x + pf.y;
+          pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
+        }
+        tmem_st16(s_tmem + (uint32_t)(c * 16), pk);
+      }
+      l_run += lsum;
+      m_run = m_new;
+      tmem_st_wait();
+      if (j > 0) {
+        // O must hold PV_{j-1} before it is rescaled and before PV_j accumulates on top
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, corr != 1.0f)) {
+          const uint32_t o_tmem = tmem_base + lane_off + TM_O;
+#pragma unroll 1
+          for (int c = 0; c < p.d16; c += 16) {
+            uint32_t oo[16];
+            tmem_ld16(o_tmem + (uint32_t)c, oo);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) oo[i] = __float_as_uint(__uint_as_float(oo[i]) * corr);
+            tmem_st16(o_tmem + (uint32_t)c, oo);
+          }
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
+    }
+    // epilogue: O / l
+    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const bool valid = (q0 + r) < p.sq;
+    __nv_bfloat16* orow = p.out + ((long long)b * p.sq + q0 + r) * p.ldo + h * p.d;
+    const uint32_t o_tmem = tmem_base + lane_off + TM_O;
+#pragma unroll 1
+    for (int c = 0; c < p.d16; c += 16) {
+      uint32_t oo[16];
+      tmem_ld16(o_tmem + (uint32_t)c, oo);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (c + hh * 8 + 8 <= p.d) {
+            uint4 ov;
+            ov.x = pack_bf16x2(__uint_as_float(oo[hh * 8 + 0]) * inv_l, __uint_as_float(oo[hh * 8 + 1]) * inv_l);
+            ov.y = pack_bf16x2(__uint_as_float(oo[hh * 8 + 2]) * inv_l, __uint_as_float(oo[hh * 8 + 3]) * inv_l);
+            ov.z = pack_bf16x2(__uint_as_float(oo[hh * 8 + 4]) * inv_l, __uint_as_float(oo[hh * 8 + 5]) * inv_l);
+            ov.w = pack_bf16x2(__uint_as_float(oo[hh * 8 + 6]) * inv_l, __uint_as_float(oo[hh * 8 + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + hh * 8) = ov;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static int attn_tc_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                          long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
+                          int skv, int heads, int d, float scale, cudaStream_t stream) {
+  DL_CHECK_ARG(d % 8 == 0 && d >= 8, "attention: head dim %d must be a multiple of 8", d);
+  const int d16 = (d + 15) / 16 * 16;
+  DL_CHECK_ARG(d16 <= 192, "attention(tc): head dim %d > 192 unsupported (use the GEMM path)", d);
+  DL_CHECK_ARG(dh_stride >= d16 || dh_stride == d,
+               "attention(tc): dh_stride=%d must be >= %d (zero-padded heads) or == d", dh_stride, d16);
+  DL_CHECK_ARG(dh_stride % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
+               "attention(tc): strides must be multiples of 8 elements");
+  if (d != d16) DL_CHECK_ARG(dh_stride >= d16, "attention(tc): d=%d needs zero-padded dh_stride >= %d", d, d16);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.ldo = ldo;
+  p.sq = sq; p.skv = skv; p.d = d; p.d16 = d16; p.dh_stride = dh_stride;
+  p.nchunk = (d16 + 63) / 64;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  const int q_bytes = p.nchunk * AT_CHUNK_BYTES;
+  const int budget = 227 * 1024 - 1024 - 256;
+  p.stages = (budget - q_bytes) / (2 * q_bytes);
+  if (p.stages > 4) p.stages = 4;
+  DL_CHECK_ARG(p.stages >= 1, "attention(tc): head dim %d does not fit shared memory", d);
+  const uint32_t box[2] = {64, AT_TILE};
+  {
+    const uint64_t dims[2] = {(uint64_t)ldq, (uint64_t)batch * sq};
+    const uint64_t str[1] = {(uint64_t)ldq * 2};
+    if (make_tmap_bf16(&p.tmQ, q, 2, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)ldk, (uint64_t)batch * skv};
+    const uint64_t str[1] = {(uint64_t)ldk * 2};
+    if (make_tmap_bf16(&p.tmK, k, 2, dims, str, box)) return 1;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)ldv, (uint64_t)batch * skv};
+    const uint64_t str[1] = {(uint64_t)ldv * 2};
+    if (make_tmap_bf16(&p.tmV, v, 2, dims, str, box)) return 1;
+  }
+  const int smem_bytes = q_bytes + p.stages * 2 * q_bytes + 1024 + 256;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set[dev & 63] = true;
+  }
+  dim3 grid((sq + AT_TILE - 1) / AT_TILE, heads, batch);
+  attn_tc_kernel<<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  return check_launch("attention(tc)");
+}
+
+}  // namespace dl
+
+extern "C" int dl_attention(const void* q, long long ldq, const void* k, long long ldk,
+                            const void* v, long long ldv, int dh_stride, void* out, long long ldo,
+                            int batch, int sq, int skv, int heads, int d, float scale, int impl,
+                            void* stream_) {
+  using namespace dl;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DL_CHECK_ARG(q && k && v && out, "attention: null pointer");
+  DL_CHECK_ARG(batch > 0 && sq > 0 && skv > 0 && heads > 0 && d > 0, "attention: bad dims");
+  if (impl == DL_ATTN_SIMT)
+    return attn_simt_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d,
+                            scale, stream);
+  DL_CHECK_ARG(impl == DL_ATTN_TC, "attention: unknown impl %d", impl);
+  return attn_tc_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d,
+                        scale, stream);
+}

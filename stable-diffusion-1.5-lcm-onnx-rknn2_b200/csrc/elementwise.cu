@@ -1,0 +1,343 @@
+// Bandwidth-/latency-bound pieces of the hot path: timestep embedding,
+// tiny time-MLP GEMMs, nearest-2x upsample, stride-2 im2col, latent packing, the fused LCM
+// scheduler update and the 8x8 latent pool.  All vectorised (16-byte) and coalesced.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "dreamlab_b200.h"
+
+namespace dl {
+
+// ---- Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) ---------------------------------------
+__global__ void sinusoid_kernel(const float* __restrict__ t, int batch, int dim,
+                                float* __restrict__ out) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i % half;
+  // exp(-ln(10000) * k / half) in fp32, then t * f: same op order as the oracle
+  const float f = expf(-9.210340371976184f * (float)k / (float)half);
+  const float a = t[b] * f;
+  out[(size_t)b * dim + k] = cosf(a);
+  out[(size_t)b * dim + half + k] = sinf(a);
+}
+
+// ---- out[m,n] = act_out(sum_k act_in(x[m,k]) w[n,k] + bias[n] + add[m,n]) ; one warp per n ----
+template <int MMAX>
+__global__ void small_linear_kernel(const float* __restrict__ x, int m, int k,
+                                    const __nv_bfloat16* __restrict__ w,
+                                    const float* __restrict__ bias, const float* __restrict__ add,
+                                    int n, int silu_in, int silu_out, float* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  float acc[MMAX];
+#pragma unroll
+  for (int i = 0; i < MMAX; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* wr = w + (size_t)warp * k;
+  for (int kk = lane * 8; kk < k; kk += 256) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + kk));
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+    float wf[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(ww[j]);
+      wf[2 * j] = f.x; wf[2 * j + 1] = f.y;
+    }
+#pragma unroll
+    for (int i = 0; i < MMAX; ++i) {
+      if (i < m) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * k + kk));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * k + kk + 4));
+        float xv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xx = silu_in ? silu_f(xv[j]) : xv[j];
+          acc[i] += xx * wf[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MMAX; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0 && i < m) {
+      float r = s + (bias ? bias[warp] : 0.f) + (add ? add[(size_t)i * n + warp] : 0.f);
+      if (silu_out) r = silu_f(r);
+      out[(size_t)i * n + warp] = r;
+    }
+  }
+}
+
+// ---- nearest 2x upsample, NHWC bf16 ---------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int nimg, int h, int w, int V,
+                                  uint4* __restrict__ out) {
+  const long long total = (long long)nimg * h * w * V;   // one thread per input vector
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    long long p = i / V;
+    const int xx = (int)(p % w);
+    p /= w;
+    const int yy = (int)(p % h);
+    const int n = (int)(p / h);
+    const uint4 val = __ldg(x + i);
+    const long long ow = 2LL * w;
+    const long long base = (((long long)n * 2 * h + 2 * yy) * ow + 2 * xx) * V + v;
+    out[base] = val;
+    out[base + V] = val;
+    out[base + ow * V] = val;
+    out[base + ow * V + V] = val;
+  }
+}
+
+// ---- im2col for conv3x3 stride 2 pad 1 (Downsample2D): cols[(n,yo,xo), tap*c + ch] ----------
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, int nimg, int h, int w, int V,
+                                 uint4* __restrict__ cols) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)nimg * ho * wo * 9 * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    long long r = i / V;
+    const int tap = (int)(r % 9);
+    r /= 9;
+    const int xo = (int)(r % wo);
+    r /= wo;
+    const int yo = (int)(r % ho);
+    const int n = (int)(r / ho);
+    const int yi = 2 * yo + tap / 3 - 1;
+    const int xi = 2 * xo + tap % 3 - 1;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (yi >= 0 && yi < h && xi >= 0 && xi < w)
+      val = __ldg(x + (((long long)n * h + yi) * w + xi) * V + v);
+    cols[i] = val;
+  }
+}
+
+// out[p, c] = bf16( sum_j mat[c][j] * (x[p, j] * scale) + vec[c] ) for c < cin, 0 for the pad
+// (mat == NULL: identity).  The optional cin x cin matrix is the VAE post_quant_conv (1x1).
+__global__ void pack_latent_kernel(const float* __restrict__ x, long long npix, int cin, int cpad,
+                                   float scale, const float* __restrict__ mat,
+                                   const float* __restrict__ vec, __nv_bfloat16* __restrict__ out) {
+  const long long total = npix * cpad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpad);
+    const long long p = i / cpad;
+    float r = 0.f;
+    if (c < cin) {
+      if (mat == nullptr) {
+        r = x[p * cin + c] * scale;
+      } else {
+        r = vec ? vec[c] : 0.f;
+        for (int j = 0; j < cin; ++j) r += mat[c * cin + j] * (x[p * cin + j] * scale);
+      }
+    }
+    out[i] = __float2bfloat16(r);
+  }
+}
+
+// row softmax: fp32 scores [rows, cols] -> bf16 probabilities (VAE mid-block attention, d=512)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, long long rows, int cols,
+                                    __nv_bfloat16* __restrict__ out) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * cols;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, sr[i]);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+    v = warp_max(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  m = red[0];
+  __syncthreads();
+  float l = 0.f;
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) l += __expf(sr[i] - m);
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float inv = 1.f / red[0];
+  for (int i = threadIdx.x; i < cols; i += blockDim.x)
+    out[row * cols + i] = __float2bfloat16(__expf(sr[i] - m) * inv);
+}
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int nimg, int c, int hw,
+                                    float* __restrict__ out) {
+  const long long total = (long long)nimg * c * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    long long r = i / c;
+    const int p = (int)(r % hw);
+    const int n = (int)(r / hw);
+    out[i] = x[((long long)n * c + ch) * hw + p];
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int nimg, int c, int hw,
+                                    float* __restrict__ out) {
+  const long long total = (long long)nimg * c * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % hw);
+    long long r = i / hw;
+    const int ch = (int)(r % c);
+    const int n = (int)(r / c);
+    out[i] = x[((long long)n * hw + p) * c + ch];
+  }
+}
+
+// ---- LCMScheduler.step, fused (fp32 latents; coefficients are the scheduler's fp32 scalars) ---
+__global__ void lcm_step_kernel(const float4* __restrict__ eps, const float4* __restrict__ x,
+                                const float4* __restrict__ noise, float4* __restrict__ x_next,
+                                float4* __restrict__ denoised, long long n4, dl_lcm_coeffs k) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 e = eps[i], xv = x[i];
+    const float ev[4] = {e.x, e.y, e.z, e.w};
+    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+    float zz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise != nullptr) {
+      const float4 z = noise[i];
+      zz[0] = z.x; zz[1] = z.y; zz[2] = z.z; zz[3] = z.w;
+    }
+    float d[4], o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // no FMA contraction: keep the reference's op order (mul, sub, div, mul, mul, add)
+      const float x0 = __fdiv_rn(__fsub_rn(xx[j], __fmul_rn(k.sqrt_beta_t, ev[j])), k.sqrt_alpha_t);
+      d[j] = __fadd_rn(__fmul_rn(k.c_out, x0), __fmul_rn(k.c_skip, xx[j]));
+      o[j] = (noise != nullptr)
+                 ? __fadd_rn(__fmul_rn(k.sqrt_alpha_prev, d[j]), __fmul_rn(k.sqrt_beta_prev, zz[j]))
+                 : d[j];
+    }
+    denoised[i] = make_float4(d[0], d[1], d[2], d[3]);
+    x_next[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---- fp32 adaptive_avg_pool2d -> (8,8) -> fp16, NHWC in, NCHW out -----------------------------
+__global__ void latent_pool8_kernel(const float* __restrict__ lat, int nimg, int h, int w, int c,
+                                    __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nimg * c * 64) return;
+  const int ox = i % 8, oy = (i / 8) % 8, ch = (i / 64) % c, n = i / (64 * c);
+  const int bh = h / 8, bw = w / 8;
+  float s = 0.f;
+  for (int y = 0; y < bh; ++y)
+    for (int x = 0; x < bw; ++x)
+      s += lat[(((long long)n * h + oy * bh + y) * w + ox * bw + x) * c + ch];
+  out[i] = __float2half_rn(s / (float)(bh * bw));
+}
+
+static inline unsigned grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace dl
+
+using namespace dl;
+#define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int dl_timestep_sinusoid(const float* t, int batch, int dim, float* out, void* stream_) {
+  DL_CHECK_ARG(t && out && dim % 2 == 0 && batch > 0, "timestep_sinusoid: bad args");
+  const int total = batch * dim / 2;
+  sinusoid_kernel<<<(total + 127) / 128, 128, 0, STREAM>>>(t, batch, dim, out);
+  return check_launch("timestep_sinusoid");
+}
+
+extern "C" int dl_small_linear(const float* x, int m, int k, const void* w, const float* bias,
+                               const float* add, int n, int silu_in, int silu_out, float* out,
+                               void* stream_) {
+  DL_CHECK_ARG(x && w && out, "small_linear: null pointer");
+  DL_CHECK_ARG(k % 8 == 0, "small_linear: k=%d must be a multiple of 8", k);
+  DL_CHECK_ARG(m >= 1 && m <= 64, "small_linear: m=%d must be in [1,64]", m);
+  const int threads = 256;
+  const int blocks = (n * 32 + threads - 1) / threads;
+  const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(w);
+  for (int m0 = 0; m0 < m; m0 += 16) {
+    const int mm = (m - m0) < 16 ? (m - m0) : 16;
+    small_linear_kernel<16><<<blocks, threads, 0, STREAM>>>(
+        x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
+        silu_out, out + (size_t)m0 * n);
+  }
+  return check_launch("small_linear");
+}
+
+extern "C" int dl_upsample2x(const void* x, int nimg, int h, int w, int c, void* out, void* stream_) {
+  DL_CHECK_ARG(x && out && c % 8 == 0, "upsample2x: bad args");
+  const long long total = (long long)nimg * h * w * (c / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(out));
+  return check_launch("upsample2x");
+}
+
+extern "C" int dl_im2col_s2(const void* x, int nimg, int h, int w, int c, void* cols, void* stream_) {
+  DL_CHECK_ARG(x && cols && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_s2: bad args");
+  const long long total = (long long)nimg * (h / 2) * (w / 2) * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(cols));
+  return check_launch("im2col_s2");
+}
+
+extern "C" int dl_pack_latent(const float* x, long long npix, int cin, int cpad, float scale,
+                              const float* mat, const float* vec, void* out, void* stream_) {
+  DL_CHECK_ARG(x && out && cin <= cpad, "pack_latent: bad args");
+  pack_latent_kernel<<<grid_for(npix * cpad, 256), 256, 0, STREAM>>>(
+      x, npix, cin, cpad, scale, mat, vec, reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("pack_latent");
+}
+
+extern "C" int dl_softmax_rows(const float* scores, long long rows, int cols, void* out,
+                               void* stream_) {
+  DL_CHECK_ARG(scores && out && rows > 0 && cols > 0, "softmax_rows: bad args");
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(scores, rows, cols,
+                                                         reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("softmax_rows");
+}
+
+extern "C" int dl_nchw_to_nhwc_f32(const float* x, int nimg, int c, int hw, float* out, void* stream_) {
+  DL_CHECK_ARG(x && out, "nchw_to_nhwc: null pointer");
+  nchw_to_nhwc_kernel<<<grid_for((long long)nimg * c * hw, 256), 256, 0, STREAM>>>(x, nimg, c, hw, out);
+  return check_launch("nchw_to_nhwc");
+}
+extern "C" int dl_nhwc_to_nchw_f32(const float* x, int nimg, int c, int hw, float* out, void* stream_) {
+  DL_CHECK_ARG(x && out, "nhwc_to_nchw: null pointer");
+  nhwc_to_nchw_kernel<<<grid_for((long long)nimg * c * hw, 256), 256, 0, STREAM>>>(x, nimg, c, hw, out);
+  return check_launch("nhwc_to_nchw");
+}
+
+extern "C" int dl_lcm_step(const float* eps, const float* x, const float* noise, float* x_next,
+                           float* denoised, long long n, const dl_lcm_coeffs* k, void* stream_) {
+  DL_CHECK_ARG(eps && x && x_next && denoised && k, "lcm_step: null pointer");
+  DL_CHECK_ARG(n % 4 == 0, "lcm_step: n must be a multiple of 4");
+  lcm_step_kernel<<<grid_for(n / 4, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(x),
+      reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(x_next),
+      reinterpret_cast<float4*>(denoised), n / 4, *k);
+  return check_launch("lcm_step");
+}
+
+extern "C" int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16,
+                               void* stream_) {
+  DL_CHECK_ARG(lat && out_f16 && h % 8 == 0 && w % 8 == 0, "latent_pool8: h, w must be multiples of 8");
+  const int total = nimg * c * 64;
+  latent_pool8_kernel<<<(total + 127) / 128, 128, 0, STREAM>>>(lat, nimg, h, w, c,
+                                                                reinterpret_cast<__half*>(out_f16));
+  return check_launch("latent_pool8");
+}

@@ -1,0 +1,408 @@
+// Implicit-GEMM convolution / linear kernel for sm_100a (tcgen05 + TMEM + TMA).
+//
+//   out[pixel, n] = epilogue( sum_{tap, c} act[pixel + tap_offset, c] * wgt[n, tap, c] )
+//
+// Covers every dense contraction of the UNet / VAE except attention (SURVEY.md §2.2 K1-K4,
+// K13-K14): conv3x3 s1 p1 (9 taps), conv1x1 / Linear (1 tap), two-source K loop for the
+// skip-concat, fused bias + per-image channel add (time embedding) + residual, GEGLU,
+// u8 image tail.  No reference analogue: the reference delegates these to cuDNN/cuBLAS through
+// diffusers (`backends/cuda_worker.py:222`).
+//
+// Design
+//   * activations NHWC bf16; an M tile is a (tw x th x tn) = 128-pixel patch fetched by ONE 4-D
+//     TMA box per (tap, 64-channel chunk); the conv halo/padding is TMA out-of-bounds zero fill
+//     (tap offsets are just shifted box coordinates, possibly negative) -> no im2col buffer.
+//   * weights [N, taps*C] K-major bf16, one 2-D TMA box (64 x BN) per k-block.
+//   * both land in 128B-swizzled K-major smem tiles = the canonical UMMA operand layout.
+//   * warp-specialised persistent CTA (1 per SM): warp0 TMA producer, warp1 MMA issuer
+//     (single elected thread, tcgen05.mma M=128 x N=BN x K=16), warps 2-5 epilogue
+//     (tcgen05.ld -> registers -> fused epilogue -> global).  Accumulators double-buffered in
+//     TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+//   * BN is a runtime parameter (any multiple of 16 up to 256): UMMA N is encoded in the
+//     runtime instruction descriptor, the box size in the tensor map.
+#include "common.cuh"
+#include "dreamlab_b200.h"
+
+namespace dl {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int IGEMM_THREADS = 192;
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
+
+struct IgemmParams {
+  CUtensorMap tmA0, tmA1, tmB;
+  int tw_log2, th_log2;
+  int tiles_x, tiles_y, tiles_n;
+  int W, H, NIMG;
+  int taps, kc0, kc1;
+  int N, BN, n_tiles, m_tiles;
+  int stages, tmem_cols, acc_bufs;
+  void* out;
+  long long ldo;
+  const float* bias;
+  const float* rowadd;
+  int ld_rowadd;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  int mode;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(IGEMM_THREADS, 1)
+igemm_kernel(const __grid_constant__ IgemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  const int b_tile_bytes = p.BN * BK * 2;
+  const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tfull_bar = bars + 2 * p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int kc = p.kc0 + p.kc1;
+  const int num_kb = p.taps * kc;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmB);
+    if (p.kc1 > 0) tma_prefetch_desc(&p.tmA1);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);     // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_blk = t % p.n_tiles;
+        int m = t / p.n_tiles;
+        const int tx = m % p.tiles_x;
+        m /= p.tiles_x;
+        const int ty = m % p.tiles_y;
+        const int tn = m / p.tiles_y;
+        const int x0 = tx << p.tw_log2;
+        const int y0 = ty << p.th_log2;
+        const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
+        int kb = 0;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
+          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          for (int c = 0; c < kc; ++c, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sb = sa + A_TILE_BYTES;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            if (c < p.kc0)
+              tma_load_4d(sa, &p.tmA0, &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
+            else
+              tma_load_4d(sa, &p.tmA1, &full_bar[stage], (c - p.kc0) * BK, x0 + dx, y0 + dy, n0);
+            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, n_blk * p.BN);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa, 1024);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sb, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+            umma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);            // frees the smem slot when MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);                // accumulator ready for the epilogue
+        if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+        else acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int r = quad * 32 + lane;                  // row of the 128-row tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int tw_mask = (1 << p.tw_log2) - 1;
+    const int th_mask = (1 << p.th_log2) - 1;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_blk = t % p.n_tiles;
+      int m = t / p.n_tiles;
+      const int tx = m % p.tiles_x;
+      m /= p.tiles_x;
+      const int ty = m % p.tiles_y;
+      const int tn = m / p.tiles_y;
+      const int x = (tx << p.tw_log2) + (r & tw_mask);
+      const int y = (ty << p.th_log2) + ((r >> p.tw_log2) & th_mask);
+      const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + (r >> (p.tw_log2 + p.th_log2));
+      const bool valid = (x < p.W) && (y < p.H) && (n < p.NIMG);
+      const long long row = ((long long)n * p.H + y) * p.W + x;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t rr[16];
+        tmem_ld16(t_row + (uint32_t)c, rr);
+        tmem_ld_wait();
+        const int col = n_blk * p.BN + c;
+        if (valid && col < p.N) {
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+        const int ncols = min(16, p.N - col);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) v[j] += __ldg(p.bias + col + j);
+        }
+        if (p.rowadd != nullptr) {
+          const float* ra = p.rowadd + (long long)n * p.ld_rowadd + col;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) v[j] += __ldg(ra + j);
+        }
+        if (p.mode == DL_EPI_BF16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h * 8 + 8 > ncols) break;
+            if (p.residual != nullptr) {
+              const uint4 rv =
+                  __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col + h * 8));
+              const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16x2(ru[j]);
+                v[h * 8 + 2 * j] += f.x;
+                v[h * 8 + 2 * j + 1] += f.y;
+              }
+            }
+            uint4 ov;
+            ov.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]);
+            ov.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
+            ov.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]);
+            ov.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
+            *reinterpret_cast<uint4*>(o + h * 8) = ov;
+          }
+        } else if (p.mode == DL_EPI_GEGLU) {
+          // interleaved columns: even = value, odd = gate  ->  out col = col/2 + j
+          if (ncols == 16) {
+            float g[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
+            uint4 ov;
+            ov.x = pack_bf16x2(g[0], g[1]);
+            ov.y = pack_bf16x2(g[2], g[3]);
+            ov.z = pack_bf16x2(g[4], g[5]);
+            ov.w = pack_bf16x2(g[6], g[7]);
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col >> 1);
+            *reinterpret_cast<uint4*>(o) = ov;
+          }
+        } else if (p.mode == DL_EPI_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) o[j] = v[j];
+        } else if (p.mode == DL_EPI_U8_IMAGE) {
+          // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
+          uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < ncols) {
+              // image is bf16-rounded first (the decoder output dtype), like the reference's
+              // dtype-typed vae output
+              const float xb = __bfloat162float(__float2bfloat16(v[j]));
+              const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
+              o[j] = (uint8_t)__float2int_rn(f);
+            }
+        }
+      }  // valid
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
+      else acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+}
+
+static int ilog2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+static int pick_bn(int N, long long m_tiles, int sms) {
+  static const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+  if (N <= 16) return 16;
+  int smallest_ge64 = 0, smallest = 0;
+  for (int bn : cands) {
+    if (bn > N || N % bn != 0) continue;
+    if (m_tiles * (N / bn) >= sms) return bn;        // largest divisor that still fills the GPU
+    smallest = bn;
+    if (bn >= 64) smallest_ge64 = bn;
+  }
+  if (smallest_ge64) return smallest_ge64;           // cannot fill: most tiles at a sane width
+  if (smallest) return smallest;
+  return (N >= 128) ? 128 : ((N + 15) / 16) * 16;    // no divisor: masked tail tile
+}
+
+// largest power-of-two tile extent <= cap with the least padding of `extent`
+static int pick_extent(int extent, int cap) {
+  int best = 1;
+  long long best_pad = -1;
+  for (int t = cap; t >= 1; t >>= 1) {
+    const long long padded = (long long)((extent + t - 1) / t) * t;
+    if (best_pad < 0 || padded < best_pad) { best_pad = padded; best = t; }
+  }
+  return best;
+}
+
+int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
+  DL_CHECK_ARG(d->a0 && d->wgt && d->out, "igemm: null pointer");
+  DL_CHECK_ARG(d->taps == 1 || d->taps == 9, "igemm: taps must be 1 or 9 (got %d)", d->taps);
+  DL_CHECK_ARG(d->c0 > 0 && d->c0 % BK == 0, "igemm: c0=%d must be a positive multiple of 64", d->c0);
+  DL_CHECK_ARG(d->c1 >= 0 && d->c1 % BK == 0, "igemm: c1=%d must be a multiple of 64", d->c1);
+  DL_CHECK_ARG(d->c1 == 0 || d->a1 != nullptr, "igemm: c1>0 needs a1");
+  DL_CHECK_ARG(d->n > 0 && d->nimg > 0 && d->h > 0 && d->w > 0, "igemm: bad dims");
+  DL_CHECK_ARG(d->mode >= 0 && d->mode <= DL_EPI_U8_IMAGE, "igemm: bad epilogue mode %d", d->mode);
+  if (d->mode == DL_EPI_BF16)
+    DL_CHECK_ARG(d->n % 8 == 0 && d->ldo % 8 == 0, "igemm: bf16 output needs n, ldo multiples of 8");
+  if (d->mode == DL_EPI_GEGLU)
+    DL_CHECK_ARG(d->n % 16 == 0 && d->ldo % 8 == 0, "igemm: GEGLU needs n %% 16 == 0");
+  if (d->residual) DL_CHECK_ARG(d->ldr % 8 == 0, "igemm: residual ld must be a multiple of 8");
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  // ---- M tiling: tw x th x tn = 128 (powers of two; partial tiles are masked) ----
+  const int tw = pick_extent(d->w, 128);
+  const int th = pick_extent(d->h, 128 / tw);
+  const int tn = 128 / (tw * th);
+  p.tw_log2 = ilog2_exact(tw);
+  p.th_log2 = ilog2_exact(th);
+  p.tiles_x = (d->w + tw - 1) / tw;
+  p.tiles_y = (d->h + th - 1) / th;
+  p.tiles_n = (d->nimg + tn - 1) / tn;
+  p.W = d->w; p.H = d->h; p.NIMG = d->nimg;
+  p.taps = d->taps;
+  p.kc0 = d->c0 / BK;
+  p.kc1 = d->c1 / BK;
+  p.N = d->n;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+  const int sms = num_sms();
+  int bn = d->bn > 0 ? d->bn : pick_bn(d->n, p.m_tiles, sms);
+  DL_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "igemm: bn=%d must be a multiple of 16 in [16,256]", bn);
+  if (d->mode == DL_EPI_GEGLU) DL_CHECK_ARG(bn % 16 == 0, "igemm: GEGLU bn");
+  p.BN = bn;
+  p.n_tiles = (d->n + bn - 1) / bn;
+  const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
+  p.stages = SMEM_BUDGET / stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  const int num_kb = p.taps * (p.kc0 + p.kc1);
+  if (p.stages > num_kb && num_kb >= 2) p.stages = num_kb;
+  DL_CHECK_ARG(p.stages >= 2, "igemm: not enough smem for 2 stages");
+  p.acc_bufs = (2 * bn <= 512) ? 2 : 1;
+  int cols = p.acc_bufs * bn;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < cols) p.tmem_cols <<= 1;
+  p.out = d->out; p.ldo = d->ldo;
+  p.bias = d->bias; p.rowadd = d->rowadd; p.ld_rowadd = d->ld_rowadd;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
+  p.mode = d->mode;
+  p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+
+  // ---- tensor maps ----
+  {
+    const uint64_t dims[4] = {(uint64_t)d->c0, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    const uint64_t ps = (uint64_t)d->a0_pix_stride * 2;
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (make_tmap_bf16(&p.tmA0, d->a0, 4, dims, strides, box)) return 1;
+  }
+  if (d->c1 > 0) {
+    const uint64_t dims[4] = {(uint64_t)d->c1, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    const uint64_t ps = (uint64_t)d->a1_pix_stride * 2;
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (make_tmap_bf16(&p.tmA1, d->a1, 4, dims, strides, box)) return 1;
+  }
+  {
+    const uint64_t K = (uint64_t)d->taps * (d->c0 + d->c1);
+    const uint64_t dims[2] = {K, (uint64_t)d->n};
+    const uint64_t strides[1] = {(d->ldw > 0 ? (uint64_t)d->ldw : K) * 2};
+    const uint32_t box[2] = {BK, (uint32_t)bn};
+    if (make_tmap_bf16(&p.tmB, d->wgt, 2, dims, strides, box)) return 1;
+  }
+
+  const int smem_bytes = p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) { set_error("igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
+    attr_set[dev & 63] = true;
+  }
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int grid = num_tiles < sms ? num_tiles : sms;
+  igemm_kernel<<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
+  return check_launch("igemm");
+}
+
+}  // namespace dl
+
+extern "C" int dl_igemm(const dl_igemm_desc* d, void* stream) {
+  return dl::igemm_launch(d, reinterpret_cast<cudaStream_t>(stream));
+}

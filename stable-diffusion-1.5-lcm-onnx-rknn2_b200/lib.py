@@ -1,0 +1,249 @@
+"""ctypes binding of libdreamlab_b200.so (the C-ABI in include/dreamlab_b200.h).
+
+Fails loudly: a missing library or a failing call raises RuntimeError — nothing falls back to
+PyTorch ops or the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdreamlab_b200.so")
+
+EPI_BF16, EPI_GEGLU, EPI_F32, EPI_U8_IMAGE = 0, 1, 2, 3
+ATTN_TC, ATTN_SIMT = 0, 1
+
+EXPORTS = [
+    "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm",
+    "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention",
+    "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
+    "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
+]
+
+
+class IgemmDesc(C.Structure):
+    _fields_ = [
+        ("a0", C.c_void_p), ("a0_pix_stride", C.c_longlong), ("c0", C.c_int),
+        ("a1", C.c_void_p), ("a1_pix_stride", C.c_longlong), ("c1", C.c_int),
+        ("nimg", C.c_int), ("h", C.c_int), ("w", C.c_int), ("taps", C.c_int),
+        ("wgt", C.c_void_p), ("ldw", C.c_longlong), ("n", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int),
+        ("residual", C.c_void_p), ("ldr", C.c_longlong),
+        ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
+    ]
+
+
+class LcmCoeffs(C.Structure):
+    _fields_ = [("sqrt_alpha_t", C.c_float), ("sqrt_beta_t", C.c_float), ("c_skip", C.c_float),
+                ("c_out", C.c_float), ("sqrt_alpha_prev", C.c_float), ("sqrt_beta_prev", C.c_float)]
+
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0      # number of native kernel-launching calls made (bench: gpu_launches)
+
+
+def load() -> C.CDLL:
+    """Load the native library (no build here: `__graft_entry__.build()` / build.py does that)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"dreamlab_b200: native library missing: {LIB_PATH} "
+                    "(run `python -c 'import __graft_entry__ as g; g.build()'`). "
+                    "There is no CPU/PyTorch fallback.")
+            lib = C.CDLL(LIB_PATH)
+            lib.dl_last_error.restype = C.c_char_p
+            lib.dl_groupnorm_workspace_bytes.restype = C.c_size_t
+            lib.dl_groupnorm_workspace_bytes.argtypes = [C.c_int, C.c_int]
+            lib.dl_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+            lib.dl_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_layernorm.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_attention.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                                         C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
+                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_int, C.c_void_p]
+            lib.dl_timestep_sinusoid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            lib.dl_small_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p]
+            lib.dl_upsample2x.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]
+            lib.dl_im2col_s2.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p]
+            lib.dl_pack_latent.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_softmax_rows.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+            lib.dl_nchw_to_nhwc_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p]
+            lib.dl_nhwc_to_nchw_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                                C.c_void_p]
+            lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_latent_pool8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+            _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().dl_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"dreamlab_b200.{what} failed (status {rc}): {msg}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dreamlab_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------
+# thin wrappers: torch tensors in, launches on torch's current stream
+# ------------------------------------------------------------------------------------------------
+def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
+          a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
+          mode=EPI_BF16, alpha=1.0, bn=0):
+    """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
+    nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
+    d = IgemmDesc()
+    c0 = a0.shape[-1] if c0 is None else c0
+    d.a0, d.c0 = a0.data_ptr(), c0
+    d.a0_pix_stride = a0.stride(-2) if a0_stride is None else a0_stride
+    if a1 is not None:
+        c1 = a1.shape[-1] if not c1 else c1
+        d.a1, d.c1 = a1.data_ptr(), c1
+        d.a1_pix_stride = a1.stride(-2) if a1_stride is None else a1_stride
+    d.nimg, d.h, d.w, d.taps = nimg, h, w, taps
+    d.wgt, d.n = wgt.data_ptr(), n
+    d.ldw = wgt.stride(0) if wgt.dim() == 2 and wgt.stride(0) != wgt.shape[1] else 0
+    d.out = out.data_ptr()
+    d.ldo = out.stride(-2) if ldo is None else ldo
+    d.bias = _ptr(bias)
+    d.rowadd = _ptr(rowadd)
+    d.ld_rowadd = rowadd.stride(0) if rowadd is not None else 0
+    d.residual = _ptr(residual)
+    d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
+    d.mode, d.alpha, d.bn = mode, alpha, bn
+    _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
+    _count()
+
+
+def groupnorm_workspace_bytes(nimg, groups=32):
+    return load().dl_groupnorm_workspace_bytes(nimg, groups)
+
+
+def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5, silu=True, x1=None):
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    _check(load().dl_groupnorm(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
+                               gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
+                               workspace.data_ptr(), _stream()), "groupnorm")
+    _count(2)
+
+
+def layernorm(x, out, gamma, beta, eps=1e-5):
+    rows = x.numel() // x.shape[-1]
+    _check(load().dl_layernorm(x.data_ptr(), rows, x.shape[-1], eps, gamma.data_ptr(),
+                               beta.data_ptr(), out.data_ptr(), _stream()), "layernorm")
+    _count()
+
+
+def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ldv, ldo, scale,
+              impl=ATTN_TC):
+    _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
+                               out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
+                               _stream()), "attention")
+    _count()
+
+
+def timestep_sinusoid(t, out):
+    _check(load().dl_timestep_sinusoid(t.data_ptr(), t.numel(), out.shape[-1], out.data_ptr(),
+                                       _stream()), "timestep_sinusoid")
+    _count()
+
+
+def small_linear(x, w, out, bias=None, add=None, silu_in=False, silu_out=False):
+    m, k = x.shape
+    n = w.shape[0]
+    _check(load().dl_small_linear(x.data_ptr(), m, k, w.data_ptr(), _ptr(bias), _ptr(add), n,
+                                  int(silu_in), int(silu_out), out.data_ptr(), _stream()),
+           "small_linear")
+    _count((m + 15) // 16)
+
+
+def upsample2x(x, out, *, nimg, h, w):
+    _check(load().dl_upsample2x(x.data_ptr(), nimg, h, w, x.shape[-1], out.data_ptr(), _stream()),
+           "upsample2x")
+    _count()
+
+
+def im2col_s2(x, cols, *, nimg, h, w):
+    _check(load().dl_im2col_s2(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
+           "im2col_s2")
+    _count()
+
+
+def pack_latent(x, out, *, cin, scale=1.0, mat=None, vec=None):
+    npix = x.numel() // cin
+    _check(load().dl_pack_latent(x.data_ptr(), npix, cin, out.shape[-1], scale, _ptr(mat),
+                                 _ptr(vec), out.data_ptr(), _stream()), "pack_latent")
+    _count()
+
+
+def softmax_rows(scores, out):
+    rows, cols = scores.shape
+    _check(load().dl_softmax_rows(scores.data_ptr(), rows, cols, out.data_ptr(), _stream()),
+           "softmax_rows")
+    _count()
+
+
+def nchw_to_nhwc_f32(x, out):
+    n, c, h, w = x.shape
+    _check(load().dl_nchw_to_nhwc_f32(x.data_ptr(), n, c, h * w, out.data_ptr(), _stream()),
+           "nchw_to_nhwc_f32")
+    _count()
+
+
+def nhwc_to_nchw_f32(x, out):
+    n, c, h, w = out.shape
+    _check(load().dl_nhwc_to_nchw_f32(x.data_ptr(), n, c, h * w, out.data_ptr(), _stream()),
+           "nhwc_to_nchw_f32")
+    _count()
+
+
+def lcm_step(eps, x, noise, x_next, denoised, coeffs):
+    k = LcmCoeffs(*[float(v) for v in coeffs])
+    _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
+                              denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def latent_pool8(lat_nhwc, out_f16):
+    n, h, w, c = lat_nhwc.shape
+    _check(load().dl_latent_pool8(lat_nhwc.data_ptr(), n, h, w, c, out_f16.data_ptr(), _stream()),
+           "latent_pool8")
+    _count()

@@ -1,0 +1,286 @@
+"""Per-kernel parity of the hand-written sm_100a kernels (through the C-ABI) against plain
+PyTorch fp32 references of the same op on the same bf16-rounded inputs."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def L():
+    import dreamlab_b200.lib as lib
+    lib.load()
+    return lib
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------ igemm: linear
+@pytest.mark.parametrize("M,K,N,bn", [
+    (256, 320, 320, 0), (128, 64, 16, 16), (154, 768, 640, 0), (4096, 320, 960, 160),
+    (1000, 1280, 1280, 256), (300, 5120, 1280, 64), (512, 640, 1920, 0), (128, 128, 48, 48),
+    (8192, 320, 2560, 0),
+])
+def test_igemm_linear(M, K, N, bn):
+    lib = L()
+    x = bf(rand(M, K, seed=1))
+    w = bf(rand(N, K, seed=2, scale=K ** -0.5))
+    bias = rand(N, seed=3)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x, w, out, nimg=1, h=1, w=M, taps=1, n=N, bias=bias, bn=bn)
+    ref = x.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    assert e < 1e-2, f"rel err {e}"
+
+
+def test_igemm_linear_epilogues():
+    lib = L()
+    M, K, N = 640, 320, 640
+    x = bf(rand(M, K, seed=1))
+    w = bf(rand(N, K, seed=2, scale=K ** -0.5))
+    bias = rand(N, seed=3)
+    res = bf(rand(M, N, seed=4))
+    # rowadd: 5 "images" of 128 rows each
+    rowadd = rand(5, N, seed=5)
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x.view(5, 1, 128, K), w, out, nimg=5, h=1, w=128, taps=1, n=N, bias=bias,
+              rowadd=rowadd, residual=res, alpha=0.5)
+    ref = 0.5 * (x.float() @ w.float().t()) + bias + rowadd.repeat_interleave(128, 0) + res.float()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    # fp32 output, N = 4 (UNet conv_out shape class)
+    w4 = bf(rand(4, K, seed=6, scale=K ** -0.5))
+    o4 = torch.zeros(M, 4, device=DEV, dtype=torch.float32)
+    lib.igemm(x, w4, o4, nimg=1, h=1, w=M, taps=1, n=4, bias=bias[:4].contiguous(), mode=lib.EPI_F32)
+    ref4 = x.float() @ w4.float().t() + bias[:4]
+    torch.cuda.synchronize()
+    assert rel_err(o4, ref4) < 2e-3
+    # GEGLU: interleaved (value, gate) rows
+    inner = 1280
+    wg = bf(rand(2 * inner, K, seed=7, scale=K ** -0.5))
+    bg = rand(2 * inner, seed=8)
+    wi = torch.stack([wg[:inner], wg[inner:]], 1).reshape(2 * inner, K).contiguous()
+    bi = torch.stack([bg[:inner], bg[inner:]], 1).reshape(-1).contiguous()
+    og = torch.empty(M, inner, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x, wi, og, nimg=1, h=1, w=M, taps=1, n=2 * inner, bias=bi, mode=lib.EPI_GEGLU)
+    proj = x.float() @ wg.float().t() + bg
+    refg = proj[:, :inner] * F.gelu(proj[:, inner:])
+    torch.cuda.synchronize()
+    assert rel_err(og, refg) < 1e-2
+
+
+# ------------------------------------------------------------------ igemm: conv3x3
+@pytest.mark.parametrize("B,H,W,C0,C1,N", [
+    (2, 16, 16, 64, 0, 64), (1, 64, 64, 320, 0, 320), (3, 8, 8, 1280, 1280, 1280),
+    (2, 32, 32, 640, 320, 640), (1, 24, 24, 128, 0, 128), (1, 96, 96, 64, 0, 128),
+    (1, 128, 128, 256, 0, 128), (2, 12, 12, 64, 0, 64),
+])
+def test_igemm_conv3x3(B, H, W, C0, C1, N):
+    lib = L()
+    C = C0 + C1
+    x0 = bf(rand(B, H, W, C0, seed=1))
+    x1 = bf(rand(B, H, W, C1, seed=2)) if C1 else None
+    wt = bf(rand(N, C, 3, 3, seed=3, scale=(9 * C) ** -0.5))          # torch OIHW
+    bias = rand(N, seed=4)
+    w_pack = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()    # [N, tap, C]
+    out = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x0, w_pack, out, nimg=B, h=H, w=W, taps=9, n=N, a1=x1, bias=bias)
+    xin = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    assert e < 1e-2, f"rel err {e}"
+
+
+def test_igemm_u8_image_tail():
+    lib = L()
+    B, H, W, C = 1, 64, 64, 128
+    x = bf(rand(B, H, W, C, seed=1))
+    wt = bf(rand(3, C, 3, 3, seed=2, scale=3 * (9 * C) ** -0.5))
+    bias = rand(3, seed=3, scale=0.1)
+    w_pack = wt.permute(0, 2, 3, 1).reshape(3, 9 * C).contiguous()
+    out = torch.zeros(B, H, W, 3, device=DEV, dtype=torch.uint8)
+    lib.igemm(x, w_pack, out, nimg=B, h=H, w=W, taps=9, n=3, bias=bias, mode=lib.EPI_U8_IMAGE, ldo=3)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = ((ref.bfloat16().float() / 2 + 0.5).clamp(0, 1) * 255).round()
+    torch.cuda.synchronize()
+    diff = (out.float() - ref).abs()
+    assert diff.max().item() <= 2 and (diff > 0).float().mean().item() < 0.05
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,HW,C0,C1,silu", [
+    (2, 4096, 320, 0, True), (2, 1024, 640, 320, True), (3, 64, 1280, 1280, True),
+    (1, 65536, 128, 0, True), (2, 256, 1280, 640, False), (1, 4096, 512, 0, False),
+    (2, 300, 256, 0, True),
+])
+def test_groupnorm(B, HW, C0, C1, silu):
+    lib = L()
+    C = C0 + C1
+    x0 = bf(rand(B, HW, C0, seed=1) * 2 + 0.5)
+    x1 = bf(rand(B, HW, C1, seed=2) - 1.0) if C1 else None
+    gamma, beta = rand(C, seed=3) * 0.2 + 1, rand(C, seed=4) * 0.2
+    out = torch.empty(B, HW, C, device=DEV, dtype=torch.bfloat16)
+    ws = torch.empty(lib.groupnorm_workspace_bytes(B), device=DEV, dtype=torch.uint8)
+    lib.groupnorm(x0, out, gamma, beta, ws, nimg=B, hw=HW, eps=1e-5, silu=silu, x1=x1)
+    xin = x0 if x1 is None else torch.cat([x0, x1], -1)
+    ref = F.group_norm(xin.float().transpose(1, 2), 32, gamma, beta, 1e-5).transpose(1, 2)
+    if silu:
+        ref = F.silu(ref)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (77, 1280), (5, 64)])
+def test_layernorm(rows, C):
+    lib = L()
+    x = bf(rand(rows, C, seed=1) * 3 + 1)
+    gamma, beta = rand(C, seed=2) * 0.2 + 1, rand(C, seed=3) * 0.2
+    out = torch.empty_like(x)
+    lib.layernorm(x, out, gamma, beta, 1e-5)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() < 3e-2
+
+
+# ------------------------------------------------------------------ attention
+def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0):
+    d16 = (d + 15) // 16 * 16
+    hs = d16                       # zero-padded per-head stride
+    q = torch.zeros(B * Sq, heads * hs, device=DEV, dtype=torch.bfloat16)
+    k = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
+    v = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
+    qr, kr, vr = (bf(rand(B, n, heads, d, seed=seed + i)) for i, n in enumerate((Sq, Skv, Skv)))
+    q.view(B, Sq, heads, hs)[..., :d] = qr
+    k.view(B, Skv, heads, hs)[..., :d] = kr
+    v.view(B, Skv, heads, hs)[..., :d] = vr
+    out = torch.zeros(B * Sq, heads * d, device=DEV, dtype=torch.bfloat16)
+    lib.attention(q, k, v, out, batch=B, sq=Sq, skv=Skv, heads=heads, d=d, dh_stride=hs,
+                  ldq=heads * hs, ldk=heads * hs, ldv=heads * hs, ldo=heads * d,
+                  scale=1 / math.sqrt(d), impl=impl)
+    ref = F.scaled_dot_product_attention(qr.float().transpose(1, 2), kr.float().transpose(1, 2),
+                                         vr.float().transpose(1, 2)).transpose(1, 2)
+    torch.cuda.synchronize()
+    return rel_err(out.view(B, Sq, heads, d), ref)
+
+
+@pytest.mark.parametrize("B,Sq,Skv,heads,d", [
+    (1, 256, 256, 8, 160), (2, 64, 77, 8, 160), (1, 1024, 1024, 2, 80), (1, 300, 77, 8, 40),
+    (1, 1024, 1024, 4, 40),
+])
+def test_attention_simt(B, Sq, Skv, heads, d):
+    assert _attn_case(L(), B, Sq, Skv, heads, d, 1) < 2e-2
+
+
+@pytest.mark.parametrize("B,Sq,Skv,heads,d", [
+    (1, 128, 128, 1, 64), (1, 256, 256, 2, 64), (1, 128, 128, 1, 40), (1, 4096, 4096, 2, 40),
+    (2, 1024, 1024, 8, 80), (2, 256, 256, 8, 160), (2, 64, 64, 8, 160), (2, 1024, 77, 8, 80),
+    (1, 4096, 77, 8, 40), (3, 64, 77, 8, 160), (1, 2304, 2304, 2, 80), (1, 576, 576, 2, 160),
+])
+def test_attention_tc(B, Sq, Skv, heads, d):
+    e = _attn_case(L(), B, Sq, Skv, heads, d, 0)
+    assert e < 2e-2, f"rel err {e}"
+
+
+# ------------------------------------------------------------------ elementwise / scheduler
+def test_upsample_im2col_pack():
+    lib = L()
+    B, H, W, C = 2, 8, 16, 64
+    x = bf(rand(B, H, W, C, seed=1))
+    up = torch.empty(B, 2 * H, 2 * W, C, device=DEV, dtype=torch.bfloat16)
+    lib.upsample2x(x, up, nimg=B, h=H, w=W)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(up.float(), ref)
+    cols = torch.empty(B * (H // 2) * (W // 2), 9 * C, device=DEV, dtype=torch.bfloat16)
+    lib.im2col_s2(x, cols, nimg=B, h=H, w=W)
+    un = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)       # [B, C*9, L]
+    un = un.view(B, C, 9, -1).permute(0, 3, 2, 1).reshape(-1, 9 * C)
+    torch.cuda.synchronize()
+    assert torch.equal(cols.float(), un)
+    lat = rand(B, 8, 8, 4, seed=2)
+    packed = torch.empty(B, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
+    lib.pack_latent(lat, packed, cin=4, scale=2.0)
+    torch.cuda.synchronize()
+    assert torch.equal(packed[..., :4], (lat * 2.0).bfloat16()) and packed[..., 4:].abs().sum() == 0
+    a = rand(B, 4, 8, 8, seed=3)
+    o = torch.empty(B, 8, 8, 4, device=DEV)
+    lib.nchw_to_nhwc_f32(a, o)
+    back = torch.empty_like(a)
+    lib.nhwc_to_nchw_f32(o, back)
+    torch.cuda.synchronize()
+    assert torch.equal(o, a.permute(0, 2, 3, 1).contiguous()) and torch.equal(back, a)
+
+
+def test_lcm_step_bit_exact_vs_oracle():
+    """Scheduler update is bit-exact against the oracle's fp32 arithmetic."""
+    lib = L()
+    from oracle.scheduler import OracleLCMScheduler
+    from dreamlab_b200.scheduler import LCMSchedule
+    for n in (1, 2, 4, 8):
+        osch = OracleLCMScheduler()
+        ts = osch.set_timesteps(n)
+        sch = LCMSchedule(n)
+        assert sch.timesteps == ts.tolist()
+        x = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(5))
+        for i, t in enumerate(ts):
+            eps = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(10 + i))
+            z = torch.randn(2, 4, 64, 64, generator=torch.Generator().manual_seed(20 + i)) if i < n - 1 else None
+            ref_prev, ref_den = osch.step(eps, int(t), x, noise=z)
+            xn = torch.empty(2, 4, 64, 64, device=DEV)
+            dn = torch.empty_like(xn)
+            lib.lcm_step(eps.to(DEV), x.to(DEV), None if z is None else z.to(DEV), xn, dn, sch.coeffs(i))
+            torch.cuda.synchronize()
+            assert torch.equal(xn.cpu(), ref_prev), f"prev_sample mismatch n={n} i={i}"
+            assert torch.equal(dn.cpu(), ref_den), f"denoised mismatch n={n} i={i}"
+            x = ref_prev
+
+
+def test_time_embedding_pieces():
+    lib = L()
+    from oracle.unet import timestep_embedding
+    t = torch.tensor([999.0, 759.0, 499.0, 259.0], device=DEV)
+    out = torch.empty(4, 320, device=DEV)
+    lib.timestep_sinusoid(t, out)
+    ref = timestep_embedding(t.cpu(), 320)
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max().item() < 2e-3      # sin/cos of ~1e3 rad in fp32
+    x = rand(20, 320, seed=1)
+    w = bf(rand(1280, 320, seed=2, scale=320 ** -0.5))
+    b = rand(1280, seed=3)
+    add = rand(20, 1280, seed=4)
+    o = torch.empty(20, 1280, device=DEV)
+    lib.small_linear(x, w, o, bias=b, add=add, silu_in=True, silu_out=True)
+    ref = F.silu(F.silu(x) @ w.float().t() + b + add)
+    torch.cuda.synchronize()
+    assert (o - ref).abs().max().item() < 1e-3
+
+
+def test_latent_pool8():
+    lib = L()
+    from oracle.pipeline import pooled_latent_bytes
+    lat = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(3))
+    nhwc = lat.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.empty(1, 4, 8, 8, device=DEV, dtype=torch.float16)
+    lib.latent_pool8(nhwc, out)
+    torch.cuda.synchronize()
+    ref = torch.frombuffer(bytearray(pooled_latent_bytes(lat)), dtype=torch.float16).view(1, 4, 8, 8)
+    assert (out.cpu().float() - ref.float()).abs().max().item() < 1e-3
+    assert len(out.cpu().numpy().tobytes()) == 512
