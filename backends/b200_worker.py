@@ -1,0 +1,231 @@
+"""`b200` worker: the reference's `PipelineWorker` contract on the B200-native hot path.
+
+Drop-in replacement for `DiffusersCudaWorker` (reference `backends/cuda_worker.py:20-304`):
+same constructor (`B200Worker(worker_id)`), same env (`MODEL_ROOT`, `MODEL`, `CUDA_DEVICE`,
+`CUDA_DTYPE`), same attributes (`worker_id`, `pipe`, `device`, `dtype`), same results
+(`run_job -> (png, seed)`, `run_job_with_latents -> (png, seed, 512 B fp16 [1,4,8,8])`), same
+errors (`RuntimeError("Invalid size '…', expected 'WIDTHxHEIGHT'")`, missing env ->
+RuntimeError).  What changes is everything below `self.pipe(...)`: the LCM loop, UNet, scheduler
+step and VAE decode run in `dreamlab_b200` (hand-written sm_100a kernels, no diffusers).
+
+Extras the reference does not have: `run_batch(jobs)` generates many
+requests of the same geometry in ONE batched pass (per-request Philox streams preserved) and
+`run_job_with_latents` returns the latent of the same pass instead of re-running the pipeline.
+"""
+from __future__ import annotations
+
+import io
+import json
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from .base import PipelineWorker
+
+
+def parse_size(size) -> Tuple[int, int]:
+    try:
+        w_str, h_str = str(size).lower().split("x")
+        return int(w_str), int(h_str)
+    except Exception:
+        raise RuntimeError(f"Invalid size '{size}', expected 'WIDTHxHEIGHT'")
+
+
+def _device_for(worker_id: int) -> str:
+    """One worker per GPU: worker k -> cuda:k, unless CUDA_DEVICE pins worker 0."""
+    env = (os.environ.get("CUDA_DEVICE") or "").strip()
+    if env and worker_id == 0:
+        return env
+    n = torch.cuda.device_count()
+    return f"cuda:{worker_id % max(n, 1)}"
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _load_component(path: str):
+    """diffusers-layout component dir -> (config dict, state dict)."""
+    from safetensors.torch import load_file
+    with open(os.path.join(path, "config.json")) as f:
+        cfg = json.load(f)
+    for name in ("diffusion_pytorch_model.safetensors", "model.safetensors"):
+        p = os.path.join(path, name)
+        if os.path.exists(p):
+            return cfg, load_file(p)
+    raise RuntimeError(f"no safetensors weights under {path}")
+
+
+def unet_cfg_from_json(c: dict):
+    from types import SimpleNamespace
+    down = c.get("down_block_types", ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"])
+    heads = c.get("attention_head_dim", 8)
+    if isinstance(heads, (list, tuple)):
+        if len(set(heads)) != 1:
+            raise RuntimeError("b200 worker: per-level attention_head_dim (SDXL) is not supported yet")
+        heads = heads[0]
+    if c.get("use_linear_projection", False) or c.get("addition_embed_type"):
+        raise RuntimeError("b200 worker: SDXL-class UNet configs are not supported yet")
+    return SimpleNamespace(
+        in_channels=c.get("in_channels", 4), out_channels=c.get("out_channels", 4),
+        block_out_channels=tuple(c.get("block_out_channels", (320, 640, 1280, 1280))),
+        down_attn=tuple("CrossAttn" in t for t in down),
+        layers_per_block=c.get("layers_per_block", 2),
+        cross_attention_dim=c.get("cross_attention_dim", 768),
+        attention_head_dim=heads, norm_num_groups=c.get("norm_num_groups", 32),
+        norm_eps=c.get("norm_eps", 1e-5), time_cond_proj_dim=c.get("time_cond_proj_dim"))
+
+
+def vae_cfg_from_json(c: dict):
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        latent_channels=c.get("latent_channels", 4), out_channels=c.get("out_channels", 3),
+        block_out_channels=tuple(c.get("block_out_channels", (128, 256, 512, 512))),
+        layers_per_block=c.get("layers_per_block", 2), norm_num_groups=c.get("norm_num_groups", 32),
+        scaling_factor=c.get("scaling_factor", 0.18215), sample_size=c.get("sample_size", 512))
+
+
+class B200Worker(PipelineWorker):
+    def __init__(self, worker_id: int):
+        self.worker_id = worker_id
+        model_root = (os.environ.get("MODEL_ROOT") or "").strip()
+        model_name = (os.environ.get("MODEL") or "").strip()
+        if not model_root:
+            raise RuntimeError("MODEL_ROOT is required for BACKEND=cuda")
+        if not model_name:
+            raise RuntimeError("MODEL is required for BACKEND=cuda")
+        path = os.path.join(model_root, model_name)
+        if not (os.path.isdir(path) and os.path.exists(os.path.join(path, "model_index.json"))):
+            raise RuntimeError(f"b200 worker needs a diffusers-layout model directory, got: {path}")
+        if not torch.cuda.is_available():
+            raise RuntimeError("b200 worker needs a CUDA device (sm_100a); there is no CPU fallback")
+
+        from dreamlab_b200.engine import LCMPipelineB200
+        from dreamlab_b200 import lib
+        lib.load()
+
+        self.device = _device_for(worker_id)
+        # CUDA_DTYPE keeps its meaning for the *noise stream*: the reference draws latents and
+        # step noise in this dtype (fp16 default, `backends/cuda_worker.py:55-61`).  The kernels
+        # themselves compute in bf16 (fp32 accumulate) regardless.
+        dtype_str = os.environ.get("CUDA_DTYPE", "fp16").lower().strip()
+        self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}.get(dtype_str, torch.float16)
+        torch.cuda.set_device(self.device)
+
+        ucfg_json, unet_sd = _load_component(os.path.join(path, "unet"))
+        vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
+        self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
+                                    vae_cfg_from_json(vcfg_json), self.device)
+        self._text = _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
+        print(f"[b200] worker {worker_id} loaded: {model_name} on {self.device} "
+              f"(noise dtype={dtype_str}, compute bf16)")
+
+    # ------------------------------------------------------------------ jobs
+    def _parse(self, req):
+        width, height = parse_size(req.size)
+        if width % 8 or height % 8 or width <= 0 or height <= 0:
+            raise RuntimeError(f"Invalid size '{req.size}', expected 'WIDTHxHEIGHT'")
+        seed = int(req.seed) if getattr(req, "seed", None) is not None else \
+            int(torch.randint(0, 100_000_000, (1,)).item())
+        return width, height, seed
+
+    def _draw(self, seed: int, h8: int, w8: int, steps: int):
+        """The reference's per-request Philox stream (`backends/cuda_worker.py:212-213`,
+        SURVEY.md App. A.5): latents first, then one draw per non-final step."""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(seed)
+        shape = (1, 4, h8, w8)
+        lat = torch.randn(shape, generator=gen, device=self.device, dtype=torch.float32)
+        noise = [torch.randn(shape, generator=gen, device=self.device, dtype=torch.float32)
+                 for _ in range(steps - 1)]
+        lat = lat.to(self.dtype).float()
+        noise = [z.to(self.dtype).float() for z in noise]
+        return lat, noise
+
+    @torch.no_grad()
+    def run_batch(self, jobs: Sequence, with_latents: bool = False) -> List[tuple]:
+        """All jobs must share size / steps; guidance may differ per job."""
+        with torch.cuda.device(self.device):
+            parsed = [self._parse(j.req) for j in jobs]
+            width, height = parsed[0][0], parsed[0][1]
+            steps = int(jobs[0].req.num_inference_steps)
+            for (w, h, _), j in zip(parsed, jobs):
+                if (w, h) != (width, height) or int(j.req.num_inference_steps) != steps:
+                    raise RuntimeError("run_batch: jobs must share size and num_inference_steps")
+            draws = [self._draw(seed, height // 8, width // 8, steps) for _, _, seed in parsed]
+            lat = torch.cat([d[0] for d in draws], 0)
+            noise = (torch.stack([torch.cat([d[1][i] for d in draws], 0) for i in range(steps - 1)])
+                     if steps > 1 else None)
+            pe = self._text.encode([str(j.req.prompt) for j in jobs])
+            gs = torch.tensor([float(j.req.guidance_scale) for j in jobs])
+            img, final = self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True)
+            pooled = None
+            if with_latents:
+                from dreamlab_b200 import lib
+                pooled = torch.empty(len(jobs), 4, 8, 8, device=self.device, dtype=torch.float16)
+                lib.latent_pool8(final, pooled)
+                pooled = pooled.cpu().numpy()
+            img = img.cpu().numpy()
+        out = []
+        for i, (_, _, seed) in enumerate(parsed):
+            png = _encode_png(img[i])
+            out.append((png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed))
+        return out
+
+    def run_job(self, job) -> Tuple[bytes, int]:
+        return self.run_batch([job])[0]
+
+    def run_job_with_latents(self, job) -> Tuple[bytes, int, bytes]:
+        return self.run_batch([job], with_latents=True)[0]
+
+
+def _encode_png(arr) -> bytes:
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(arr).save(buf, format="PNG")
+    return buf.getvalue()
+
+
+class _TextEncoder:
+    """Prompt -> [B,77,D] embeddings.  The step *before* the hot path:
+    the stock `transformers` CLIP text tower is used as a library.  When the model directory
+    ships no tokenizer files (offline fixtures), token ids come from a deterministic hash of
+    the prompt bytes — good for synthetic load, meaningless for real prompts."""
+
+    def __init__(self, model_dir: str, device: str, dim: int):
+        self.device, self.dim = device, dim
+        self.model = None
+        self.tokenizer = None
+        te = os.path.join(model_dir, "text_encoder")
+        if os.path.exists(os.path.join(te, "config.json")):
+            from transformers import CLIPTextModel
+            self.model = CLIPTextModel.from_pretrained(te, torch_dtype=torch.float16).to(device).eval()
+            tk = os.path.join(model_dir, "tokenizer")
+            if os.path.exists(os.path.join(tk, "vocab.json")):
+                from transformers import CLIPTokenizer
+                self.tokenizer = CLIPTokenizer.from_pretrained(tk)
+
+    def _hash_tokens(self, prompts: List[str]) -> torch.Tensor:
+        ids = torch.full((len(prompts), 77), 49407, dtype=torch.long)
+        for i, p in enumerate(prompts):
+            ids[i, 0] = 49406
+            for j, b in enumerate(p.encode("utf-8")[:75]):
+                ids[i, 1 + j] = (b * 193 + j * 7919) % 49406
+        return ids
+
+    @torch.no_grad()
+    def encode(self, prompts: List[str]) -> torch.Tensor:
+        if self.model is None:
+            # no text tower in the model dir: seeded N(0,1) embeddings keyed by the prompt
+            out = []
+            for p in prompts:
+                g = torch.Generator().manual_seed(int.from_bytes(p.encode("utf-8")[:7] or b"\0", "little"))
+                out.append(torch.randn(1, 77, self.dim, generator=g))
+            return torch.cat(out, 0).to(self.device)
+        if self.tokenizer is not None:
+            ids = self.tokenizer(prompts, padding="max_length", max_length=77, truncation=True,
+                                 return_tensors="pt").input_ids
+        else:
+            ids = self._hash_tokens(prompts)
+        return self.model(ids.to(self.device))[0].float()

@@ -1,0 +1,346 @@
+"""Worker pool — one worker per GPU, shared FIFO, request micro-batching.
+
+Public API identical to the reference's (`backends/worker_pool.py:147-181, 343-485`):
+`WorkerPool(queue_max, worker_factory, mode_config, registry)`, `submit_job(job) -> Future`
+(raises `queue.Full`), `switch_mode(name) -> Future` (raises `KeyError` for unknown modes),
+`get_current_mode()`, `get_queue_size()`, `shutdown()`, module-level `get_worker_pool(...)` /
+`reset_worker_pool()`, and the job classes `Job / GenerationJob / ModeSwitchJob / CustomJob /
+JobType`.  `server/lcm_sr_server.py` and `server/model_routes.py` use it unchanged.
+
+What is new (the reference runs ONE worker and ONE job at a time, `worker_pool.py:140,228,328`):
+  * N workers, worker k pinned to GPU k, each driven by its own thread pulling from the one
+    FIFO — independent images shard across GPUs with no collective;
+  * a worker that exposes `run_batch(jobs)` gets up to `B200_MAX_BATCH` queued generation jobs
+    of the same geometry in one call (B200 needs batch >= 16 to approach its roofline);
+  * a mode switch is a barrier: it waits for in-flight jobs, recreates every worker, and
+    later jobs see the new mode (same FIFO semantics as the reference's single thread).
+
+N comes from the ctor (`num_workers`), else `B200_NUM_WORKERS`, else the number of visible
+CUDA devices (1 when that is not a positive integer, e.g. under mocked torch).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import queue
+import threading
+from abc import ABC, abstractmethod
+from concurrent.futures import Future
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Any, Callable, List, Optional
+
+import torch
+
+logger = logging.getLogger(__name__)
+
+
+class JobType(Enum):
+    GENERATION = "generation"
+    MODE_SWITCH = "mode_switch"
+    MODEL_LOAD = "model_load"
+    MODEL_UNLOAD = "model_unload"
+    CUSTOM = "custom"
+
+
+@dataclass
+class Job(ABC):
+    """Base of everything that travels through the queue; subclass to add job kinds."""
+    job_type: JobType = field(init=False)
+    fut: Future = field(init=False, default=None)
+
+    def __post_init__(self):
+        if self.fut is None:
+            self.fut = Future()
+
+    @abstractmethod
+    def execute(self, worker) -> Any:
+        ...
+
+
+@dataclass
+class GenerationJob(Job):
+    req: Any
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.job_type = JobType.GENERATION
+
+    def execute(self, worker) -> Any:
+        if worker is None:
+            raise RuntimeError("No worker available for generation")
+        return worker.run_job(self)
+
+
+@dataclass
+class ModeSwitchJob(Job):
+    target_mode: str
+    on_complete: Optional[Callable] = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.job_type = JobType.MODE_SWITCH
+
+    def execute(self, worker) -> Any:
+        if self.on_complete:
+            self.on_complete(self.target_mode)
+        return {"mode": self.target_mode, "status": "switched"}
+
+
+@dataclass
+class CustomJob(Job):
+    handler: Callable
+    args: tuple = ()
+    kwargs: dict = None
+
+    def __post_init__(self):
+        super().__post_init__()
+        self.job_type = JobType.CUSTOM
+        if self.kwargs is None:
+            self.kwargs = {}
+
+    def execute(self, worker) -> Any:
+        return self.handler(*self.args, **self.kwargs)
+
+
+def _auto_num_workers() -> int:
+    env = os.environ.get("B200_NUM_WORKERS", "").strip()
+    if env:
+        return max(1, int(env))
+    try:
+        n = torch.cuda.device_count()
+    except Exception:
+        return 1
+    return n if isinstance(n, int) and n > 0 else 1
+
+
+def _batch_key(job):
+    """Generation jobs that may share one batched pass: same size and step count."""
+    req = getattr(job, "req", None)
+    try:
+        return (str(req.size).lower(), int(req.num_inference_steps))
+    except Exception:
+        return None
+
+
+class WorkerPool:
+    def __init__(self, queue_max: int = 64, worker_factory=None, mode_config=None, registry=None,
+                 num_workers: Optional[int] = None, max_batch: Optional[int] = None):
+        self.queue_max = queue_max
+        self.q: "queue.Queue[Job]" = queue.Queue(maxsize=queue_max)
+        self._stop = threading.Event()
+        self._workers: List[Any] = []
+        self._worker_threads: List[threading.Thread] = []
+        self._current_mode: Optional[str] = None
+        self._lock = threading.Lock()
+        # gate: generation jobs hold a share, a mode switch needs it exclusively
+        self._gate = threading.Condition()
+        self._active = 0
+        self._switching = False
+        self.num_workers = num_workers if num_workers else _auto_num_workers()
+        self.max_batch = max_batch if max_batch else int(os.environ.get("B200_MAX_BATCH", "16"))
+
+        self._worker_factory = worker_factory or self._default_worker_factory
+        if mode_config is None:
+            from server.mode_config import get_mode_config
+            mode_config = get_mode_config()
+        if registry is None:
+            from backends.model_registry import get_model_registry
+            registry = get_model_registry()
+        self._mode_config = mode_config
+        self._registry = registry
+        self._load_mode(self._mode_config.get_default_mode())
+
+    # reference-compatible single-worker views
+    @property
+    def _worker(self):
+        return self._workers[0] if self._workers else None
+
+    @property
+    def _worker_thread(self):
+        return self._worker_threads[0] if self._worker_threads else None
+
+    @staticmethod
+    def _default_worker_factory(worker_id: int):
+        from backends.worker_factory import create_cuda_worker
+        return create_cuda_worker(worker_id)
+
+    # ------------------------------------------------------------------ lifecycle
+    def _load_mode(self, mode_name: str):
+        mode = self._mode_config.get_mode(mode_name)
+        if self._workers:
+            self._unload_current_worker()
+        # the workers read the model location from the environment (reference contract)
+        os.environ["MODEL_ROOT"] = self._mode_config.config.model_root
+        os.environ["MODEL"] = mode.model
+        vram_before = self._registry.get_used_vram()
+        self._workers = [self._worker_factory(worker_id=k) for k in range(self.num_workers)]
+        vram_used = self._registry.get_used_vram() - vram_before
+        self._registry.register_model(
+            name=mode_name, model_path=mode.model_path, vram_bytes=vram_used, worker_id=0,
+            loras=[lora.path for lora in mode.loras])
+        self._current_mode = mode_name
+        self._start_worker_threads()
+        logger.info("[WorkerPool] mode '%s' loaded on %d worker(s)", mode_name, len(self._workers))
+
+    def _unload_current_worker(self):
+        if not self._workers:
+            return
+        if self._current_mode:
+            self._registry.unregister_model(self._current_mode)
+        self._workers = []
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+
+    def _start_worker_threads(self):
+        alive = [t for t in self._worker_threads if t.is_alive()]
+        self._worker_threads = alive
+        for k in range(len(alive), self.num_workers):
+            t = threading.Thread(target=self._worker_loop, args=(k,), daemon=True,
+                                 name="WorkerThread" if k == 0 else f"WorkerThread-{k}")
+            self._worker_threads.append(t)
+            t.start()
+
+    # ------------------------------------------------------------------ worker threads
+    def _take_batch(self, first: Job, worker) -> List[Job]:
+        """Pull more queued generation jobs compatible with `first` (never blocks)."""
+        batch = [first]
+        if not (isinstance(first, GenerationJob) and hasattr(worker, "run_batch")
+                and not isinstance(getattr(worker, "run_batch"), type(None))):
+            return batch
+        key = _batch_key(first)
+        if key is None or self.max_batch <= 1:
+            return batch
+        with self.q.mutex:                      # peek under the queue's own lock: FIFO prefix only
+            while len(batch) < self.max_batch and self.q.queue:
+                nxt = self.q.queue[0]
+                if isinstance(nxt, GenerationJob) and type(nxt) is type(first) and _batch_key(nxt) == key:
+                    batch.append(self.q.queue.popleft())
+                    self.q.not_full.notify()
+                else:
+                    break
+        return batch
+
+    def _run_generation(self, k: int, job: Job):
+        with self._gate:
+            while self._switching:
+                self._gate.wait()
+            self._active += 1
+            worker = self._workers[k] if k < len(self._workers) else None
+        batch = [job]
+        try:
+            if worker is not None and type(job) is GenerationJob and _is_real_batcher(worker):
+                batch = self._take_batch(job, worker)
+            if len(batch) > 1:
+                results = worker.run_batch(batch)
+                for j, r in zip(batch, results):
+                    if not j.fut.done():
+                        j.fut.set_result(r)
+            else:
+                result = job.execute(worker)
+                if not job.fut.done():
+                    job.fut.set_result(result)
+        except Exception as e:
+            logger.error("[WorkerPool] Job failed: %s", e, exc_info=True)
+            for j in batch:
+                if not j.fut.done():
+                    j.fut.set_exception(e)
+        finally:
+            for _ in batch:
+                self.q.task_done()
+            with self._gate:
+                self._active -= 1
+                self._gate.notify_all()
+
+    def _run_mode_switch(self, job: ModeSwitchJob):
+        with self._gate:
+            while self._switching:
+                self._gate.wait()
+            self._switching = True
+            while self._active > 0:
+                self._gate.wait()
+        try:
+            if self._current_mode == job.target_mode:
+                result = {"mode": job.target_mode, "status": "already_loaded"}
+            else:
+                result = job.execute(self._worker)
+                self._load_mode(job.target_mode)
+            if not job.fut.done():
+                job.fut.set_result(result)
+        except Exception as e:
+            logger.error("[WorkerPool] Mode switch failed: %s", e, exc_info=True)
+            if not job.fut.done():
+                job.fut.set_exception(e)
+        finally:
+            self.q.task_done()
+            with self._gate:
+                self._switching = False
+                self._gate.notify_all()
+
+    def _worker_loop(self, k: int = 0):
+        while not self._stop.is_set():
+            try:
+                job = self.q.get(timeout=0.25)
+            except queue.Empty:
+                continue
+            if isinstance(job, ModeSwitchJob):
+                self._run_mode_switch(job)
+            else:
+                self._run_generation(k, job)
+
+    # ------------------------------------------------------------------ public API
+    def submit_job(self, job: Job) -> Future:
+        try:
+            self.q.put_nowait(job)
+            return job.fut
+        except queue.Full:
+            raise queue.Full(f"Job queue full (max: {self.queue_max}). "
+                             "Try again later or increase QUEUE_MAX.")
+
+    def switch_mode(self, mode_name: str) -> Future:
+        self._mode_config.get_mode(mode_name)          # raises KeyError for unknown modes
+        return self.submit_job(ModeSwitchJob(target_mode=mode_name))
+
+    def get_current_mode(self) -> Optional[str]:
+        return self._current_mode
+
+    def get_queue_size(self) -> int:
+        return self.q.qsize()
+
+    def shutdown(self):
+        self.q.join()
+        self._stop.set()
+        for t in self._worker_threads:
+            if t.is_alive():
+                t.join(timeout=5.0)
+        self._unload_current_worker()
+
+
+def _is_real_batcher(worker) -> bool:
+    """`run_batch` must be a real method, not an auto-attribute of a Mock."""
+    fn = getattr(type(worker), "run_batch", None)
+    return callable(fn)
+
+
+_worker_pool: Optional[WorkerPool] = None
+
+
+def get_worker_pool(worker_factory=None, mode_config=None, registry=None) -> WorkerPool:
+    """Process-wide pool; the first call wins (dependency injection honoured on that call)."""
+    global _worker_pool
+    if _worker_pool is None:
+        _worker_pool = WorkerPool(queue_max=int(os.environ.get("QUEUE_MAX", "64")),
+                                  worker_factory=worker_factory, mode_config=mode_config,
+                                  registry=registry)
+    return _worker_pool
+
+
+def reset_worker_pool():
+    global _worker_pool
+    if _worker_pool is not None:
+        try:
+            _worker_pool.shutdown()
+        except Exception:
+            pass
+    _worker_pool = None

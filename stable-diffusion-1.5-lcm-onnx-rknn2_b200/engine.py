@@ -293,6 +293,32 @@ class VAEDecoderB200:
 # ------------------------------------------------------------------------------------------------
 # pipeline: denoise loop + decode
 # ------------------------------------------------------------------------------------------------
+class _StaticGraph:
+    """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps)."""
+
+    def __init__(self, pipe: "LCMPipelineB200", B, h, w, steps):
+        dev = pipe.device
+        D = pipe.unet.cfg.cross_attention_dim
+        self.pe = torch.zeros(B, 77, D, device=dev, dtype=BF16)
+        cd = pipe.unet.cfg.time_cond_proj_dim
+        self.w_emb = torch.zeros(B, cd, device=dev, dtype=torch.float32) if cd else None
+        self.lat = torch.zeros(B, 4, h, w, device=dev, dtype=torch.float32)
+        self.noise = torch.zeros(max(steps - 1, 1), B, 4, h, w, device=dev, dtype=torch.float32)
+        self.steps = steps
+        # warm-up on a side stream (lazy per-device init: smem attributes, module load)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            pipe.run_static(self.pe, self.w_emb, self.lat, self.noise, steps)
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.img, self.final = pipe.run_static(self.pe, self.w_emb, self.lat, self.noise, steps)
+        self.launches = lib.launch_count - n0        # native kernel launches per replay
+
+
 class LCMPipelineB200:
     """The hot path as one object: `generate()` = 4..8 x (UNet + scheduler step) + VAE decode."""
 
@@ -302,31 +328,43 @@ class LCMPipelineB200:
         self.vae = VAEDecoderB200(vae_sd, vae_cfg, device)
         self._graphs = {}
 
+    def _w_emb(self, B, guidance_scale):
+        cd = self.unet.cfg.time_cond_proj_dim
+        if not cd:
+            return None
+        gs = torch.as_tensor(guidance_scale, dtype=torch.float32).reshape(-1).expand(B)
+        return guidance_scale_embedding(gs - 1.0, cd)           # host, fp32 [B, cd]
+
     @torch.no_grad()
-    def prepare(self, prompt_embeds, num_inference_steps: int, guidance_scale=1.0):
-        """Per-request constants: hoisted cross-attn K/V, per-step time embeddings."""
-        B = prompt_embeds.shape[0]
-        sched = LCMSchedule(num_inference_steps)
-        w_emb = None
-        if self.unet.cfg.time_cond_proj_dim:
-            gs = torch.as_tensor(guidance_scale, dtype=torch.float32).reshape(-1).expand(B)
-            w_emb = guidance_scale_embedding(gs - 1.0, self.unet.cfg.time_cond_proj_dim).to(self.device)
-        kvs = self.unet.encode_context(prompt_embeds)
+    def run_static(self, pe_bf16, w_emb, lat_nchw, noise_nchw, steps: int, record: dict = None):
+        """Everything on device, no host sync, graph-capturable.  Returns (u8 images, latents)."""
+        B = lat_nchw.shape[0]
+        sched = LCMSchedule(steps)
+        kvs = self.unet.encode_context(pe_bf16)
         tembs = self.unet.time_embeddings(sched.timesteps, B, w_emb)
-        return sched, kvs, tembs
+        lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record)
+        return self.vae.decode(lat), lat
+
+    def graph_for(self, B, h, w, steps) -> _StaticGraph:
+        key = (B, h, w, steps)
+        g = self._graphs.get(key)
+        if g is None:
+            with torch.cuda.device(self.device):
+                g = self._graphs[key] = _StaticGraph(self, B, h, w, steps)
+        return g
 
     @torch.no_grad()
     def denoise(self, latents_nchw, step_noise_nchw, sched, kvs, tembs, record: dict = None):
         """latents fp32 NCHW [B,4,h,w]; step_noise [steps-1,B,4,h,w].  Returns final latents NHWC."""
         B, C, H, W = latents_nchw.shape
         x = torch.empty(B, H, W, C, device=self.device, dtype=torch.float32)
-        lib.nchw_to_nhwc_f32(latents_nchw.to(self.device, torch.float32).contiguous(), x)
+        lib.nchw_to_nhwc_f32(latents_nchw, x)
         n = sched.num_inference_steps
         noise = None
         if n > 1:
-            sn = step_noise_nchw.to(self.device, torch.float32).contiguous()
             noise = torch.empty(n - 1, B, H, W, C, device=self.device, dtype=torch.float32)
-            lib.nchw_to_nhwc_f32(sn.view((n - 1) * B, C, H, W), noise.view((n - 1) * B, H, W, C))
+            lib.nchw_to_nhwc_f32(step_noise_nchw[:n - 1].reshape((n - 1) * B, C, H, W),
+                                 noise.view((n - 1) * B, H, W, C))
         den = torch.empty_like(x)
         for i in range(n):
             eps = self.unet.forward(x, tembs[i], kvs)
@@ -340,9 +378,30 @@ class LCMPipelineB200:
 
     @torch.no_grad()
     def generate(self, prompt_embeds, latents_nchw, step_noise_nchw, num_inference_steps: int,
-                 guidance_scale=1.0, record: dict = None, return_latents: bool = False):
-        """-> u8 images [B, H, W, 3] on device (and the final latents NHWC fp32 if asked)."""
-        sched, kvs, tembs = self.prepare(prompt_embeds, num_inference_steps, guidance_scale)
-        lat = self.denoise(latents_nchw, step_noise_nchw, sched, kvs, tembs, record)
-        img = self.vae.decode(lat)
+                 guidance_scale=1.0, record: dict = None, return_latents: bool = False,
+                 use_graph: bool = False):
+        """Public entry: host or device tensors in -> u8 images [B,H,W,3] on device (and the
+        final latents NHWC fp32 if asked).  With use_graph the whole pass is one CUDA-graph
+        replay; the returned tensors are the graph's static outputs (consume before next call)."""
+        B, _, h, w = latents_nchw.shape
+        steps = int(num_inference_steps)
+        w_emb = self._w_emb(B, guidance_scale)
+        with torch.cuda.device(self.device):
+            if use_graph and record is None:
+                g = self.graph_for(B, h, w, steps)
+                g.pe.copy_(prompt_embeds, non_blocking=True)
+                if w_emb is not None:
+                    g.w_emb.copy_(w_emb, non_blocking=True)
+                g.lat.copy_(latents_nchw, non_blocking=True)
+                if steps > 1:
+                    g.noise.copy_(step_noise_nchw, non_blocking=True)
+                g.graph.replay()
+                img, lat = g.img, g.final
+            else:
+                pe = prompt_embeds.to(self.device, BF16).contiguous()
+                we = w_emb.to(self.device) if w_emb is not None else None
+                lat0 = latents_nchw.to(self.device, torch.float32).contiguous()
+                nz = (step_noise_nchw.to(self.device, torch.float32).contiguous()
+                      if steps > 1 else None)
+                img, lat = self.run_static(pe, we, lat0, nz, steps, record)
         return (img, lat) if return_latents else img

@@ -1,0 +1,44 @@
+"""Generates the committed golden fixtures from the oracle (run from the repo root:
+`python tests/golden/make_golden.py`).  The reference itself cannot produce vectors here:
+its arithmetic lives in `diffusers`, which is absent from this image."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.pipeline import build_random_init, run_pipeline, synthetic_inputs  # noqa: E402
+from oracle.unet import UNetConfig  # noqa: E402
+from oracle.vae import VAEConfig  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def tiny():
+    unet, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    pe, lat, noise = synthetic_inputs(1, 64, 64, 2, ctx_dim=unet.cfg.cross_attention_dim)
+    rec = {}
+    img = run_pipeline(unet, vae, pe, lat, noise, 2, 1.0, record=rec, tiling=False)
+    np.savez_compressed(os.path.join(HERE, "tiny_pipeline.npz"),
+                        noise_pred0=rec["noise_pred"][0].numpy(),
+                        final_latents=rec["latents"][-1].numpy(), image=img)
+
+
+def full(size=512, steps=4):
+    """BASELINE config C1: SD1.5-LCM arch, random-init seed 0, 512x512, 4 steps, gs 1.0, B=1."""
+    torch.set_num_threads(os.cpu_count())
+    unet, vae = build_random_init(seed=0)
+    pe, lat, noise = synthetic_inputs(1, size, size, steps)
+    rec = {}
+    img = run_pipeline(unet, vae, pe, lat, noise, steps, 1.0, record=rec, tiling=False)
+    np.savez_compressed(os.path.join(HERE, f"sd15_lcm_{size}_{steps}step.npz"),
+                        noise_pred=torch.stack(rec["noise_pred"]).numpy().astype(np.float32),
+                        latents=torch.stack(rec["latents"]).numpy().astype(np.float32),
+                        image=img)
+
+
+if __name__ == "__main__":
+    tiny()
+    if "--full" in sys.argv:
+        full()

@@ -1,0 +1,140 @@
+"""Pins the oracle to every known answer that is derivable offline:
+parameter counts of the named architectures, LCM timestep tables, alphas_cumprod values,
+boundary scalings, the w=0 guidance embedding, and the committed golden fixtures."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.pipeline import (build_random_init, denormalize_to_u8, pooled_latent_bytes,
+                             run_pipeline, synthetic_inputs)
+from oracle.scheduler import OracleLCMScheduler, guidance_scale_embedding
+from oracle.unet import OracleUNet, UNetConfig, timestep_embedding
+from oracle.vae import OracleVAEDecoder, VAEConfig
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+TIMESTEPS = {
+    1: [999], 2: [999, 499], 4: [999, 759, 499, 259],
+    8: [999, 879, 759, 639, 499, 379, 259, 139],
+    30: [999, 979, 939, 899, 879, 839, 799, 779, 739, 699, 679, 639, 599, 579, 539, 499, 479,
+         439, 399, 379, 339, 299, 279, 239, 199, 179, 139, 99, 79, 39],
+}
+ALPHAS = {999: 0.00466009509, 759: 0.0522128902, 499: 0.27766943, 259: 0.658975244,
+          19: 0.982243955, 0: 0.999149978}
+
+
+def _meta_count(mod_cls, cfg):
+    with torch.device("meta"):
+        m = mod_cls(cfg)
+    return sum(p.numel() for p in m.parameters()), m
+
+
+def test_param_counts_match_published_architectures():
+    n_unet, m = _meta_count(OracleUNet, UNetConfig())
+    assert n_unet == 859_602_884                      # 859.52 M SD1.5 + 81 920 cond_proj (LCM)
+    assert m.time_embedding.cond_proj.weight.numel() == 81_920
+    n_vanilla, _ = _meta_count(OracleUNet, UNetConfig(time_cond_proj_dim=None))
+    assert n_vanilla == 859_520_964                   # the published SD1.5 UNet size
+    n_vae, v = _meta_count(OracleVAEDecoder, VAEConfig())
+    assert n_vae == 49_490_199                        # decoder 49 490 179 + post_quant_conv 20
+
+
+def test_diffusers_state_dict_names():
+    _, m = _meta_count(OracleUNet, UNetConfig())
+    keys = set(m.state_dict().keys())
+    for k in ["conv_in.weight", "time_embedding.linear_1.weight", "time_embedding.cond_proj.weight",
+              "down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_k.weight",
+              "down_blocks.2.downsamplers.0.conv.bias", "mid_block.attentions.0.proj_in.weight",
+              "up_blocks.1.resnets.2.conv_shortcut.weight", "up_blocks.2.upsamplers.0.conv.weight",
+              "up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.weight",
+              "up_blocks.3.attentions.2.transformer_blocks.0.ff.net.2.bias",
+              "conv_norm_out.weight", "conv_out.bias"]:
+        assert k in keys, k
+    assert m.state_dict()["up_blocks.1.resnets.2.conv1.weight"].shape == (1280, 1920, 3, 3)
+    assert m.state_dict()["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"].shape == (320, 768)
+    _, v = _meta_count(OracleVAEDecoder, VAEConfig())
+    vk = set(v.state_dict().keys())
+    for k in ["post_quant_conv.weight", "decoder.conv_in.weight",
+              "decoder.mid_block.attentions.0.group_norm.weight",
+              "decoder.mid_block.attentions.0.to_out.0.bias",
+              "decoder.up_blocks.2.resnets.0.conv_shortcut.weight",
+              "decoder.up_blocks.2.upsamplers.0.conv.weight", "decoder.conv_out.weight"]:
+        assert k in vk, k
+
+
+@pytest.mark.parametrize("n", sorted(TIMESTEPS))
+def test_lcm_timesteps_bit_exact(n):
+    s = OracleLCMScheduler()
+    ts = s.set_timesteps(n)
+    assert ts.dtype == torch.int64 and ts.tolist() == TIMESTEPS[n]
+
+
+def test_alphas_cumprod_known_answers():
+    s = OracleLCMScheduler()
+    for t, v in ALPHAS.items():
+        assert abs(s.alphas_cumprod[t].item() - v) <= 1e-6 * max(v, 1e-3), (t, s.alphas_cumprod[t].item())
+
+
+def test_boundary_scalings_and_last_step():
+    s = OracleLCMScheduler()
+    c_skip, c_out = s.boundary_scalings(259)
+    assert abs(float(c_skip) - 3.7e-8) < 1e-9 and abs(float(c_out) - 1.0) < 1e-6
+    s.set_timesteps(4)
+    x = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    eps = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    for i, t in enumerate(s.timesteps):
+        z = torch.zeros_like(x) if i < 3 else None
+        prev, den = s.step(eps, int(t), x, noise=z)
+        if i == 3:
+            assert torch.equal(prev, den)              # final step returns the denoised sample
+        x = prev
+
+
+def test_guidance_embedding_w0():
+    e = guidance_scale_embedding(torch.zeros(2), 256)
+    assert e.shape == (2, 256)
+    assert torch.equal(e[:, :128], torch.zeros(2, 128)) and torch.equal(e[:, 128:], torch.ones(2, 128))
+
+
+def test_timestep_embedding_layout():
+    e = timestep_embedding(torch.tensor([0.0, 999.0]), 320)
+    assert torch.equal(e[0, :160], torch.ones(160)) and torch.equal(e[0, 160:], torch.zeros(160))
+    assert abs(e[1, 0].item() - np.cos(999.0)) < 1e-4 and abs(e[1, 160].item() - np.sin(999.0)) < 1e-4
+
+
+def test_postprocess_and_pool_contract():
+    img = torch.tensor([[[[-1.0, 0.0], [1.0, 3.0]]]]).repeat(1, 3, 1, 1)
+    u8 = denormalize_to_u8(img)
+    assert u8.dtype == np.uint8 and u8.shape == (1, 2, 2, 3)
+    assert u8[0, :, :, 0].tolist() == [[0, 128], [255, 255]]          # (0.5*255).round() == 128 (half-even)
+    b = pooled_latent_bytes(torch.ones(1, 4, 64, 64))
+    assert len(b) == 512 and np.frombuffer(b, dtype="<f2").tolist() == [1.0] * 256
+
+
+def test_tiny_pipeline_matches_committed_golden():
+    """The oracle itself is frozen by a small committed fixture (tests/golden/make_golden.py)."""
+    path = os.path.join(GOLD, "tiny_pipeline.npz")
+    g = np.load(path)
+    unet, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    pe, lat, noise = synthetic_inputs(1, 64, 64, 2, ctx_dim=unet.cfg.cross_attention_dim)
+    rec = {}
+    img = run_pipeline(unet, vae, pe, lat, noise, 2, 1.0, record=rec, tiling=False)
+    np.testing.assert_allclose(rec["noise_pred"][0].numpy(), g["noise_pred0"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rec["latents"][-1].numpy(), g["final_latents"], rtol=1e-4, atol=1e-5)
+    assert np.abs(img.astype(int) - g["image"].astype(int)).max() <= 1
+
+
+def test_vae_tiling_switch():
+    """`vae.enable_tiling()` semantics (App. A.4): tiled only above tile_latent_min_size, and a
+    tiled decode of a constant-statistics input stays close to the untiled one away from seams."""
+    _, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    z = torch.randn(1, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    a = vae(z, tiling=True)
+    b = vae.decode(z)
+    assert torch.equal(a, b)                                            # 16 <= 128/8: untiled
+    z2 = torch.randn(1, 4, 24, 24, generator=torch.Generator().manual_seed(0))
+    t = vae(z2, tiling=True)
+    assert t.shape == (1, 3, 192, 192)

@@ -1,0 +1,165 @@
+"""Worker pool: the reference's contract (its own `tests/test_worker_pool.py` also passes against
+this module) plus what is new here — N workers, micro-batching, barrier switch."""
+import queue
+import threading
+import time
+from concurrent.futures import Future
+from types import SimpleNamespace
+from unittest.mock import Mock
+
+import pytest
+
+from backends.worker_pool import (CustomJob, GenerationJob, JobType, ModeSwitchJob, WorkerPool,
+                                  get_worker_pool, reset_worker_pool)
+
+
+def make_config():
+    cfg = Mock()
+    cfg.config = Mock()
+    cfg.config.model_root = "/models"
+    modes = {}
+    for name, model in (("sd15-fast", "sd15"), ("sd15-alt", "alt")):
+        m = Mock()
+        m.name, m.model, m.model_path, m.loras = name, model, f"/models/{model}", []
+        modes[name] = m
+    cfg.get_mode.side_effect = lambda n: modes[n]
+    cfg.get_default_mode.return_value = "sd15-fast"
+    return cfg
+
+
+def make_registry():
+    r = Mock()
+    r.get_used_vram.return_value = 0
+    return r
+
+
+class FakeWorker:
+    """Worker with a real run_batch (what B200Worker offers)."""
+
+    def __init__(self, worker_id, delay=0.0):
+        self.worker_id = worker_id
+        self.delay = delay
+        self.batches = []
+        self.lock = threading.Lock()
+
+    def run_batch(self, jobs, with_latents=False):
+        time.sleep(self.delay)
+        with self.lock:
+            self.batches.append(len(jobs))
+        return [(f"png-{j.req.prompt}".encode(), self.worker_id) for j in jobs]
+
+    def run_job(self, job):
+        return self.run_batch([job])[0]
+
+
+def req(prompt, size="512x512", steps=4):
+    return SimpleNamespace(prompt=prompt, size=size, num_inference_steps=steps, guidance_scale=1.0, seed=1)
+
+
+@pytest.fixture
+def pool_factory():
+    pools = []
+
+    def make(**kw):
+        reset_worker_pool()
+        p = WorkerPool(queue_max=kw.pop("queue_max", 64), mode_config=make_config(),
+                       registry=make_registry(), **kw)
+        pools.append(p)
+        return p
+    yield make
+    for p in pools:
+        p.shutdown()
+
+
+def test_default_is_one_worker_id0(pool_factory):
+    factory = Mock(return_value=Mock(run_job=Mock(return_value="ok")))
+    pool = pool_factory(worker_factory=factory, num_workers=None)
+    factory.assert_called_once_with(worker_id=0)
+    assert pool._current_mode == "sd15-fast" and pool._worker is not None
+    assert pool._worker_thread.is_alive() and pool.queue_max == 64
+    job = GenerationJob(req=req("a"))
+    assert job.job_type == JobType.GENERATION
+    assert pool.submit_job(job).result(timeout=5) == "ok"
+
+
+def test_n_workers_pinned_and_all_used(pool_factory):
+    workers = {}
+
+    def factory(worker_id):
+        workers[worker_id] = FakeWorker(worker_id, delay=0.05)
+        return workers[worker_id]
+    pool = pool_factory(worker_factory=factory, num_workers=4, max_batch=1)
+    assert sorted(workers) == [0, 1, 2, 3] and len(pool._worker_threads) == 4
+    futs = [pool.submit_job(GenerationJob(req=req(str(i)))) for i in range(32)]
+    used = {f.result(timeout=10)[1] for f in futs}
+    assert used == {0, 1, 2, 3}                      # independent images shard across workers
+    assert [f.result()[0] for f in futs] == [f"png-{i}".encode() for i in range(32)]
+
+
+def test_micro_batching_groups_same_geometry_fifo_prefix(pool_factory):
+    w = FakeWorker(0, delay=0.2)
+    pool = pool_factory(worker_factory=lambda worker_id: w, num_workers=1, max_batch=8)
+    first = pool.submit_job(GenerationJob(req=req("warm")))      # occupies the worker
+    time.sleep(0.05)
+    futs = [pool.submit_job(GenerationJob(req=req(f"a{i}"))) for i in range(5)]
+    futs += [pool.submit_job(GenerationJob(req=req("b", size="768x768")))]
+    futs += [pool.submit_job(GenerationJob(req=req(f"c{i}"))) for i in range(2)]
+    for f in [first] + futs:
+        f.result(timeout=10)
+    assert w.batches == [1, 5, 1, 2]                  # never reorders across a different geometry
+    assert futs[5].result()[0] == b"png-b"
+
+
+def test_mode_switch_is_a_barrier_and_recreates_all_workers(pool_factory):
+    created = []
+
+    def factory(worker_id):
+        created.append(worker_id)
+        return FakeWorker(worker_id, delay=0.05)
+    pool = pool_factory(worker_factory=factory, num_workers=2, max_batch=1)
+    before = [pool.submit_job(GenerationJob(req=req(f"x{i}"))) for i in range(4)]
+    sw = pool.switch_mode("sd15-alt")
+    after = [pool.submit_job(GenerationJob(req=req(f"y{i}"))) for i in range(4)]
+    assert sw.result(timeout=10) == {"mode": "sd15-alt", "status": "switched"}
+    for f in before + after:
+        f.result(timeout=10)
+    assert created == [0, 1, 0, 1] and pool.get_current_mode() == "sd15-alt"
+    assert pool.switch_mode("sd15-alt").result(timeout=5)["status"] == "already_loaded"
+    with pytest.raises(KeyError):
+        pool.switch_mode("nope")
+
+
+def test_errors_propagate_and_pool_keeps_serving(pool_factory):
+    w = Mock()
+    w.run_job.side_effect = [RuntimeError("Invalid size 'x', expected 'WIDTHxHEIGHT'"), "fine"]
+    pool = pool_factory(worker_factory=lambda worker_id: w, num_workers=1)
+    f1 = pool.submit_job(GenerationJob(req=req("bad", size="x")))
+    with pytest.raises(RuntimeError, match="Invalid size"):
+        f1.result(timeout=5)
+    assert pool.submit_job(GenerationJob(req=req("ok"))).result(timeout=5) == "fine"
+    assert pool.submit_job(CustomJob(handler=lambda a, b=0: a + b, args=(1,), kwargs={"b": 2})).result(timeout=5) == 3
+
+
+def test_queue_full_and_shutdown(pool_factory):
+    gate = threading.Event()
+    w = Mock()
+    w.run_job.side_effect = lambda job: (gate.wait(5), "done")[1]
+    pool = pool_factory(worker_factory=lambda worker_id: w, num_workers=1, queue_max=2)
+    futs = [pool.submit_job(GenerationJob(req=req("0")))]
+    time.sleep(0.4)                                   # the worker thread took job 0
+    futs += [pool.submit_job(GenerationJob(req=req(str(i)))) for i in (1, 2)]
+    with pytest.raises(queue.Full):
+        pool.submit_job(GenerationJob(req=req("3")))
+    gate.set()
+    assert [f.result(timeout=5) for f in futs] == ["done"] * 3
+    pool.shutdown()
+    assert pool._worker is None and pool.get_queue_size() == 0
+
+
+def test_singleton_first_call_wins():
+    reset_worker_pool()
+    f = Mock(return_value=Mock())
+    p1 = get_worker_pool(worker_factory=f, mode_config=make_config(), registry=make_registry())
+    p2 = get_worker_pool(worker_factory=Mock(), mode_config=make_config(), registry=make_registry())
+    assert p1 is p2
+    reset_worker_pool()
