@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""Headline benchmark: 512x512 LCM 4-step images/sec (UNet + VAE) — BASELINE.json metric.
+
+  python bench.py --gpus N --steps K --warmup W            # the B200-native arm
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch: 4 x (UNet forward + LCM scheduler step)
+followed by the VAE decode of a batch of 16 images (BASELINE config C2; at N GPUs each rank
+runs its own batch of 16 = config C4's 128/8 shard, weak scaling, no data-path collective).
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "512x512 LCM 4-step images/sec (UNet+VAE)"
+UNIT = "images/s"
+GFLOP_UNET, GFLOP_VAE = 803.27, 2514.52            # per sample, BASELINE.md §3 (2*MAC)
+GFLOP_IMAGE = 4 * GFLOP_UNET + GFLOP_VAE           # 5727.6
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1386.3), d.get("bf16_tflops", 1632.4), d.get("hbm_gbs", 6535.7), "measured"
+    return 1400.0, 1590.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_sample(threads: int):
+    """Bounded sample of config C1 on the host cores: one UNet forward at the full 64^2 latent
+    + one VAE decode of a 32^2 latent (256^2 image; conv FLOPs scale with pixel count: x4).
+    images/s = 1 / (4 t_unet + 4 t_vae256)."""
+    import torch
+    from oracle.pipeline import build_random_init, synthetic_inputs
+    from oracle.scheduler import guidance_scale_embedding
+    torch.set_num_threads(threads)
+    unet, vae = build_random_init(seed=0)
+    pe, lat, _ = synthetic_inputs(1, 512, 512, 4)
+    w = guidance_scale_embedding(torch.zeros(1), 256)
+    z = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+
+    def once():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            unet(lat, torch.tensor(999), pe, w)
+            t1 = time.perf_counter()
+            vae.decode(z)
+            t2 = time.perf_counter()
+        return 4 * (t1 - t0) + 4 * (t2 - t1), (t1 - t0), (t2 - t1)
+    return once
+
+
+SAMPLE_TXT = ("config C1 (B=1, fp32 torch CPU restatement of the diffusers path): 1 UNet forward @64^2 "
+              "latent + 1 VAE decode @32^2 latent scaled x4 by pixel count; images/s = 1/(4*t_unet + 4*t_vae256)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    once = cpu_oracle_sample(threads)
+    for _ in range(args.warmup):
+        once()
+    ts = [once()[0] for _ in range(args.steps)]
+    sec_per_image = sum(ts) / len(ts)
+    v = 1.0 / sec_per_image
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_image,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "SD1.5-LCM arch (random-init seed 0) 512x512, 4 steps, guidance 1.0, batch 1 on host CPU"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_TXT},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    if world > 1:
+        dist.barrier()
+    from dreamlab_b200 import lib
+    from dreamlab_b200.engine import LCMPipelineB200
+    from dreamlab_b200 import synthetic as syn
+    from dreamlab_b200.synthetic import synthetic_inputs
+    B, size, nsteps = args.batch, args.size, args.lcm_steps
+    ucfg, vcfg = syn.sd15_lcm_unet_cfg(), syn.sd_vae_cfg()
+    pipe = LCMPipelineB200(syn.random_state_dict(syn.unet_shapes(ucfg), 0), ucfg,
+                           syn.random_state_dict(syn.vae_decoder_shapes(vcfg), 1), vcfg, dev)
+    pe, lat, noise = synthetic_inputs(B, size, size, nsteps, seed_base=1000 + rank * B)
+    gr = pipe.graph_for(B, size // 8, size // 8, nsteps)
+    # ---- device-resident inputs (value) ----
+    gr.pe.copy_(pe)
+    gr.lat.copy_(lat)
+    gr.noise.copy_(noise)
+    from dreamlab_b200.scheduler import guidance_scale_embedding
+    gr.w_emb.copy_(guidance_scale_embedding(torch.zeros(B), 256))
+    l2_flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        gr.graph.replay()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        l2_flush.zero_()                      # flush L2 between timed iterations
+        a.record()
+        gr.graph.replay()
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    value = world * B * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: host pinned inputs -> public API -> host image, every step ----
+    pe_h, lat_h, noise_h = pe.pin_memory(), lat.pin_memory(), noise.pin_memory()
+    img_h = torch.empty(B, size, size, 3, dtype=torch.uint8).pin_memory()
+    h2d = pe_h.numel() * 4 + lat_h.numel() * 4 + noise_h.numel() * 4 + B * 256 * 4
+    d2h = img_h.numel()
+
+    def e2e_once():
+        img = pipe.generate(pe_h, lat_h, noise_h, nsteps, 1.0, use_graph=True)
+        img_h.copy_(img, non_blocking=True)
+    for _ in range(2):
+        e2e_once()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        e2e_once()
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (te.item() / 1e3)
+
+    # ---- roofline of the dominant kernel (igemm), CUDA events around every launch ----
+    roof = None
+    if rank == 0:
+        lib.profile_begin()
+        pipe.generate(gr.pe, gr.lat, gr.noise, nsteps, 1.0, use_graph=False)
+        prof = lib.profile_end()
+        sustained, burst, hbm, src = peaks()
+        ig = prof.get("igemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+        tot_ms = sum(v["ms"] for v in prof.values())
+        ach = ig["flops"] / (ig["ms"] / 1e3) / 1e12 if ig["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear)",
+                "achieved": ach, "peak": sustained, "peak_kind": f"bf16 dense sustained, {src}",
+                "unit": "TFLOP/s", "frac": ach / sustained, "traffic": None,
+                "launches": ig["n"], "share_of_step": ig["ms"] / tot_ms if tot_ms else None,
+                "step_achieved_tflops": GFLOP_IMAGE * value / world / 1e3,
+                "step_frac": GFLOP_IMAGE * value / world / 1e3 / sustained,
+                "by_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        once = cpu_oracle_sample(threads)
+        once()
+        s, tu, tv = once()
+        cpu = {"value": 1.0 / s, "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_TXT,
+               "t_unet_s": tu, "t_vae256_s": tv}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"SD1.5-LCM arch (random-init seed 0) {size}x{size}, {nsteps} LCM steps, "
+                                   f"guidance 1.0, batch {B} per GPU (UNet x{nsteps} + scheduler + VAE decode)",
+                       "batch_per_gpu": B, "global_batch": B * world, "l2": "flushed between timed iterations",
+                       "cuda_graph": True, "parallelism": f"replicas x{world} (no collective)"},
+            "p50_latency_ms_per_batch": statistics.median(step_ms),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": gr.launches * args.steps,
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--lcm-steps", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -5,4 +5,4 @@ hand-written sm_100a kernels of `csrc/` behind the C-ABI of `include/dreamlab_b2
 There is no CPU fallback: importing is cheap, but every op raises if the native library or a
 CUDA device is missing.
 """
-__all__ = ["lib", "scheduler", "weights", "engine"]
+__all__ = ["lib", "scheduler", "weights", "engine", "synthetic"]

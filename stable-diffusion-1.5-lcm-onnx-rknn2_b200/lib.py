@@ -116,6 +116,49 @@ def _count(n=1):
     launch_count += n
 
 
+# ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {kernel: {"ms": total, "flops": total, "bytes": total, "n": launches}}"""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for name, flops, nbytes, a, b in _prof:
+        d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
+        d["ms"] += a.elapsed_time(b)
+        d["flops"] += flops
+        d["bytes"] += nbytes
+        d["n"] += 1
+    _prof = None
+    return out
+
+
+class _timed:
+    __slots__ = ("name", "flops", "nbytes", "a")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _prof is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _prof is not None and exc[0] is None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            _prof.append((self.name, self.flops, self.nbytes, self.a, b))
+        return False
+
+
 def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("dreamlab_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -148,7 +191,8 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.residual = _ptr(residual)
     d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
     d.mode, d.alpha, d.bn = mode, alpha, bn
-    _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
+    with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1)):
+        _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
     _count()
 
 
@@ -159,24 +203,27 @@ def groupnorm_workspace_bytes(nimg, groups=32):
 def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5, silu=True, x1=None):
     c0 = x0.shape[-1]
     c1 = x1.shape[-1] if x1 is not None else 0
-    _check(load().dl_groupnorm(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
-                               gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
-                               workspace.data_ptr(), _stream()), "groupnorm")
+    with _timed("groupnorm", 0.0, 4.0 * nimg * hw * (c0 + c1)):
+        _check(load().dl_groupnorm(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
+                                   gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
+                                   workspace.data_ptr(), _stream()), "groupnorm")
     _count(2)
 
 
 def layernorm(x, out, gamma, beta, eps=1e-5):
     rows = x.numel() // x.shape[-1]
-    _check(load().dl_layernorm(x.data_ptr(), rows, x.shape[-1], eps, gamma.data_ptr(),
-                               beta.data_ptr(), out.data_ptr(), _stream()), "layernorm")
+    with _timed("layernorm", 0.0, 4.0 * x.numel()):
+        _check(load().dl_layernorm(x.data_ptr(), rows, x.shape[-1], eps, gamma.data_ptr(),
+                                   beta.data_ptr(), out.data_ptr(), _stream()), "layernorm")
     _count()
 
 
 def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ldv, ldo, scale,
               impl=ATTN_TC):
-    _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
-                               out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
-                               _stream()), "attention")
+    with _timed("attention", 4.0 * batch * heads * sq * skv * d):
+        _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
+                                   out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
+                                   _stream()), "attention")
     _count()
 
 
@@ -196,14 +243,16 @@ def small_linear(x, w, out, bias=None, add=None, silu_in=False, silu_out=False):
 
 
 def upsample2x(x, out, *, nimg, h, w):
-    _check(load().dl_upsample2x(x.data_ptr(), nimg, h, w, x.shape[-1], out.data_ptr(), _stream()),
-           "upsample2x")
+    with _timed("upsample2x", 0.0, 10.0 * x.numel()):
+        _check(load().dl_upsample2x(x.data_ptr(), nimg, h, w, x.shape[-1], out.data_ptr(), _stream()),
+               "upsample2x")
     _count()
 
 
 def im2col_s2(x, cols, *, nimg, h, w):
-    _check(load().dl_im2col_s2(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
-           "im2col_s2")
+    with _timed("im2col_s2", 0.0, 2.0 * x.numel() + 2.0 * cols.numel()):
+        _check(load().dl_im2col_s2(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
+               "im2col_s2")
     _count()
 
 
@@ -216,8 +265,9 @@ def pack_latent(x, out, *, cin, scale=1.0, mat=None, vec=None):
 
 def softmax_rows(scores, out):
     rows, cols = scores.shape
-    _check(load().dl_softmax_rows(scores.data_ptr(), rows, cols, out.data_ptr(), _stream()),
-           "softmax_rows")
+    with _timed("softmax_rows", 0.0, 6.0 * scores.numel()):
+        _check(load().dl_softmax_rows(scores.data_ptr(), rows, cols, out.data_ptr(), _stream()),
+               "softmax_rows")
     _count()
 
 

@@ -1,0 +1,50 @@
+"""Product-side shape tables (dreamlab_b200.synthetic) agree key-for-key, shape-for-shape with
+the oracle modules (and hence with the published parameter counts)."""
+import torch
+
+from dreamlab_b200 import synthetic as S
+from oracle.unet import OracleUNet, UNetConfig
+from oracle.vae import OracleVAEDecoder, VAEConfig
+
+
+def _shapes(mod):
+    return {k: tuple(v.shape) for k, v in mod.state_dict().items()}
+
+
+def test_unet_and_vae_shape_tables_match_oracle():
+    with torch.device("meta"):
+        u, v = OracleUNet(UNetConfig()), OracleVAEDecoder(VAEConfig())
+        ut, vt = OracleUNet(UNetConfig.tiny()), OracleVAEDecoder(VAEConfig.tiny())
+    assert S.unet_shapes(S.sd15_lcm_unet_cfg()) == _shapes(u)
+    assert S.vae_decoder_shapes(S.sd_vae_cfg()) == _shapes(v)
+    assert S.unet_shapes(ut.cfg) == _shapes(ut)
+    assert S.vae_decoder_shapes(vt.cfg) == _shapes(vt)
+    n = sum(torch.Size(s).numel() for s in S.unet_shapes(S.sd15_lcm_unet_cfg()).values())
+    assert n == 859_602_884
+
+
+def test_random_state_dict_is_deterministic_and_bounded():
+    shp = S.vae_decoder_shapes(VAEConfig.tiny())
+    a, b = S.random_state_dict(shp, 3), S.random_state_dict(shp, 3)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    w = a["decoder.conv_in.weight"]
+    assert w.abs().max() <= 1 / (4 * 9) ** 0.5 + 1e-6
+    assert torch.equal(a["decoder.conv_norm_out.weight"], torch.ones(64))
+
+
+def test_synthetic_inputs_match_oracle_protocol():
+    from oracle.pipeline import synthetic_inputs as oracle_inputs
+    a = S.synthetic_inputs(3, 64, 64, 4)
+    b = oracle_inputs(3, 64, 64, 4)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_write_model_dir_roundtrip(tmp_path):
+    from backends.b200_worker import _load_component, unet_cfg_from_json, vae_cfg_from_json
+    p = S.write_model_dir(str(tmp_path / "m"), UNetConfig.tiny(), VAEConfig.tiny())
+    cj, sd = _load_component(p + "/unet")
+    cfg = unet_cfg_from_json(cj)
+    assert cfg.block_out_channels == (64, 128, 256, 256) and cfg.down_attn == (True, True, True, False)
+    assert set(sd) == set(S.unet_shapes(cfg))
+    vj, vsd = _load_component(p + "/vae")
+    assert vae_cfg_from_json(vj).sample_size == 128 and set(vsd) == set(S.vae_decoder_shapes(VAEConfig.tiny()))
