@@ -287,17 +287,17 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   DL_CHECK_ARG(p.stages >= 1, "attention(tc): head dim %d does not fit shared memory", d);
   const uint32_t box[2] = {64, AT_TILE};
   {
-    const uint64_t dims[2] = {(uint64_t)ldq, (uint64_t)batch * sq};
+    const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * sq};   // columns owned by Q only
     const uint64_t str[1] = {(uint64_t)ldq * 2};
     if (make_tmap_bf16(&p.tmQ, q, 2, dims, str, box)) return 1;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)ldk, (uint64_t)batch * skv};
+    const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * skv};
     const uint64_t str[1] = {(uint64_t)ldk * 2};
     if (make_tmap_bf16(&p.tmK, k, 2, dims, str, box)) return 1;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)ldv, (uint64_t)batch * skv};
+    const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * skv};
     const uint64_t str[1] = {(uint64_t)ldv * 2};
     if (make_tmap_bf16(&p.tmV, v, 2, dims, str, box)) return 1;
   }

@@ -97,10 +97,18 @@ def load() -> C.CDLL:
     return _lib
 
 
+_SYNC_DEBUG = os.environ.get("DREAMLAB_SYNC", "") not in ("", "0")
+
+
 def _check(rc: int, what: str):
     if rc != 0:
         msg = load().dl_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"dreamlab_b200.{what} failed (status {rc}): {msg}")
+    if _SYNC_DEBUG:                      # debugging aid: surface device faults at the faulting op
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise RuntimeError(f"dreamlab_b200.{what}: device fault after launch: {e}")
 
 
 def _stream() -> int:

@@ -26,7 +26,9 @@ def worker(tmp_path_factory):
     from oracle.unet import UNetConfig
     from oracle.vae import VAEConfig
     root = tmp_path_factory.mktemp("models")
-    S.write_model_dir(str(root / "tiny-lcm"), UNetConfig.tiny(), VAEConfig.tiny())
+    ucfg = UNetConfig.tiny()
+    ucfg.cross_attention_dim = 768            # the factory routes on 768/1024 -> sd15
+    S.write_model_dir(str(root / "tiny-lcm"), ucfg, VAEConfig.tiny())
     os.environ["MODEL_ROOT"], os.environ["MODEL"] = str(root), "tiny-lcm"
     os.environ.pop("CUDA_DEVICE", None)
     from backends.worker_factory import create_cuda_worker
