@@ -89,11 +89,13 @@ int dl_layernorm(const void* x, long long rows, int c, float eps, const float* g
 /* ---- attention (diffusers Attention / AttnProcessor2_0, K5/K6) ---------------------------- *
  * q: bf16 [batch*sq, ldq]  head h at columns [h*dh_stride, h*dh_stride+d); k, v likewise over
  * [batch*skv, ld].  out: bf16 [batch*sq, ldo], head h at columns [h*d, (h+1)*d).
- * impl: DL_ATTN_TC = tcgen05 flash kernel (product path), DL_ATTN_SIMT = CUDA-core checker.   */
+ * impl: DL_ATTN_TC = tcgen05 flash kernel (product path), DL_ATTN_SIMT = CUDA-core checker.
+ * v_ones = 1: column d of every V head holds 1.0 (per-head stride >= ceil16(d+1)); the PV MMA
+ * then accumulates the softmax denominator on the tensor core instead of the CUDA cores.       */
 enum { DL_ATTN_TC = 0, DL_ATTN_SIMT = 1 };
 int dl_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                  long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
-                 int skv, int heads, int d, float scale, int impl, void* stream);
+                 int skv, int heads, int d, float scale, int impl, int v_ones, void* stream);
 
 /* ---- time / guidance embedding pieces (diffusers Timesteps + TimestepEmbedding, K9) ------- */
 /* out[b, :] = [cos(t_b f_i), sin(t_b f_i)], f_i = exp(-ln(1e4) i/half)  (flip_sin_to_cos)     */

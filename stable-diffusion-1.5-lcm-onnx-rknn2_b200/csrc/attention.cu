@@ -31,21 +31,27 @@ struct AttnParams {
   CUtensorMap tmQ, tmK, tmV;
   __nv_bfloat16* out;
   long long ldo;
-  int sq, skv, d, d16, nchunk, dh_stride;
-  int stages;
+  int sq, skv, d, dh_stride;
+  int ksteps;        // QK^T K-steps of 16 (ceil(d/16))
+  int nchunk_qk;     // 64-column TMA boxes per Q / K tile
+  int dv;            // PV MMA N = O columns (multiple of 16; includes the ones column if any)
+  int nchunk_v;      // 64-column TMA boxes per V tile
+  int l_col;         // O column that accumulates the softmax denominator (V ones column), or -1
+  int stages;        // K/V smem ring depth
+  int sbuf;          // S/P TMEM buffers (2: S_{j+1} overlaps softmax_j; 1: two CTAs per SM)
+  int tmem_cols;
   float scale_log2;
 };
 
-// TMEM column map (512 columns allocated): S0 [0,128) S1 [128,256) O [256, 256+d16)
-constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256;
-
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
-  const int q_bytes = p.nchunk * AT_CHUNK_BYTES;
-  const int kv_bytes = 2 * q_bytes;                       // K tile + V tile
+  const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
+  const int k_bytes = q_bytes;
+  const int v_bytes = p.nchunk_v * AT_CHUNK_BYTES;
+  const int kv_bytes = k_bytes + v_bytes;
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + q_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * kv_bytes);
@@ -61,6 +67,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   const int q0 = blockIdx.x * AT_TILE;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.skv + AT_TILE - 1) / AT_TILE;
+  const uint32_t o_col = (uint32_t)(p.sbuf * AT_TILE);   // TMEM: S/P buffers first, then O
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -72,7 +79,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,40 +90,41 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     if (lane == 0) {
       const int col0 = h * p.dh_stride;
       mbar_expect_tx(q_full, (uint32_t)q_bytes);
-      for (int c = 0; c < p.nchunk; ++c)
+      for (int c = 0; c < p.nchunk_qk; ++c)
         tma_load_2d(sQ + c * AT_CHUNK_BYTES, &p.tmQ, q_full, col0 + c * 64, b * p.sq + q0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
         uint8_t* sK = sKV + (size_t)stage * kv_bytes;
-        uint8_t* sV = sK + q_bytes;
+        uint8_t* sV = sK + k_bytes;
         mbar_expect_tx(&kv_full[stage], (uint32_t)kv_bytes);
         const int row = b * p.skv + j * AT_TILE;
-        for (int c = 0; c < p.nchunk; ++c) {
+        for (int c = 0; c < p.nchunk_qk; ++c)
           tma_load_2d(sK + c * AT_CHUNK_BYTES, &p.tmK, &kv_full[stage], col0 + c * 64, row);
+        for (int c = 0; c < p.nchunk_v; ++c)
           tma_load_2d(sV + c * AT_CHUNK_BYTES, &p.tmV, &kv_full[stage], col0 + c * 64, row);
-        }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);              // Q K^T
-      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.d16, 0, 1);  // P V (B MN-major)
-      const int ksteps = p.d16 / 16;
+      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);             // Q K^T
+      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv, 0, 1);  // P V (B MN-major)
       const uint32_t sq_addr = smem_u32(sQ);
       auto issue_s = [&](int j, int stage) {
         const uint32_t sk_addr = smem_u32(sKV + (size_t)stage * kv_bytes);
-        const uint32_t d_tmem = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
-        for (int ks = 0; ks < ksteps; ++ks) {
+        const int sb = j % p.sbuf;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+        for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t off = (uint32_t)((ks >> 2) * AT_CHUNK_BYTES + (ks & 3) * 32);
           umma_ss(d_tmem, umma_desc_kmajor_sw128(sq_addr + off, 1024),
                   umma_desc_kmajor_sw128(sk_addr + off, 1024), idesc_s, ks > 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[sb]);
       };
+      const bool prefetch_s = (p.sbuf == 2 && p.stages >= 2);
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
@@ -127,17 +135,18 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
-        if (p.stages >= 2 && j + 1 < n_tiles) {
+        if (prefetch_s && j + 1 < n_tiles) {
           mbar_wait(&kv_full[nstage], nphase);
           tc_fence_after();
           issue_s(j + 1, nstage);
         }
-        mbar_wait(&p_ready[j & 1], (uint32_t)((j >> 1) & 1));
+        const int sb = j % p.sbuf;
+        mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
         tc_fence_after();
         {
-          const uint32_t sv_addr = smem_u32(sKV + (size_t)stage * kv_bytes + q_bytes);
-          const uint32_t p_tmem = tmem_base + ((j & 1) ? TM_S1 : TM_S0);
-          const uint32_t o_tmem = tmem_base + TM_O;
+          const uint32_t sv_addr = smem_u32(sKV + (size_t)stage * kv_bytes + k_bytes);
+          const uint32_t p_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+          const uint32_t o_tmem = tmem_base + o_col;
           for (int ks = 0; ks < AT_TILE / 16; ++ks) {
             // 16 keys = two 8-row swizzle atoms = 2048 B; P advances 8 packed columns
             umma_ts(o_tmem, p_tmem + (uint32_t)(ks * 8),
@@ -147,7 +156,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           umma_commit(&kv_empty[stage]);
           umma_commit(pv_done);
         }
-        if (p.stages < 2 && j + 1 < n_tiles) {
+        if (!prefetch_s && j + 1 < n_tiles) {
+          // in-order tensor pipe: S_{j+1} may overwrite the S/P buffer right behind PV_j
           mbar_wait(&kv_full[nstage], nphase);
           tc_fence_after();
           issue_s(j + 1, nstage);
@@ -161,12 +171,15 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const uint32_t o_tmem = tmem_base + lane_off + o_col;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t s_tmem = tmem_base + lane_off + ((j & 1) ? TM_S1 : TM_S0);
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      const int sb = j % p.sbuf;
+      const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * AT_TILE);
+      mbar_wait(&s_full[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
       const int kbase = j * AT_TILE;
+      const bool need_mask = (kbase + AT_TILE > p.skv);        // only the last tile (warp-uniform)
       // pass 1: row max
       float mx = -INFINITY;
 #pragma unroll 1
@@ -174,15 +187,26 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         uint32_t rr[32];
         tmem_ld32(s_tmem + (uint32_t)(c * 32), rr);
         tmem_ld_wait();
+        if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kbase + c * 32 + i < p.skv) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          for (int i = 0; i < 32; ++i)
+            if (kbase + c * 32 + i < p.skv) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        } else {
+          float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(rr[i]));
+            m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(rr[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(rr[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float corr = fast_exp2(m_run - m_new);
-      l_run *= corr;
       // pass 2: p = exp2(s*scale - m), write packed bf16 P over the S columns already consumed
-      float lsum = 0.f;
+      float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t rr[32];
@@ -191,20 +215,25 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int k0 = kbase + c * 32 + 2 * i;
-          float p0 = fast_exp2(__uint_as_float(rr[2 * i]) * p.scale_log2 - m_new);
-          float p1 = fast_exp2(__uint_as_float(rr[2 * i + 1]) * p.scale_log2 - m_new);
-          if (k0 >= p.skv) p0 = 0.f;
-          if (k0 + 1 >= p.skv) p1 = 0.f;
-          // sum what the tensor core will actually multiply (bf16-rounded P)
+          float p0 = fast_exp2(fmaf(__uint_as_float(rr[2 * i]), p.scale_log2, -m_new));
+          float p1 = fast_exp2(fmaf(__uint_as_float(rr[2 * i + 1]), p.scale_log2, -m_new));
+          if (need_mask) {
+            const int k0 = kbase + c * 32 + 2 * i;
+            if (k0 >= p.skv) p0 = 0.f;
+            if (k0 + 1 >= p.skv) p1 = 0.f;
+          }
           const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          const float2 pf = __bfloat1622float2(pb);
-          lsum += pf.x + pf.y;
+          if (p.l_col < 0) {
+            // no ones column in V: sum what the tensor core will multiply (bf16-rounded P)
+            const float2 pf = __bfloat1622float2(pb);
+            lsum0 += pf.x;
+            lsum1 += pf.y;
+          }
           pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
         tmem_st16(s_tmem + (uint32_t)(c * 16), pk);
       }
-      l_run += lsum;
+      l_run = l_run * corr + (lsum0 + lsum1);
       m_run = m_new;
       tmem_st_wait();
       if (j > 0) {
@@ -212,9 +241,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
         tc_fence_after();
         if (__any_sync(0xffffffffu, corr != 1.0f)) {
-          const uint32_t o_tmem = tmem_base + lane_off + TM_O;
 #pragma unroll 1
-          for (int c = 0; c < p.d16; c += 16) {
+          for (int c = 0; c < p.dv; c += 16) {
             uint32_t oo[16];
             tmem_ld16(o_tmem + (uint32_t)c, oo);
             tmem_ld_wait();
@@ -227,17 +255,27 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[j & 1]);
+      if (lane == 0) mbar_arrive(&p_ready[sb]);
     }
     // epilogue: O / l
     mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
+    if (p.l_col >= 0) {
+      // the ones column of V made the tensor core accumulate l = sum_j P_j (rescaled with O)
+      uint32_t oo[16];
+      tmem_ld16(o_tmem + (uint32_t)(p.l_col & ~15), oo);
+      tmem_ld_wait();
+      float lv = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.l_col & 15)) lv = __uint_as_float(oo[i]);
+      l_run = lv;
+    }
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + r) < p.sq;
     __nv_bfloat16* orow = p.out + ((long long)b * p.sq + q0 + r) * p.ldo + h * p.d;
-    const uint32_t o_tmem = tmem_base + lane_off + TM_O;
 #pragma unroll 1
-    for (int c = 0; c < p.d16; c += 16) {
+    for (int c = 0; c < p.d; c += 16) {
       uint32_t oo[16];
       tmem_ld16(o_tmem + (uint32_t)c, oo);
       tmem_ld_wait();
@@ -259,35 +297,57 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 static int attn_tc_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                           long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
-                          int skv, int heads, int d, float scale, cudaStream_t stream) {
+                          int skv, int heads, int d, float scale, int v_ones, cudaStream_t stream) {
   DL_CHECK_ARG(d % 8 == 0 && d >= 8, "attention: head dim %d must be a multiple of 8", d);
   const int d16 = (d + 15) / 16 * 16;
-  DL_CHECK_ARG(d16 <= 192, "attention(tc): head dim %d > 192 unsupported (use the GEMM path)", d);
-  DL_CHECK_ARG(dh_stride >= d16 || dh_stride == d,
-               "attention(tc): dh_stride=%d must be >= %d (zero-padded heads) or == d", dh_stride, d16);
   DL_CHECK_ARG(dh_stride % 8 == 0 && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0,
                "attention(tc): strides must be multiples of 8 elements");
-  if (d != d16) DL_CHECK_ARG(dh_stride >= d16, "attention(tc): d=%d needs zero-padded dh_stride >= %d", d, d16);
+  DL_CHECK_ARG(dh_stride >= d16 || (dh_stride == d && d == d16),
+               "attention(tc): d=%d needs a zero-padded per-head stride >= %d (got %d)", d, d16, dh_stride);
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.ldo = ldo;
-  p.sq = sq; p.skv = skv; p.d = d; p.d16 = d16; p.dh_stride = dh_stride;
-  p.nchunk = (d16 + 63) / 64;
+  p.sq = sq; p.skv = skv; p.d = d; p.dh_stride = dh_stride;
+  p.ksteps = d16 / 16;
+  p.nchunk_qk = (d16 + 63) / 64;
+  if (v_ones) {
+    DL_CHECK_ARG(dh_stride >= (d + 1 + 15) / 16 * 16,
+                 "attention(tc): v_ones needs per-head stride >= ceil16(d+1)");
+    p.dv = (d + 1 + 15) / 16 * 16;
+    p.l_col = d;
+  } else {
+    p.dv = d16;
+    p.l_col = -1;
+  }
+  DL_CHECK_ARG(p.dv <= 256, "attention(tc): head dim %d > 240 unsupported (use the GEMM path)", d);
+  p.nchunk_v = (p.dv + 63) / 64;
   p.scale_log2 = scale * 1.4426950408889634f;
-  const int q_bytes = p.nchunk * AT_CHUNK_BYTES;
-  const int budget = 227 * 1024 - 1024 - 256;
-  p.stages = (budget - q_bytes) / (2 * q_bytes);
+  const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
+  const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
+  const int overhead = 1024 + 256;
+  const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
+  const int full_budget = 227 * 1024;
+  if (p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
+    // small heads: 2 CTAs/SM interleave (one softmaxes while the other's MMAs run)
+    p.sbuf = 1;
+    p.tmem_cols = 256;
+    p.stages = (half_budget - overhead - q_bytes) / kv_bytes;
+  } else {
+    p.sbuf = (2 * AT_TILE + p.dv <= 512) ? 2 : 1;
+    p.tmem_cols = 512;
+    p.stages = (full_budget - overhead - q_bytes) / kv_bytes;
+  }
   if (p.stages > 4) p.stages = 4;
   DL_CHECK_ARG(p.stages >= 1, "attention(tc): head dim %d does not fit shared memory", d);
   const uint32_t box[2] = {64, AT_TILE};
   {
-    const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * sq};   // columns owned by Q only
+    const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * sq};
     const uint64_t str[1] = {(uint64_t)ldq * 2};
     if (make_tmap_bf16(&p.tmQ, q, 2, dims, str, box)) return 1;
   }
@@ -301,7 +361,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
     const uint64_t str[1] = {(uint64_t)ldv * 2};
     if (make_tmap_bf16(&p.tmV, v, 2, dims, str, box)) return 1;
   }
-  const int smem_bytes = q_bytes + p.stages * 2 * q_bytes + 1024 + 256;
+  const int smem_bytes = q_bytes + p.stages * kv_bytes + overhead;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -321,7 +381,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
 extern "C" int dl_attention(const void* q, long long ldq, const void* k, long long ldk,
                             const void* v, long long ldv, int dh_stride, void* out, long long ldo,
                             int batch, int sq, int skv, int heads, int d, float scale, int impl,
-                            void* stream_) {
+                            int v_ones, void* stream_) {
   using namespace dl;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DL_CHECK_ARG(q && k && v && out, "attention: null pointer");
@@ -331,5 +391,5 @@ extern "C" int dl_attention(const void* q, long long ldq, const void* k, long lo
                             scale, stream);
   DL_CHECK_ARG(impl == DL_ATTN_TC, "attention: unknown impl %d", impl);
   return attn_tc_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d,
-                        scale, stream);
+                        scale, v_ones, stream);
 }

@@ -1,147 +1,194 @@
 // GroupNorm(+SiLU) and LayerNorm for NHWC bf16 activations (HBM-bound kernels).
 //
-// GroupNorm is two deterministic launches (no float atomics: same seed => same bytes):
-//   1. gn_stats: each CTA reduces a slab of pixels of one image to per-group (mean, M2)
-//      partials (fp32 sums inside the slab, Chan-merged across slabs later);
-//   2. gn_apply: merges the partials (fixed order), builds per-channel scale/shift in smem,
-//      then streams x -> y with 16-byte vector loads/stores, SiLU fused.
-// Both accept two sources and emit the channel concat [x0 | x1] (UNet skip concat folded
+// GroupNorm is ONE persistent cooperative launch (grid <= resident CTAs): the batch is cut into
+// waves of images small enough to stay in the 126 MB L2; per wave every CTA
+//   A. reduces its slab of pixels to per-group (mean, M2) partials (fp32, fixed order),
+//   -- grid barrier --
+//   B. Chan-merges the partials of its image (fixed order => deterministic, no float atomics),
+//      builds per-channel scale/shift in registers and re-reads its slab (an L2 hit: it read it
+//      a few microseconds ago) -> normalise (+SiLU) -> 16-byte stores.
+// HBM traffic is therefore the algorithmic read-once + write-once (4 B/element).
+// Both phases accept two sources and emit the channel concat [x0 | x1] (UNet skip concat folded
 // into the norm: the concat tensor is never written in un-normalised form).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "dreamlab_b200.h"
 
 namespace dl {
 
-constexpr int GN_MAX_CHUNKS = 128;
+constexpr int GN_THREADS = 512;
 constexpr int GN_MAX_C = 2560;
+constexpr int GN_MAX_GROUPS = 64;
+constexpr long long GN_WAVE_BYTES = 40ll << 20;     // input bytes per wave (L2-resident)
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int c0,
                                          const __nv_bfloat16* x1, int c1, long long pix, int v) {
   // vector v covers channels [8v, 8v+8) of the virtual concat
   const int ch = v * 8;
   const __nv_bfloat16* p = (ch < c0) ? (x0 + pix * c0 + ch) : (x1 + pix * c1 + (ch - c0));
-  return __ldg(reinterpret_cast<const uint4*>(p));
+  return *reinterpret_cast<const uint4*>(p);
 }
 
-// grid: (chunks, nimg); block: V*L threads (V = C/8 vectors per pixel, L pixel lanes)
-__global__ void gn_stats_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
-                                const __nv_bfloat16* __restrict__ x1, int c1, int hw, int groups,
-                                int V, int L, float* __restrict__ partial /* [nimg][chunks][G][2] */) {
-  extern __shared__ float sm[];            // [L][C] sums, [L][C] sumsq
-  const int C = c0 + c1;
-  const int cpg = C / groups;
-  const int img = blockIdx.y;
-  const int chunks = gridDim.x;
-  const int ppc = (hw + chunks - 1) / chunks;
-  const int p_begin = blockIdx.x * ppc;
-  const int p_end = min(hw, p_begin + ppc);
-  const int v = threadIdx.x % V;
-  const int l = threadIdx.x / V;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-  for (int p = p_begin + l; p < p_end; p += L) {
-    const uint4 u = ld_vec8(x0, c0, x1, c1, (long long)img * hw + p, v);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(w[j]);
-      s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-      s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-    }
-  }
-  float* ssum = sm;
-  float* ssq = sm + (size_t)L * C;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    ssum[(size_t)l * C + v * 8 + j] = s[j];
-    ssq[(size_t)l * C + v * 8 + j] = q[j];
+struct GnParams {
+  const __nv_bfloat16* x0; int c0;
+  const __nv_bfloat16* x1; int c1;
+  int nimg, hw, groups, V, L;
+  float eps;
+  const float* gamma; const float* beta;
+  int apply_silu;
+  __nv_bfloat16* out;
+  float* partial;            // [2][gridDim][groups][2]
+  unsigned int* counter;     // grid barrier (zeroed before launch)
+  int wave_imgs, slabs;      // images per wave, slabs (CTAs) per image
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(64);
+    __threadfence();
   }
   __syncthreads();
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    float ts = 0.f, tq = 0.f;
-    for (int ll = 0; ll < L; ++ll)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        ts += ssum[(size_t)ll * C + c];
-        tq += ssq[(size_t)ll * C + c];
+}
+
+__global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams p) {
+  __shared__ float s_sum[GN_THREADS * 8];
+  __shared__ float s_sq[GN_THREADS * 8];
+  __shared__ float s_mean[GN_MAX_GROUPS];
+  __shared__ float s_rstd[GN_MAX_GROUPS];
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const int v = threadIdx.x % p.V;
+  const int l = threadIdx.x / p.V;
+  const bool lane_ok = l < p.L;                       // threads beyond V*L idle in the loops
+  const int num_waves = (p.nimg + p.wave_imgs - 1) / p.wave_imgs;
+  const int pps = (p.hw + p.slabs - 1) / p.slabs;     // pixels per slab
+  for (int w = 0; w < num_waves; ++w) {
+    const int item = blockIdx.x;
+    const int img = w * p.wave_imgs + item / p.slabs;
+    const int slab = item % p.slabs;
+    const bool active = (item < p.wave_imgs * p.slabs) && (img < p.nimg);
+    const int p_begin = slab * pps;
+    const int p_end = min(p.hw, p_begin + pps);
+    float* part = p.partial + ((size_t)(w & 1) * gridDim.x) * p.groups * 2;
+    // ---------------- phase A: partial statistics of my slab ----------------
+    if (active) {
+      float s[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      if (lane_ok) {
+        const long long base = (long long)img * p.hw;
+        int px = p_begin + l;
+        for (; px + 3 * p.L < p_end; px += 4 * p.L) {          // 4 independent 16 B loads in flight
+          uint4 u[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ww[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(ww[j]);
+              s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+              s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+            }
+          }
+        }
+        for (; px < p_end; px += p.L) {
+          const uint4 u = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v);
+          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_bf16x2(ww[j]);
+            s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+            s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+          }
+        }
+        // layout [l][C]: channel-contiguous so the per-group gather below is a linear walk
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s_sum[l * C + v * 8 + j] = s[j];
+          s_sq[l * C + v * 8 + j] = q[j];
+        }
       }
-    const float cnt = (float)(p_end - p_begin) * (float)cpg;
-    float mean = 0.f, m2 = 0.f;
-    if (cnt > 0.f) {
-      mean = ts / cnt;
-      m2 = fmaxf(tq - ts * mean, 0.f);
     }
-    float* o = partial + (((size_t)img * chunks + blockIdx.x) * groups + g) * 2;
-    o[0] = mean;
-    o[1] = m2;
-  }
-}
-
-// grid: (pixel blocks, nimg); block 256
-__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0,
-                                const __nv_bfloat16* __restrict__ x1, int c1, int hw, int groups,
-                                int chunks, float eps, const float* __restrict__ partial,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                int apply_silu, __nv_bfloat16* __restrict__ out) {
-  __shared__ float s_scale[GN_MAX_C];
-  __shared__ float s_shift[GN_MAX_C];
-  __shared__ float s_mean[64];
-  __shared__ float s_rstd[64];
-  const int C = c0 + c1;
-  const int cpg = C / groups;
-  const int img = blockIdx.y;
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
-    const int ppc = (hw + chunks - 1) / chunks;
-    // Chan et al. pairwise merge, fixed chunk order (deterministic)
-    float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) {
-      const int pb = ch * ppc;
-      const int pe = min(hw, pb + ppc);
-      if (pe <= pb) break;
-      const float n_b = (float)(pe - pb) * (float)cpg;
-      const float* pp = partial + (((size_t)img * chunks + ch) * groups + g) * 2;
-      const float mean_b = pp[0], m2_b = pp[1];
-      const float n_ab = n_a + n_b;
-      const float delta = mean_b - mean_a;
-      mean_a += delta * (n_b / n_ab);
-      m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
-      n_a = n_ab;
+    __syncthreads();
+    if (active && threadIdx.x < p.groups) {
+      const int g = threadIdx.x;
+      float ts = 0.f, tq = 0.f;
+      for (int ll = 0; ll < p.L; ++ll)
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+          ts += s_sum[ll * C + c];
+          tq += s_sq[ll * C + c];
+        }
+      const float cnt = (float)max(p_end - p_begin, 0) * (float)cpg;
+      float mean = 0.f, m2 = 0.f;
+      if (cnt > 0.f) { mean = ts / cnt; m2 = fmaxf(tq - ts * mean, 0.f); }
+      part[((size_t)item * p.groups + g) * 2 + 0] = mean;
+      part[((size_t)item * p.groups + g) * 2 + 1] = m2;
     }
-    s_mean[g] = mean_a;
-    s_rstd[g] = rsqrtf(m2_a / n_a + eps);
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = s_rstd[g] * gamma[c];
-    s_scale[c] = sc;
-    s_shift[c] = beta[c] - s_mean[g] * sc;
-  }
-  __syncthreads();
-  const int V = C / 8;
-  const long long total = (long long)hw * V;
-  const long long per_block = (total + gridDim.x - 1) / gridDim.x;
-  const long long begin = (long long)blockIdx.x * per_block;
-  const long long end = min(total, begin + per_block);
-  for (long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const long long p = i / V;
-    const int v = (int)(i - p * V);
-    const long long pix = (long long)img * hw + p;
-    const uint4 u = ld_vec8(x0, c0, x1, c1, pix, v);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-    uint32_t o[4];
+    grid_barrier(p.counter, (unsigned int)(w + 1) * gridDim.x);
+    // ---------------- phase B: merge my image's partials, normalise my slab ----------------
+    if (active) {
+      if (threadIdx.x < p.groups) {
+        const int g = threadIdx.x;
+        const int first = (item / p.slabs) * p.slabs;
+        float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+        for (int sidx = 0; sidx < p.slabs; ++sidx) {            // Chan merge, fixed order
+          const int pb = sidx * pps;
+          const int pe = min(p.hw, pb + pps);
+          if (pe <= pb) break;
+          const float n_b = (float)(pe - pb) * (float)cpg;
+          const float* pp = part + ((size_t)(first + sidx) * p.groups + g) * 2;
+          const float mean_b = __ldcg(pp), m2_b = __ldcg(pp + 1);
+          const float n_ab = n_a + n_b;
+          const float delta = mean_b - mean_a;
+          mean_a += delta * (n_b / n_ab);
+          m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
+          n_a = n_ab;
+        }
+        s_mean[g] = mean_a;
+        s_rstd[g] = rsqrtf(m2_a / n_a + p.eps);
+      }
+      __syncthreads();
+      if (lane_ok) {
+        float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 f = unpack_bf16x2(w[j]);
-      const int c = v * 8 + 2 * j;
-      f.x = f.x * s_scale[c] + s_shift[c];
-      f.y = f.y * s_scale[c + 1] + s_shift[c + 1];
-      if (apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
-      o[j] = pack_bf16x2(f.x, f.y);
+        for (int j = 0; j < 8; ++j) {
+          const int c = v * 8 + j;
+          const int g = c / cpg;
+          sc[j] = s_rstd[g] * __ldg(p.gamma + c);
+          sh[j] = __ldg(p.beta + c) - s_mean[g] * sc[j];
+        }
+        const long long base = (long long)img * p.hw;
+        auto emit = [&](const uint4& u, long long pix) {
+          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_bf16x2(ww[j]);
+            f.x = f.x * sc[2 * j] + sh[2 * j];
+            f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+            if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+            o[j] = pack_bf16x2(f.x, f.y);
+          }
+          *reinterpret_cast<uint4*>(p.out + pix * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        };
+        int px = p_begin + l;
+        for (; px + 3 * p.L < p_end; px += 4 * p.L) {
+          uint4 u[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) emit(u[k], base + px + k * p.L);
+        }
+        for (; px < p_end; px += p.L) emit(ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v), base + px);
+      }
     }
-    *reinterpret_cast<uint4*>(out + pix * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    __syncthreads();      // s_sum / s_mean are reused by the next wave
   }
 }
 
@@ -203,17 +250,12 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
-static int gn_chunks(int hw) {
-  int chunks = (hw + 255) / 256;          // >= 256 pixels per slab
-  if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-  if (chunks < 1) chunks = 1;
-  return chunks;
-}
-
 }  // namespace dl
 
 extern "C" size_t dl_groupnorm_workspace_bytes(int nimg, int groups) {
-  return (size_t)nimg * dl::GN_MAX_CHUNKS * groups * 2 * sizeof(float);
+  (void)nimg;
+  // barrier counter (256 B slot) + double-buffered partials for up to 1024 CTAs
+  return 256 + (size_t)2 * 1024 * (groups > 0 ? groups : 32) * 2 * sizeof(float);
 }
 
 extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int nimg, int hw,
@@ -225,31 +267,48 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   DL_CHECK_ARG(x0 && out && workspace && gamma && beta, "groupnorm: null pointer");
   DL_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && C > 0, "groupnorm: channels must be multiples of 8");
   DL_CHECK_ARG(c1 == 0 || x1, "groupnorm: c1>0 needs x1");
-  DL_CHECK_ARG(groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: bad groups=%d for C=%d", groups, C);
+  DL_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0,
+               "groupnorm: bad groups=%d for C=%d", groups, C);
   DL_CHECK_ARG(C <= GN_MAX_C, "groupnorm: C=%d exceeds %d", C, GN_MAX_C);
-  const int V = C / 8;
-  int L = 256 / V;
-  if (L < 1) L = 1;
-  const int threads = V * L;
-  DL_CHECK_ARG(threads <= 1024 && threads >= groups, "groupnorm: unsupported C=%d", C);
-  const int chunks = gn_chunks(hw);
-  const size_t smem = (size_t)2 * L * C * sizeof(float);
-  DL_CHECK_ARG(smem <= 48 * 1024, "groupnorm: smem %zu too large", smem);
-  gn_stats_kernel<<<dim3(chunks, nimg), threads, smem, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1), c1,
-      hw, groups, V, L, reinterpret_cast<float*>(workspace));
-  if (int e = check_launch("gn_stats")) return e;
-  // enough CTAs to fill 148 SMs a few times over, >= 16 KB of work each
-  const long long total_vec = (long long)hw * V;
-  long long blocks = (total_vec + 2047) / 2048;
-  const long long max_blocks = (long long)(num_sms() * 8 + nimg - 1) / nimg;
-  if (blocks > max_blocks) blocks = max_blocks;
-  if (blocks < 1) blocks = 1;
-  gn_apply_kernel<<<dim3((unsigned)blocks, nimg), 256, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x0), c0, reinterpret_cast<const __nv_bfloat16*>(x1), c1,
-      hw, groups, chunks, eps, reinterpret_cast<const float*>(workspace), gamma, beta, apply_silu,
-      reinterpret_cast<__nv_bfloat16*>(out));
-  return check_launch("gn_apply");
+  GnParams p;
+  p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.c0 = c0;
+  p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1); p.c1 = c1;
+  p.nimg = nimg; p.hw = hw; p.groups = groups;
+  p.V = C / 8;
+  DL_CHECK_ARG(p.V <= GN_THREADS, "groupnorm: C=%d too wide", C);
+  p.L = GN_THREADS / p.V;
+  p.eps = eps; p.gamma = gamma; p.beta = beta; p.apply_silu = apply_silu;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.counter = reinterpret_cast<unsigned int*>(workspace);
+  p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  int grid = num_sms();                       // 1 CTA/SM (launch bounds + 33 KB smem): co-resident
+  if (grid > 1024) grid = 1024;
+  const long long img_bytes = (long long)hw * C * 2;
+  long long wave = GN_WAVE_BYTES / (img_bytes > 0 ? img_bytes : 1);
+  if (wave < 1) wave = 1;
+  if (wave > nimg) wave = nimg;
+  if (wave > grid) wave = grid;
+  const long long n_waves = (nimg + wave - 1) / wave;
+  wave = (nimg + n_waves - 1) / n_waves;               // balance the waves (16 -> 8+8, not 15+1)
+  p.wave_imgs = (int)wave;
+  p.slabs = grid / p.wave_imgs;
+  const int max_slabs = (hw + p.L - 1) / p.L;          // at least one pixel per lane row
+  if (p.slabs > max_slabs) p.slabs = max_slabs < 1 ? 1 : max_slabs;
+  cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream);
+  if (e != cudaSuccess) { set_error("groupnorm: memset: %s", cudaGetErrorString(e)); return 2; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // guarantees co-residency for the grid barrier
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, p);
+  if (e != cudaSuccess) { set_error("groupnorm: launch failed: %s", cudaGetErrorString(e)); return 2; }
+  return check_launch("groupnorm");
 }
 
 extern "C" int dl_layernorm(const void* x, long long rows, int c, float eps, const float* gamma,

@@ -92,21 +92,21 @@ def resnet(ctx, x, p: Packed, *, temb=None, x1=None, eps=1e-5, groups=32):
 
 
 def transformer(ctx, x, p: Packed, kv, *, groups=32):
-    """Transformer2DModel (1 BasicTransformerBlock).  kv: hoisted cross-attn [B*77, 2*heads*d16]."""
+    """Transformer2DModel (1 BasicTransformerBlock).  kv: hoisted cross-attn [B*77, 2*heads*hstride]."""
     B, H, W, C = x.shape
     S = H * W
-    heads, d, d16 = p["heads"], p["d"], p["d16"]
-    hs = heads * d16
+    heads, d, hstride = p["heads"], p["d"], p["hstride"]
+    hs = heads * hstride
     scale = 1.0 / math.sqrt(d)
     hn = groupnorm(ctx, x, p["norm_w"], p["norm_b"], eps=1e-6, silu=False, groups=groups)
     h = linear(ctx, hn.view(B * S, C), p["proj_in_w"], p["proj_in_b"], C)
     # --- self attention
     n1 = ctx.empty(B * S, C)
     lib.layernorm(h, n1, p["ln1_w"], p["ln1_b"])
-    qkv = linear(ctx, n1, p["qkv_w"], None, 3 * hs)
+    qkv = linear(ctx, n1, p["qkv_w"], p["qkv_b"], 3 * hs)
     a = ctx.empty(B * S, C)
     lib.attention(qkv, qkv[:, hs:], qkv[:, 2 * hs:], a, batch=B, sq=S, skv=S, heads=heads, d=d,
-                  dh_stride=d16, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale)
+                  dh_stride=hstride, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale, v_ones=True)
     h = linear(ctx, a, p["o1_w"], p["o1_b"], C, residual=h)
     # --- cross attention (K/V precomputed once per request)
     n2 = ctx.empty(B * S, C)
@@ -114,8 +114,8 @@ def transformer(ctx, x, p: Packed, kv, *, groups=32):
     q = linear(ctx, n2, p["q2_w"], None, hs)
     skv = kv.shape[0] // B
     a2 = ctx.empty(B * S, C)
-    lib.attention(q, kv, kv[:, hs:], a2, batch=B, sq=S, skv=skv, heads=heads, d=d, dh_stride=d16,
-                  ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale)
+    lib.attention(q, kv, kv[:, hs:], a2, batch=B, sq=S, skv=skv, heads=heads, d=d, dh_stride=hstride,
+                  ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale, v_ones=True)
     h = linear(ctx, a2, p["o2_w"], p["o2_b"], C, residual=h)
     # --- GEGLU feed-forward
     n3 = ctx.empty(B * S, C)
@@ -159,7 +159,8 @@ class UNetB200:
         B, T, D = prompt_embeds.shape
         ctx = _Ctx(self.device, B)
         pe = prompt_embeds.to(self.device, BF16).contiguous().view(B * T, D)
-        return [linear(ctx, pe, t["kv2_w"], None, 2 * t["heads"] * t["d16"]) for t in self.P["transformers"]]
+        return [linear(ctx, pe, t["kv2_w"], t["kv2_b"], 2 * t["heads"] * t["hstride"])
+                for t in self.P["transformers"]]
 
     @torch.no_grad()
     def time_embeddings(self, timesteps: List[int], batch: int, w_emb: Optional[torch.Tensor]):

@@ -73,7 +73,7 @@ def load() -> C.CDLL:
             lib.dl_attention.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                          C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                         C.c_int, C.c_void_p]
+                                         C.c_int, C.c_int, C.c_void_p]
             lib.dl_timestep_sinusoid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
             lib.dl_small_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
@@ -227,11 +227,11 @@ def layernorm(x, out, gamma, beta, eps=1e-5):
 
 
 def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ldv, ldo, scale,
-              impl=ATTN_TC):
+              impl=ATTN_TC, v_ones=False):
     with _timed("attention", 4.0 * batch * heads * sq * skv * d):
         _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
                                    out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
-                                   _stream()), "attention")
+                                   int(v_ones), _stream()), "attention")
     _count()
 
 

@@ -43,16 +43,30 @@ def pack_conv1x1(w: torch.Tensor, device) -> torch.Tensor:
     return _bf(w.reshape(w.shape[0], -1), device)
 
 
+def head_stride(d: int) -> int:
+    """Per-head column stride of the packed Q/K/V: room for d values, zero padding up to a
+    multiple of 16 (tcgen05 K-steps) and one extra column that holds 1.0 in V (the PV MMA then
+    accumulates the softmax denominator for free)."""
+    return ceil16(d + 1)
+
+
 def pad_heads(w: torch.Tensor, heads: int) -> torch.Tensor:
-    """[heads*d, K] -> [heads*d16, K] with zero rows after each head's d rows."""
+    """[heads*d, K] -> [heads*stride, K] with zero rows after each head's d rows."""
     c, k = w.shape
     d = c // heads
-    d16 = ceil16(d)
-    if d16 == d:
-        return w
-    out = w.new_zeros(heads, d16, k)
+    hs = head_stride(d)
+    out = w.new_zeros(heads, hs, k)
     out[:, :d] = w.view(heads, d, k)
-    return out.reshape(heads * d16, k)
+    return out.reshape(heads * hs, k)
+
+
+def ones_bias(heads: int, d: int, sections: int, v_section: int) -> torch.Tensor:
+    """fp32 bias for a fused projection of `sections` head-padded blocks: 1.0 in column d of
+    every head of the V block (its weight rows are zero), 0 elsewhere."""
+    hs = head_stride(d)
+    b = torch.zeros(sections, heads, hs)
+    b[v_section, :, d] = 1.0
+    return b.reshape(-1)
 
 
 def interleave_geglu(w: torch.Tensor) -> torch.Tensor:
@@ -91,15 +105,17 @@ def pack_transformer(sd, prefix: str, heads: int, device) -> Packed:
     b = prefix + "transformer_blocks.0."
     c = sd[b + "attn1.to_q.weight"].shape[0]
     p["c"], p["heads"], p["d"] = c, heads, c // heads
-    p["d16"] = ceil16(c // heads)
+    p["hstride"] = head_stride(c // heads)
     for i in (1, 2, 3):
         p[f"ln{i}_w"], p[f"ln{i}_b"] = _f32(sd[b + f"norm{i}.weight"], device), _f32(sd[b + f"norm{i}.bias"], device)
     qkv = torch.cat([pad_heads(sd[b + f"attn1.to_{n}.weight"].float(), heads) for n in "qkv"], 0)
     p["qkv_w"] = _bf(qkv, device)
+    p["qkv_b"] = _f32(ones_bias(heads, c // heads, 3, 2), device)
     p["o1_w"], p["o1_b"] = _bf(sd[b + "attn1.to_out.0.weight"], device), _f32(sd[b + "attn1.to_out.0.bias"], device)
     p["q2_w"] = _bf(pad_heads(sd[b + "attn2.to_q.weight"].float(), heads), device)
     kv = torch.cat([pad_heads(sd[b + f"attn2.to_{n}.weight"].float(), heads) for n in "kv"], 0)
     p["kv2_w"] = _bf(kv, device)
+    p["kv2_b"] = _f32(ones_bias(heads, c // heads, 2, 1), device)
     p["o2_w"], p["o2_b"] = _bf(sd[b + "attn2.to_out.0.weight"], device), _f32(sd[b + "attn2.to_out.0.bias"], device)
     p["ff1_w"] = _bf(interleave_geglu(sd[b + "ff.net.0.proj.weight"].float()), device)
     p["ff1_b"] = _f32(interleave_geglu(sd[b + "ff.net.0.proj.bias"].float()), device)

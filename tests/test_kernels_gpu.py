@@ -161,9 +161,9 @@ def test_layernorm(rows, C):
 
 
 # ------------------------------------------------------------------ attention
-def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0):
+def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0, v_ones=False):
     d16 = (d + 15) // 16 * 16
-    hs = d16                       # zero-padded per-head stride
+    hs = (d + 1 + 15) // 16 * 16 if v_ones else d16      # zero-padded per-head stride
     q = torch.zeros(B * Sq, heads * hs, device=DEV, dtype=torch.bfloat16)
     k = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
     v = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
@@ -171,10 +171,12 @@ def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0):
     q.view(B, Sq, heads, hs)[..., :d] = qr
     k.view(B, Skv, heads, hs)[..., :d] = kr
     v.view(B, Skv, heads, hs)[..., :d] = vr
+    if v_ones:
+        v.view(B, Skv, heads, hs)[..., d] = 1.0
     out = torch.zeros(B * Sq, heads * d, device=DEV, dtype=torch.bfloat16)
     lib.attention(q, k, v, out, batch=B, sq=Sq, skv=Skv, heads=heads, d=d, dh_stride=hs,
                   ldq=heads * hs, ldk=heads * hs, ldv=heads * hs, ldo=heads * d,
-                  scale=1 / math.sqrt(d), impl=impl)
+                  scale=1 / math.sqrt(d), impl=impl, v_ones=v_ones)
     ref = F.scaled_dot_product_attention(qr.float().transpose(1, 2), kr.float().transpose(1, 2),
                                          vr.float().transpose(1, 2)).transpose(1, 2)
     torch.cuda.synchronize()
@@ -197,6 +199,8 @@ def test_attention_simt(B, Sq, Skv, heads, d):
 def test_attention_tc(B, Sq, Skv, heads, d):
     e = _attn_case(L(), B, Sq, Skv, heads, d, 0)
     assert e < 2e-2, f"rel err {e}"
+    e1 = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True)     # denominator on the tensor core
+    assert e1 < 2e-2, f"rel err (v_ones) {e1}"
 
 
 # ------------------------------------------------------------------ elementwise / scheduler
