@@ -15,8 +15,9 @@
 //   * weights [N, taps*C] K-major bf16, one 2-D TMA box (64 x BN) per k-block.
 //   * both land in 128B-swizzled K-major smem tiles = the canonical UMMA operand layout.
 //   * warp-specialised persistent CTA (1 per SM): warp0 TMA producer, warp1 MMA issuer
-//     (single elected thread, tcgen05.mma M=128 x N=BN x K=16), warps 2-5 epilogue
-//     (tcgen05.ld -> registers -> fused epilogue -> global).  Accumulators double-buffered in
+//     (single elected thread, tcgen05.mma M=128 x N=BN x K=16), warps 2-9 epilogue
+//     (tcgen05.ld -> registers -> fused epilogue -> global; two warps per TMEM lane quadrant,
+//     residual rows prefetched one chunk ahead).  Accumulators double-buffered in
 //     TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * BN is a runtime parameter (any multiple of 16 up to 256): UMMA N is encoded in the
 //     runtime instruction descriptor, the box size in the tensor map.
@@ -28,7 +29,7 @@ namespace dl {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int IGEMM_THREADS = 192;
+constexpr int IGEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
 
 struct IgemmParams {
@@ -81,7 +82,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);     // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);     // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -162,13 +163,15 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two warps per TMEM lane quadrant) ===========
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;                // which interleaved set of 32-column chunks
     const int r = quad * 32 + lane;                  // row of the 128-row tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tw_mask = (1 << p.tw_log2) - 1;
     const int th_mask = (1 << p.th_log2) - 1;
+    const bool has_res = (p.residual != nullptr) && (p.mode == DL_EPI_BF16);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles;
       int m = t / p.n_tiles;
@@ -181,87 +184,123 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + (r >> (p.tw_log2 + p.th_log2));
       const bool valid = (x < p.W) && (y < p.H) && (n < p.NIMG);
       const long long row = ((long long)n * p.H + y) * p.W + x;
+      const int col0 = n_blk * p.BN;
+      const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr : nullptr;
+      const float* ra_row = p.rowadd ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
+
+      // residual for this warp's first chunk is requested before the accumulator is even ready
+      uint4 rv[4];
+      auto load_res = [&](int c) {
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          rv[q4] = make_uint4(0, 0, 0, 0);
+          const int cc = col0 + c + q4 * 8;
+          if (has_res && valid && c + q4 * 8 < p.BN && cc + 8 <= p.N)
+            rv[q4] = __ldg(reinterpret_cast<const uint4*>(res_row + cc));
+        }
+      };
+      load_res(half * 32);
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c = 0; c < p.BN; c += 16) {
-        uint32_t rr[16];
-        tmem_ld16(t_row + (uint32_t)c, rr);
+      for (int c = half * 32; c < p.BN; c += 64) {
+        uint32_t rr[32];
+        tmem_ld32(t_row + (uint32_t)c, rr);          // may read past BN: still inside the allocation
         tmem_ld_wait();
-        const int col = n_blk * p.BN + c;
-        if (valid && col < p.N) {
-        float v[16];
+        uint4 rcur[4] = {rv[0], rv[1], rv[2], rv[3]};
+        if (c + 64 < p.BN) load_res(c + 64);         // prefetch the next chunk's residual
+        const int col = col0 + c;
+        const int ncols = min(min(32, p.BN - c), p.N - col);
+        if (valid && ncols > 0) {
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-        const int ncols = min(16, p.N - col);
-        if (p.bias != nullptr) {
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < ncols) v[j] += __ldg(p.bias + col + j);
-        }
-        if (p.rowadd != nullptr) {
-          const float* ra = p.rowadd + (long long)n * p.ld_rowadd + col;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (j4 * 4 + 4 <= ncols) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + j4 * 4));
+                v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+              } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < ncols) v[j] += __ldg(ra + j);
-        }
-        if (p.mode == DL_EPI_BF16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h * 8 + 8 > ncols) break;
-            if (p.residual != nullptr) {
-              const uint4 rv =
-                  __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col + h * 8));
-              const uint32_t ru[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 f = unpack_bf16x2(ru[j]);
-                v[h * 8 + 2 * j] += f.x;
-                v[h * 8 + 2 * j + 1] += f.y;
+                for (int j = 0; j < 4; ++j)
+                  if (j4 * 4 + j < ncols) v[j4 * 4 + j] += __ldg(p.bias + col + j4 * 4 + j);
               }
             }
-            uint4 ov;
-            ov.x = pack_bf16x2(v[h * 8 + 0], v[h * 8 + 1]);
-            ov.y = pack_bf16x2(v[h * 8 + 2], v[h * 8 + 3]);
-            ov.z = pack_bf16x2(v[h * 8 + 4], v[h * 8 + 5]);
-            ov.w = pack_bf16x2(v[h * 8 + 6], v[h * 8 + 7]);
-            *reinterpret_cast<uint4*>(o + h * 8) = ov;
           }
-        } else if (p.mode == DL_EPI_GEGLU) {
-          // interleaved columns: even = value, odd = gate  ->  out col = col/2 + j
-          if (ncols == 16) {
-            float g[8];
+          if (ra_row != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[j] = v[2 * j] * gelu_erf_f(v[2 * j + 1]);
-            uint4 ov;
-            ov.x = pack_bf16x2(g[0], g[1]);
-            ov.y = pack_bf16x2(g[2], g[3]);
-            ov.z = pack_bf16x2(g[4], g[5]);
-            ov.w = pack_bf16x2(g[6], g[7]);
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col >> 1);
-            *reinterpret_cast<uint4*>(o) = ov;
-          }
-        } else if (p.mode == DL_EPI_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              if (j4 * 4 + 4 <= ncols) {
+                const float4 bv = __ldg(reinterpret_cast<const float4*>(ra_row + col + j4 * 4));
+                v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+              } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < ncols) o[j] = v[j];
-        } else if (p.mode == DL_EPI_U8_IMAGE) {
-          // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
-          uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (j < ncols) {
-              // image is bf16-rounded first (the decoder output dtype), like the reference's
-              // dtype-typed vae output
-              const float xb = __bfloat162float(__float2bfloat16(v[j]));
-              const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
-              o[j] = (uint8_t)__float2int_rn(f);
+                for (int j = 0; j < 4; ++j)
+                  if (j4 * 4 + j < ncols) v[j4 * 4 + j] += __ldg(ra_row + col + j4 * 4 + j);
+              }
             }
-        }
-      }  // valid
+          }
+          if (p.mode == DL_EPI_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+#pragma unroll
+            for (int h8 = 0; h8 < 4; ++h8) {
+              if (h8 * 8 + 8 <= ncols) {
+                if (has_res) {
+                  const uint32_t ru[4] = {rcur[h8].x, rcur[h8].y, rcur[h8].z, rcur[h8].w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(ru[j]);
+                    v[h8 * 8 + 2 * j] += f.x;
+                    v[h8 * 8 + 2 * j + 1] += f.y;
+                  }
+                }
+                uint4 ov;
+                ov.x = pack_bf16x2(v[h8 * 8 + 0], v[h8 * 8 + 1]);
+                ov.y = pack_bf16x2(v[h8 * 8 + 2], v[h8 * 8 + 3]);
+                ov.z = pack_bf16x2(v[h8 * 8 + 4], v[h8 * 8 + 5]);
+                ov.w = pack_bf16x2(v[h8 * 8 + 6], v[h8 * 8 + 7]);
+                *reinterpret_cast<uint4*>(o + h8 * 8) = ov;
+              }
+            }
+          } else if (p.mode == DL_EPI_GEGLU) {
+            // interleaved columns: even = value, odd = gate  ->  out col = col/2 + j
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col >> 1);
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {
+              if (h16 * 16 + 16 <= ncols) {
+                float g[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  g[j] = v[h16 * 16 + 2 * j] * gelu_erf_f(v[h16 * 16 + 2 * j + 1]);
+                uint4 ov;
+                ov.x = pack_bf16x2(g[0], g[1]);
+                ov.y = pack_bf16x2(g[2], g[3]);
+                ov.z = pack_bf16x2(g[4], g[5]);
+                ov.w = pack_bf16x2(g[6], g[7]);
+                *reinterpret_cast<uint4*>(o + h16 * 8) = ov;
+              }
+            }
+          } else if (p.mode == DL_EPI_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) o[j] = v[j];
+          } else if (p.mode == DL_EPI_U8_IMAGE) {
+            // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) {
+                // image is bf16-rounded first (the decoder output dtype), like the reference's
+                // dtype-typed vae output
+                const float xb = __bfloat162float(__float2bfloat16(v[j]));
+                const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
+                o[j] = (uint8_t)__float2int_rn(f);
+              }
+          }
+        }  // valid
         __syncwarp();
       }
       tc_fence_before();
