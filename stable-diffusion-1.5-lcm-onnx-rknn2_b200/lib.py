@@ -126,11 +126,14 @@ def _count(n=1):
 
 # ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----
 _prof = None
+_prof_detail = False
 
 
-def profile_begin():
-    global _prof
+def profile_begin(detail: bool = False):
+    """detail=True keys the result by kernel AND shape tag (per-shape efficiency tables)."""
+    global _prof, _prof_detail
     _prof = []
+    _prof_detail = detail
 
 
 def profile_end():
@@ -138,7 +141,9 @@ def profile_end():
     global _prof
     torch.cuda.synchronize()
     out = {}
-    for name, flops, nbytes, a, b in _prof:
+    for name, flops, nbytes, a, b, tag in _prof:
+        if _prof_detail:
+            name = f"{name} {tag}"
         d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         d["ms"] += a.elapsed_time(b)
         d["flops"] += flops
@@ -149,10 +154,10 @@ def profile_end():
 
 
 class _timed:
-    __slots__ = ("name", "flops", "nbytes", "a")
+    __slots__ = ("name", "flops", "nbytes", "a", "tag")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.nbytes = name, flops, nbytes
+    def __init__(self, name, flops=0.0, nbytes=0.0, tag=""):
+        self.name, self.flops, self.nbytes, self.tag = name, flops, nbytes, tag
 
     def __enter__(self):
         if _prof is not None:
@@ -163,7 +168,7 @@ class _timed:
         if _prof is not None and exc[0] is None:
             b = torch.cuda.Event(enable_timing=True)
             b.record()
-            _prof.append((self.name, self.flops, self.nbytes, self.a, b))
+            _prof.append((self.name, self.flops, self.nbytes, self.a, b, self.tag))
         return False
 
 
@@ -199,7 +204,9 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.residual = _ptr(residual)
     d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
     d.mode, d.alpha, d.bn = mode, alpha, bn
-    with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1)):
+    with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1),
+                tag=f"M={nimg * h * w} ({nimg}x{h}x{w}) N={n} K={taps}x{d.c0 + d.c1} mode={mode}"
+                    f"{' +res' if residual is not None else ''}"):
         _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
     _count()
 
@@ -211,7 +218,7 @@ def groupnorm_workspace_bytes(nimg, groups=32):
 def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5, silu=True, x1=None):
     c0 = x0.shape[-1]
     c1 = x1.shape[-1] if x1 is not None else 0
-    with _timed("groupnorm", 0.0, 4.0 * nimg * hw * (c0 + c1)):
+    with _timed("groupnorm", 0.0, 4.0 * nimg * hw * (c0 + c1), tag=f"n={nimg} hw={hw} C={c0}+{c1}"):
         _check(load().dl_groupnorm(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
                                    gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
                                    workspace.data_ptr(), _stream()), "groupnorm")
@@ -228,7 +235,8 @@ def layernorm(x, out, gamma, beta, eps=1e-5):
 
 def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ldv, ldo, scale,
               impl=ATTN_TC, v_ones=False):
-    with _timed("attention", 4.0 * batch * heads * sq * skv * d):
+    with _timed("attention", 4.0 * batch * heads * sq * skv * d,
+                tag=f"B={batch} Sq={sq} Skv={skv} h={heads} d={d}"):
         _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
                                    out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
                                    int(v_ones), _stream()), "attention")
