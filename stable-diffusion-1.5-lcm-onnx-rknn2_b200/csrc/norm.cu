@@ -116,42 +116,70 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
       }
     }
     __syncthreads();
-    if (active && threadIdx.x < p.groups) {
-      const int g = threadIdx.x;
-      float ts = 0.f, tq = 0.f;
-      for (int ll = 0; ll < p.L; ++ll)
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+    if (active) {
+      // one warp per group (round-robin): lanes stride over the L x cpg partial sums, then a
+      // fixed-order shuffle tree => deterministic
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int nvals = p.L * cpg;
+      for (int g = warp; g < p.groups; g += GN_THREADS / 32) {
+        float ts = 0.f, tq = 0.f;
+        for (int i = lane; i < nvals; i += 32) {
+          const int ll = i / cpg, c = g * cpg + (i - ll * cpg);
           ts += s_sum[ll * C + c];
           tq += s_sq[ll * C + c];
         }
-      const float cnt = (float)max(p_end - p_begin, 0) * (float)cpg;
-      float mean = 0.f, m2 = 0.f;
-      if (cnt > 0.f) { mean = ts / cnt; m2 = fmaxf(tq - ts * mean, 0.f); }
-      part[((size_t)item * p.groups + g) * 2 + 0] = mean;
-      part[((size_t)item * p.groups + g) * 2 + 1] = m2;
+        ts = warp_sum(ts);
+        tq = warp_sum(tq);
+        if (lane == 0) {
+          const float cnt = (float)max(p_end - p_begin, 0) * (float)cpg;
+          float mean = 0.f, m2 = 0.f;
+          if (cnt > 0.f) { mean = ts / cnt; m2 = fmaxf(tq - ts * mean, 0.f); }
+          part[((size_t)item * p.groups + g) * 2 + 0] = mean;
+          part[((size_t)item * p.groups + g) * 2 + 1] = m2;
+        }
+      }
     }
     grid_barrier(p.counter, (unsigned int)(w + 1) * gridDim.x);
     // ---------------- phase B: merge my image's partials, normalise my slab ----------------
     if (active) {
-      if (threadIdx.x < p.groups) {
-        const int g = threadIdx.x;
+      {
+        // Chan merge of the image's slab partials: warp per group, lane i folds slabs
+        // i, i+32, ... (all loads issued up front), then a fixed shuffle tree => deterministic
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int first = (item / p.slabs) * p.slabs;
-        float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
-        for (int sidx = 0; sidx < p.slabs; ++sidx) {            // Chan merge, fixed order
-          const int pb = sidx * pps;
-          const int pe = min(p.hw, pb + pps);
-          if (pe <= pb) break;
-          const float n_b = (float)(pe - pb) * (float)cpg;
-          const float* pp = part + ((size_t)(first + sidx) * p.groups + g) * 2;
-          const float mean_b = __ldcg(pp), m2_b = __ldcg(pp + 1);
-          const float n_ab = n_a + n_b;
-          const float delta = mean_b - mean_a;
-          mean_a += delta * (n_b / n_ab);
-          m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
-          n_a = n_ab;
+        for (int g = warp; g < p.groups; g += GN_THREADS / 32) {
+          float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+          for (int sidx = lane; sidx < p.slabs; sidx += 32) {
+            const int pb = sidx * pps;
+            const int pe = min(p.hw, pb + pps);
+            if (pe <= pb) continue;
+            const float n_b = (float)(pe - pb) * (float)cpg;
+            const float2 mm = __ldcg(reinterpret_cast<const float2*>(
+                part + ((size_t)(first + sidx) * p.groups + g) * 2));
+            const float n_ab = n_a + n_b;
+            const float delta = mm.x - mean_a;
+            mean_a += delta * (n_b / n_ab);
+            m2_a += mm.y + delta * delta * (n_a * n_b / n_ab);
+            n_a = n_ab;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const float n_b = __shfl_down_sync(0xffffffffu, n_a, o);
+            const float mean_b = __shfl_down_sync(0xffffffffu, mean_a, o);
+            const float m2_b = __shfl_down_sync(0xffffffffu, m2_a, o);
+            const float n_ab = n_a + n_b;
+            if (n_ab > 0.f && n_b > 0.f) {
+              const float delta = mean_b - mean_a;
+              mean_a += delta * (n_b / n_ab);
+              m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
+              n_a = n_ab;
+            }
+          }
+          if (lane == 0) {
+            s_mean[g] = mean_a;
+            s_rstd[g] = rsqrtf(m2_a / n_a + p.eps);
+          }
         }
-        s_mean[g] = mean_a;
-        s_rstd[g] = rsqrtf(m2_a / n_a + p.eps);
       }
       __syncthreads();
       if (lane_ok) {
