@@ -65,12 +65,16 @@ typedef struct dl_igemm_desc {
   int ld_rowadd;
   const void* residual;      /* bf16 [pixels, ldr] or NULL (DL_EPI_BF16 only)                 */
   long long ldr;
+  const void* identity;      /* 256x256 bf16 identity (dl_fill_identity); needed with residual:
+                                the add runs on the tensor core as out += R . I                */
   int mode;                  /* DL_EPI_*                                                      */
   float alpha;               /* accumulator scale (0 -> 1)                                    */
   int bn;                    /* N tile (multiple of 16, <=256); 0 = auto                      */
 } dl_igemm_desc;
 
 int dl_igemm(const dl_igemm_desc* desc, void* stream);
+/* fills a caller-owned 256x256 bf16 device buffer (128 KB) with the identity matrix            */
+int dl_fill_identity(void* dst_bf16_256x256, void* stream);
 
 /* ---- GroupNorm (+SiLU), NHWC bf16, optional two-source concat ---------------------------- *
  * Replaces torch.nn.GroupNorm + F.silu in ResnetBlock2D.norm1/norm2, conv_norm_out,

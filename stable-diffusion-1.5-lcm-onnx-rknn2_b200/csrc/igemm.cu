@@ -32,8 +32,15 @@ constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int IGEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue warps
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
 
+constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
+constexpr int EPI_STAGING_BYTES = 4 * EPI_BUF_BYTES;   // 2 epilogue halves x double buffer
+
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmB;
+  CUtensorMap tmOut;     // bf16 output, box {32, tw, th, tn}, 64B swizzle (TMA store)
+  CUtensorMap tmR;       // residual as an extra A source (box like tmA0)
+  CUtensorMap tmI;       // 256x256 bf16 identity as its B operand (box {64, BN})
+  int res_chunks;        // ceil(BN/64) when a residual is fused, else 0
   int tw_log2, th_log2;
   int tiles_x, tiles_y, tiles_n;
   int W, H, NIMG;
@@ -59,7 +66,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
                                              ~uintptr_t(1023));
   const int b_tile_bytes = p.BN * BK * 2;
   const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;         // 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -76,6 +84,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmB);
     if (p.kc1 > 0) tma_prefetch_desc(&p.tmA1);
+    if (p.res_chunks > 0) { tma_prefetch_desc(&p.tmR); tma_prefetch_desc(&p.tmI); }
+    if (p.mode == DL_EPI_BF16 || p.mode == DL_EPI_GEGLU) tma_prefetch_desc(&p.tmOut);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -127,6 +137,17 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
+        // fused residual: out += R . I  (R tile as A, 64-column identity slice as B): the add
+        // happens exactly in the fp32 accumulator and rides the same deep TMA pipeline
+        for (int rc = 0; rc < p.res_chunks; ++rc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_4d(sa, &p.tmR, &full_bar[stage], n_blk * p.BN + rc * BK, x0, y0, n0);
+          tma_load_2d(sb, &p.tmI, &full_bar[stage], rc * BK, 0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -141,7 +162,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb + p.res_chunks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -164,14 +185,22 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     }
   } else {
     // ===================== epilogue (warps 2..9: two warps per TMEM lane quadrant) ===========
+    // Each half (4 warps = the 128 rows of the tile) takes every other 32-column output chunk:
+    // tcgen05.ld -> fp32 epilogue math -> bf16 -> swizzled smem staging -> TMA store (the store
+    // clips partial tiles and streams out asynchronously; no per-thread global traffic).
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;                // which interleaved set of 32-column chunks
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;                  // row of the 128-row tile
+    const bool leader = (threadIdx.x == 64 + 128 * half);
+    const int bar_id = 1 + half;
+    uint8_t* my_staging = staging + half * 2 * EPI_BUF_BYTES;
+    int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tw_mask = (1 << p.tw_log2) - 1;
     const int th_mask = (1 << p.th_log2) - 1;
-    const bool has_res = (p.residual != nullptr) && (p.mode == DL_EPI_BF16);
+    const bool staged = (p.mode == DL_EPI_BF16 || p.mode == DL_EPI_GEGLU);
+    const int step = (p.mode == DL_EPI_GEGLU) ? 64 : 32;       // accumulator columns per chunk
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int n_blk = t % p.n_tiles;
       int m = t / p.n_tiles;
@@ -179,110 +208,97 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
       const int tn = m / p.tiles_y;
-      const int x = (tx << p.tw_log2) + (r & tw_mask);
-      const int y = (ty << p.th_log2) + ((r >> p.tw_log2) & th_mask);
-      const int n = (tn << (7 - p.tw_log2 - p.th_log2)) + (r >> (p.tw_log2 + p.th_log2));
+      const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << (7 - p.tw_log2 - p.th_log2);
+      const int x = x0 + (r & tw_mask);
+      const int y = y0 + ((r >> p.tw_log2) & th_mask);
+      const int n = n0 + (r >> (p.tw_log2 + p.th_log2));
       const bool valid = (x < p.W) && (y < p.H) && (n < p.NIMG);
       const long long row = ((long long)n * p.H + y) * p.W + x;
       const int col0 = n_blk * p.BN;
-      const __nv_bfloat16* res_row = has_res ? p.residual + row * p.ldr : nullptr;
-      const float* ra_row = p.rowadd ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
-
-      // residual for this warp's first chunk is requested before the accumulator is even ready
-      uint4 rv[4];
-      auto load_res = [&](int c) {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          rv[q4] = make_uint4(0, 0, 0, 0);
-          const int cc = col0 + c + q4 * 8;
-          if (has_res && valid && c + q4 * 8 < p.BN && cc + 8 <= p.N)
-            rv[q4] = __ldg(reinterpret_cast<const uint4*>(res_row + cc));
-        }
-      };
-      load_res(half * 32);
+      const float* ra_row = (p.rowadd && n < p.NIMG) ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c = half * 32; c < p.BN; c += 64) {
-        uint32_t rr[32];
-        tmem_ld32(t_row + (uint32_t)c, rr);          // may read past BN: still inside the allocation
-        tmem_ld_wait();
-        uint4 rcur[4] = {rv[0], rv[1], rv[2], rv[3]};
-        if (c + 64 < p.BN) load_res(c + 64);         // prefetch the next chunk's residual
-        const int col = col0 + c;
-        const int ncols = min(min(32, p.BN - c), p.N - col);
-        if (valid && ncols > 0) {
-          float v[32];
+      for (int c = half * step; c < p.BN; c += 2 * step) {
+        float v[64];
+        {
+          uint32_t rr[32];
+          tmem_ld32(t_row + (uint32_t)c, rr);        // may read past BN: still inside the allocation
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-          if (p.bias != nullptr) {
+          if (step == 64) {
+            tmem_ld32(t_row + (uint32_t)(c + 32), rr);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              if (j4 * 4 + 4 <= ncols) {
+            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(rr[j]) * p.alpha;
+          }
+        }
+        const int col = col0 + c;
+        const int ncols = min(min(step, p.BN - c), p.N - col);
+        if (ncols > 0) {
+#pragma unroll
+          for (int j4 = 0; j4 < 16; ++j4) {
+            if (j4 * 4 >= step) break;
+            if (j4 * 4 + 4 <= ncols) {
+              if (p.bias != nullptr) {
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + j4 * 4));
                 v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j4 * 4 + j < ncols) v[j4 * 4 + j] += __ldg(p.bias + col + j4 * 4 + j);
               }
-            }
-          }
-          if (ra_row != nullptr) {
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              if (j4 * 4 + 4 <= ncols) {
+              if (ra_row != nullptr) {
                 const float4 bv = __ldg(reinterpret_cast<const float4*>(ra_row + col + j4 * 4));
                 v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
-              } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (j4 * 4 + j < ncols) v[j4 * 4 + j] += __ldg(ra_row + col + j4 * 4 + j);
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j4 * 4 + j < ncols) {
+                  if (p.bias != nullptr) v[j4 * 4 + j] += __ldg(p.bias + col + j4 * 4 + j);
+                  if (ra_row != nullptr) v[j4 * 4 + j] += __ldg(ra_row + col + j4 * 4 + j);
+                }
             }
           }
-          if (p.mode == DL_EPI_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col;
+        }
+        if (staged) {
+          uint4 ov[4];
+          if (p.mode == DL_EPI_GEGLU) {
+            // interleaved columns: even = value, odd = gate -> 32 outputs from 64 accumulators
 #pragma unroll
-            for (int h8 = 0; h8 < 4; ++h8) {
-              if (h8 * 8 + 8 <= ncols) {
-                if (has_res) {
-                  const uint32_t ru[4] = {rcur[h8].x, rcur[h8].y, rcur[h8].z, rcur[h8].w};
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float g[8];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16x2(ru[j]);
-                    v[h8 * 8 + 2 * j] += f.x;
-                    v[h8 * 8 + 2 * j + 1] += f.y;
-                  }
-                }
-                uint4 ov;
-                ov.x = pack_bf16x2(v[h8 * 8 + 0], v[h8 * 8 + 1]);
-                ov.y = pack_bf16x2(v[h8 * 8 + 2], v[h8 * 8 + 3]);
-                ov.z = pack_bf16x2(v[h8 * 8 + 4], v[h8 * 8 + 5]);
-                ov.w = pack_bf16x2(v[h8 * 8 + 6], v[h8 * 8 + 7]);
-                *reinterpret_cast<uint4*>(o + h8 * 8) = ov;
-              }
+              for (int j = 0; j < 8; ++j)
+                g[j] = v[q4 * 16 + 2 * j] * gelu_erf_f(v[q4 * 16 + 2 * j + 1]);
+              ov[q4] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
+                                  pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
             }
-          } else if (p.mode == DL_EPI_GEGLU) {
-            // interleaved columns: even = value, odd = gate  ->  out col = col/2 + j
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + (col >> 1);
+          } else {
 #pragma unroll
-            for (int h16 = 0; h16 < 2; ++h16) {
-              if (h16 * 16 + 16 <= ncols) {
-                float g[8];
+            for (int q4 = 0; q4 < 4; ++q4)
+              ov[q4] = make_uint4(pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]),
+                                  pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]),
+                                  pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
+                                  pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+          }
+          // the leader only gets here after the TMA store that last read this buffer finished
+          named_bar_sync(bar_id, 128);
+          uint8_t* buf = my_staging + sbuf * EPI_BUF_BYTES;
+          const int sw = (r >> 1) & 3;               // 64B-swizzle phase of this 64-byte row
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  g[j] = v[h16 * 16 + 2 * j] * gelu_erf_f(v[h16 * 16 + 2 * j + 1]);
-                uint4 ov;
-                ov.x = pack_bf16x2(g[0], g[1]);
-                ov.y = pack_bf16x2(g[2], g[3]);
-                ov.z = pack_bf16x2(g[4], g[5]);
-                ov.w = pack_bf16x2(g[6], g[7]);
-                *reinterpret_cast<uint4*>(o + h16 * 8) = ov;
-              }
-            }
-          } else if (p.mode == DL_EPI_F32) {
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ sw) << 4)) = ov[q4];
+          fence_proxy_async_smem();
+          named_bar_sync(bar_id, 128);
+          if (leader) {
+            const int out_col = (p.mode == DL_EPI_GEGLU) ? (col >> 1) : col;
+            tma_store_4d(&p.tmOut, buf, out_col, x0, y0, n0);
+            bulk_commit_group();
+            bulk_wait_group_read<1>();               // the other buffer's store has drained
+          }
+          sbuf ^= 1;
+        } else if (valid && ncols > 0) {
+          if (p.mode == DL_EPI_F32) {
             float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -300,7 +316,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
                 o[j] = (uint8_t)__float2int_rn(f);
               }
           }
-        }  // valid
+        }
         __syncwarp();
       }
       tc_fence_before();
@@ -309,6 +325,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
     }
+    if (leader) bulk_wait_group_all();               // all output bytes are in global memory
   }
 
   tc_fence_before();
@@ -323,7 +340,7 @@ static int ilog2_exact(int v) {
 }
 
 static int pick_bn(int N, long long m_tiles, int sms) {
-  static const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+  static const int cands[] = {256, 192, 160, 128, 96, 64, 32};   // multiples of the 32-col store chunk
   if (N <= 16) return 16;
   int smallest_ge64 = 0, smallest = 0;
   for (int bn : cands) {
@@ -334,7 +351,7 @@ static int pick_bn(int N, long long m_tiles, int sms) {
   }
   if (smallest_ge64) return smallest_ge64;           // cannot fill: most tiles at a sane width
   if (smallest) return smallest;
-  return (N >= 128) ? 128 : ((N + 15) / 16) * 16;    // no divisor: masked tail tile
+  return (N >= 128) ? 128 : ((N + 31) / 32) * 32;    // no divisor: clipped tail tile
 }
 
 // largest power-of-two tile extent <= cap with the least padding of `extent`
@@ -360,7 +377,12 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
     DL_CHECK_ARG(d->n % 8 == 0 && d->ldo % 8 == 0, "igemm: bf16 output needs n, ldo multiples of 8");
   if (d->mode == DL_EPI_GEGLU)
     DL_CHECK_ARG(d->n % 16 == 0 && d->ldo % 8 == 0, "igemm: GEGLU needs n %% 16 == 0");
-  if (d->residual) DL_CHECK_ARG(d->ldr % 8 == 0, "igemm: residual ld must be a multiple of 8");
+  if (d->residual) {
+    DL_CHECK_ARG(d->ldr % 8 == 0, "igemm: residual ld must be a multiple of 8");
+    DL_CHECK_ARG(d->mode == DL_EPI_BF16, "igemm: residual needs DL_EPI_BF16");
+    DL_CHECK_ARG(d->identity != nullptr, "igemm: residual needs the identity workspace (dl_fill_identity)");
+    DL_CHECK_ARG(d->alpha == 0.0f || d->alpha == 1.0f, "igemm: residual needs alpha == 1");
+  }
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -382,13 +404,15 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   const int sms = num_sms();
   int bn = d->bn > 0 ? d->bn : pick_bn(d->n, p.m_tiles, sms);
   DL_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "igemm: bn=%d must be a multiple of 16 in [16,256]", bn);
-  if (d->mode == DL_EPI_GEGLU) DL_CHECK_ARG(bn % 16 == 0, "igemm: GEGLU bn");
+  if (d->mode == DL_EPI_BF16) DL_CHECK_ARG(bn % 32 == 0, "igemm: bf16 output needs bn %% 32 == 0 (got %d)", bn);
+  if (d->mode == DL_EPI_GEGLU) DL_CHECK_ARG(bn % 64 == 0, "igemm: GEGLU needs bn %% 64 == 0 (got %d)", bn);
   p.BN = bn;
   p.n_tiles = (d->n + bn - 1) / bn;
   const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
-  p.stages = SMEM_BUDGET / stage_bytes;
+  p.stages = (SMEM_BUDGET - EPI_STAGING_BYTES) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
-  const int num_kb = p.taps * (p.kc0 + p.kc1);
+  p.res_chunks = d->residual ? (bn + BK - 1) / BK : 0;
+  const int num_kb = p.taps * (p.kc0 + p.kc1) + p.res_chunks;
   if (p.stages > num_kb && num_kb >= 2) p.stages = num_kb;
   DL_CHECK_ARG(p.stages >= 2, "igemm: not enough smem for 2 stages");
   p.acc_bufs = (2 * bn <= 512) ? 2 : 1;
@@ -424,7 +448,27 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
     if (make_tmap_bf16(&p.tmB, d->wgt, 2, dims, strides, box)) return 1;
   }
 
-  const int smem_bytes = p.stages * stage_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  if (d->mode == DL_EPI_BF16 || d->mode == DL_EPI_GEGLU) {
+    const uint64_t ncols = d->mode == DL_EPI_GEGLU ? (uint64_t)d->n / 2 : (uint64_t)d->n;
+    const uint64_t dims[4] = {ncols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    const uint64_t ps = (uint64_t)d->ldo * 2;
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint32_t box[4] = {32, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (make_tmap_bf16(&p.tmOut, d->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+  }
+  if (d->residual) {
+    const uint64_t dims[4] = {(uint64_t)d->n, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    const uint64_t ps = (uint64_t)d->ldr * 2;
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
+    if (make_tmap_bf16(&p.tmR, d->residual, 4, dims, strides, box)) return 1;
+    const uint64_t idims[2] = {256, 256};
+    const uint64_t istr[1] = {256 * 2};
+    const uint32_t ibox[2] = {BK, (uint32_t)bn};
+    if (make_tmap_bf16(&p.tmI, d->identity, 2, idims, istr, ibox)) return 1;
+  }
+
+  const int smem_bytes = p.stages * stage_bytes + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -441,6 +485,20 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
 }
 
 }  // namespace dl
+
+namespace dl {
+__global__ void fill_identity_kernel(__nv_bfloat16* dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * n) dst[i] = __float2bfloat16((i / n) == (i % n) ? 1.0f : 0.0f);
+}
+}  // namespace dl
+
+extern "C" int dl_fill_identity(void* dst_bf16_256x256, void* stream) {
+  DL_CHECK_ARG(dst_bf16_256x256 != nullptr, "fill_identity: null pointer");
+  dl::fill_identity_kernel<<<(256 * 256 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<__nv_bfloat16*>(dst_bf16_256x256), 256);
+  return dl::check_launch("fill_identity");
+}
 
 extern "C" int dl_igemm(const dl_igemm_desc* d, void* stream) {
   return dl::igemm_launch(d, reinterpret_cast<cudaStream_t>(stream));

@@ -1,17 +1,18 @@
 // GroupNorm(+SiLU) and LayerNorm for NHWC bf16 activations (HBM-bound kernels).
 //
-// GroupNorm is ONE persistent cooperative launch (grid <= resident CTAs): the batch is cut into
-// waves of images small enough to stay in the 126 MB L2; per wave every CTA
-//   A. reduces its slab of pixels to per-group (mean, M2) partials (fp32, fixed order),
+// GroupNorm is ONE persistent cooperative launch (grid = #SMs): the batch is cut into waves of
+// images small enough to stay in the 126 MB L2; per wave every CTA owns a contiguous slab of
+// pixels of one image and
+//   A. streams it through a 6-deep ring of 16 KB shared-memory buffers filled by 1-D bulk async
+//      copies (cp.async.bulk + mbarrier: ~96 KB in flight per SM, no registers tied up) and
+//      reduces it to per-group (mean, M2) partials (fp32, fixed order),
 //   -- grid barrier --
-//   B. Chan-merges the partials of its image (fixed order => deterministic, no float atomics),
-//      builds per-channel scale/shift in registers and re-reads its slab (an L2 hit: it read it
-//      a few microseconds ago) -> normalise (+SiLU) -> 16-byte stores.
+//   B. Chan-merges the partials of its image (warp shuffles, fixed order => deterministic, no
+//      float atomics), builds per-channel scale/shift in registers, streams the slab again (an
+//      L2 hit: it was read microseconds ago) -> normalise (+SiLU) -> 16-byte coalesced stores.
 // HBM traffic is therefore the algorithmic read-once + write-once (4 B/element).
 // Both phases accept two sources and emit the channel concat [x0 | x1] (UNet skip concat folded
 // into the norm: the concat tensor is never written in un-normalised form).
-#include <cooperative_groups.h>
-
 #include "common.cuh"
 #include "dreamlab_b200.h"
 
@@ -20,20 +21,15 @@ namespace dl {
 constexpr int GN_THREADS = 512;
 constexpr int GN_MAX_C = 2560;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_STAGES = 6;
+constexpr int GN_CHUNK_BYTES = 16 * 1024;
 constexpr long long GN_WAVE_BYTES = 40ll << 20;     // input bytes per wave (L2-resident)
-
-__device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int c0,
-                                         const __nv_bfloat16* x1, int c1, long long pix, int v) {
-  // vector v covers channels [8v, 8v+8) of the virtual concat
-  const int ch = v * 8;
-  const __nv_bfloat16* p = (ch < c0) ? (x0 + pix * c0 + ch) : (x1 + pix * c1 + (ch - c0));
-  return *reinterpret_cast<const uint4*>(p);
-}
 
 struct GnParams {
   const __nv_bfloat16* x0; int c0;
   const __nv_bfloat16* x1; int c1;
   int nimg, hw, groups, V, L;
+  int P;                     // pixels per streamed chunk (multiple of L)
   float eps;
   const float* gamma; const float* beta;
   int apply_silu;
@@ -48,65 +44,103 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(64);
+    while (*reinterpret_cast<volatile unsigned int*>(counter) < target) __nanosleep(32);
     __threadfence();
   }
   __syncthreads();
 }
 
+// Streams pixels [p_begin, p_end) of image `img` through the smem ring and calls
+// f(vec, pixel) for this thread's (channel-vector v, pixel-lane l) elements.
+template <class F>
+__device__ __forceinline__ void gn_stream(const GnParams& p, uint8_t* ring, uint64_t* full,
+                                          uint32_t& chunk_base, int img, int p_begin, int p_end,
+                                          int v, int l, bool lane_ok, F&& f) {
+  const int C = p.c0 + p.c1;
+  const int npix = p_end - p_begin;
+  const int n_chunks = (npix + p.P - 1) / p.P;
+  const long long pix0 = (long long)img * p.hw + p_begin;
+  const size_t part0 = (size_t)p.P * p.c0 * 2;          // bytes of source 0 in a full chunk buffer
+  auto issue = [&](int i) {
+    const uint32_t g = chunk_base + (uint32_t)i;
+    const int stage = (int)(g % GN_STAGES);
+    const int cp = min(p.P, npix - i * p.P);
+    uint8_t* buf = ring + (size_t)stage * GN_CHUNK_BYTES;
+    const uint32_t b0 = (uint32_t)cp * p.c0 * 2, b1 = (uint32_t)cp * p.c1 * 2;
+    mbar_expect_tx(&full[stage], b0 + b1);
+    bulk_load_1d(buf, p.x0 + (pix0 + (long long)i * p.P) * p.c0, b0, &full[stage]);
+    if (p.c1 > 0)
+      bulk_load_1d(buf + part0, p.x1 + (pix0 + (long long)i * p.P) * p.c1, b1, &full[stage]);
+  };
+  if (threadIdx.x == 0)
+    for (int i = 0; i < min(GN_STAGES, n_chunks); ++i) issue(i);
+  const bool from0 = v * 8 < p.c0;
+  for (int i = 0; i < n_chunks; ++i) {
+    const uint32_t g = chunk_base + (uint32_t)i;
+    const int stage = (int)(g % GN_STAGES);
+    mbar_wait(&full[stage], (g / GN_STAGES) & 1);
+    const uint8_t* buf = ring + (size_t)stage * GN_CHUNK_BYTES;
+    const int cp = min(p.P, npix - i * p.P);
+    if (lane_ok) {
+      for (int px = l; px < cp; px += p.L) {
+        const uint8_t* src = from0 ? buf + ((size_t)px * p.c0 + v * 8) * 2
+                                   : buf + part0 + ((size_t)px * p.c1 + (v * 8 - p.c0)) * 2;
+        f(*reinterpret_cast<const uint4*>(src), pix0 + (long long)i * p.P + px);
+      }
+    }
+    __syncthreads();                                     // everyone is done with this buffer
+    if (threadIdx.x == 0 && i + GN_STAGES < n_chunks) issue(i + GN_STAGES);
+  }
+  chunk_base += (uint32_t)n_chunks;
+  (void)C;
+}
+
 __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams p) {
-  __shared__ float s_sum[GN_THREADS * 8];
-  __shared__ float s_sq[GN_THREADS * 8];
+  extern __shared__ __align__(128) uint8_t gn_smem[];
+  uint8_t* ring = gn_smem;                                                   // GN_STAGES x 16 KB
+  float* s_sum = reinterpret_cast<float*>(gn_smem + GN_STAGES * GN_CHUNK_BYTES);   // [512*8]
+  float* s_sq = s_sum + GN_THREADS * 8;
   __shared__ float s_mean[GN_MAX_GROUPS];
   __shared__ float s_rstd[GN_MAX_GROUPS];
+  __shared__ __align__(8) uint64_t full[GN_STAGES];
   const int C = p.c0 + p.c1;
   const int cpg = C / p.groups;
   const int v = threadIdx.x % p.V;
   const int l = threadIdx.x / p.V;
   const bool lane_ok = l < p.L;                       // threads beyond V*L idle in the loops
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < GN_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  uint32_t chunk_base = 0;
   const int num_waves = (p.nimg + p.wave_imgs - 1) / p.wave_imgs;
   const int pps = (p.hw + p.slabs - 1) / p.slabs;     // pixels per slab
   for (int w = 0; w < num_waves; ++w) {
     const int item = blockIdx.x;
     const int img = w * p.wave_imgs + item / p.slabs;
     const int slab = item % p.slabs;
-    const bool active = (item < p.wave_imgs * p.slabs) && (img < p.nimg);
     const int p_begin = slab * pps;
     const int p_end = min(p.hw, p_begin + pps);
+    const bool active = (item < p.wave_imgs * p.slabs) && (img < p.nimg) && (p_end > p_begin);
     float* part = p.partial + ((size_t)(w & 1) * gridDim.x) * p.groups * 2;
     // ---------------- phase A: partial statistics of my slab ----------------
     if (active) {
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      gn_stream(p, ring, full, chunk_base, img, p_begin, p_end, v, l, lane_ok,
+                [&](const uint4& u, long long) {
+                  const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = unpack_bf16x2(ww[j]);
+                    s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+                    s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+                  }
+                });
       if (lane_ok) {
-        const long long base = (long long)img * p.hw;
-        int px = p_begin + l;
-        for (; px + 3 * p.L < p_end; px += 4 * p.L) {          // 4 independent 16 B loads in flight
-          uint4 u[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, v);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ww[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(ww[j]);
-              s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-              s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-            }
-          }
-        }
-        for (; px < p_end; px += p.L) {
-          const uint4 u = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v);
-          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = unpack_bf16x2(ww[j]);
-            s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-            s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-          }
-        }
         // layout [l][C]: channel-contiguous so the per-group gather below is a linear walk
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -119,7 +153,6 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
     if (active) {
       // one warp per group (round-robin): lanes stride over the L x cpg partial sums, then a
       // fixed-order shuffle tree => deterministic
-      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
       const int nvals = p.L * cpg;
       for (int g = warp; g < p.groups; g += GN_THREADS / 32) {
         float ts = 0.f, tq = 0.f;
@@ -131,11 +164,10 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
         ts = warp_sum(ts);
         tq = warp_sum(tq);
         if (lane == 0) {
-          const float cnt = (float)max(p_end - p_begin, 0) * (float)cpg;
-          float mean = 0.f, m2 = 0.f;
-          if (cnt > 0.f) { mean = ts / cnt; m2 = fmaxf(tq - ts * mean, 0.f); }
+          const float cnt = (float)(p_end - p_begin) * (float)cpg;
+          const float mean = ts / cnt;
           part[((size_t)item * p.groups + g) * 2 + 0] = mean;
-          part[((size_t)item * p.groups + g) * 2 + 1] = m2;
+          part[((size_t)item * p.groups + g) * 2 + 1] = fmaxf(tq - ts * mean, 0.f);
         }
       }
     }
@@ -145,7 +177,6 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
       {
         // Chan merge of the image's slab partials: warp per group, lane i folds slabs
         // i, i+32, ... (all loads issued up front), then a fixed shuffle tree => deterministic
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int first = (item / p.slabs) * p.slabs;
         for (int g = warp; g < p.groups; g += GN_THREADS / 32) {
           float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
@@ -182,39 +213,29 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
         }
       }
       __syncthreads();
-      if (lane_ok) {
-        float sc[8], sh[8];
+      float sc[8], sh[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = v * 8 + j;
-          const int g = c / cpg;
-          sc[j] = s_rstd[g] * __ldg(p.gamma + c);
-          sh[j] = __ldg(p.beta + c) - s_mean[g] * sc[j];
-        }
-        const long long base = (long long)img * p.hw;
-        auto emit = [&](const uint4& u, long long pix) {
-          const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float2 f = unpack_bf16x2(ww[j]);
-            f.x = f.x * sc[2 * j] + sh[2 * j];
-            f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
-            if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
-            o[j] = pack_bf16x2(f.x, f.y);
-          }
-          *reinterpret_cast<uint4*>(p.out + pix * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
-        };
-        int px = p_begin + l;
-        for (; px + 3 * p.L < p_end; px += 4 * p.L) {
-          uint4 u[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, v);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) emit(u[k], base + px + k * p.L);
-        }
-        for (; px < p_end; px += p.L) emit(ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v), base + px);
+      for (int j = 0; j < 8; ++j) {
+        const int c = min(v * 8 + j, C - 1);
+        const int g = c / cpg;
+        sc[j] = s_rstd[g] * __ldg(p.gamma + c);
+        sh[j] = __ldg(p.beta + c) - s_mean[g] * sc[j];
       }
+      gn_stream(p, ring, full, chunk_base, img, p_begin, p_end, v, l, lane_ok,
+                [&](const uint4& u, long long pix) {
+                  const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+                  uint32_t o[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float2 f = unpack_bf16x2(ww[j]);
+                    f.x = f.x * sc[2 * j] + sh[2 * j];
+                    f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+                    if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+                    o[j] = pack_bf16x2(f.x, f.y);
+                  }
+                  *reinterpret_cast<uint4*>(p.out + pix * C + v * 8) =
+                      make_uint4(o[0], o[1], o[2], o[3]);
+                });
     }
     __syncthreads();      // s_sum / s_mean are reused by the next wave
   }
@@ -305,6 +326,13 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   p.V = C / 8;
   DL_CHECK_ARG(p.V <= GN_THREADS, "groupnorm: C=%d too wide", C);
   p.L = GN_THREADS / p.V;
+  {
+    int P = GN_CHUNK_BYTES / (C * 2);                 // pixels per 16 KB chunk
+    P = (P / p.L) * p.L;
+    if (P < p.L) P = p.L;
+    DL_CHECK_ARG((long long)P * C * 2 <= GN_CHUNK_BYTES, "groupnorm: chunk does not fit (C=%d)", C);
+    p.P = P;
+  }
   p.eps = eps; p.gamma = gamma; p.beta = beta; p.apply_silu = apply_silu;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.counter = reinterpret_cast<unsigned int*>(workspace);
@@ -327,7 +355,19 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GN_THREADS);
-  cfg.dynamicSmemBytes = 0;
+  const size_t dyn_smem = (size_t)GN_STAGES * GN_CHUNK_BYTES + (size_t)2 * GN_THREADS * 8 * sizeof(float);
+  {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      cudaError_t ea = cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)dyn_smem);
+      if (ea != cudaSuccess) { set_error("groupnorm: cudaFuncSetAttribute: %s", cudaGetErrorString(ea)); return 1; }
+      attr_set[dev & 63] = true;
+    }
+  }
+  cfg.dynamicSmemBytes = dyn_smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;     // guarantees co-residency for the grid barrier

@@ -18,7 +18,7 @@ EPI_BF16, EPI_GEGLU, EPI_F32, EPI_U8_IMAGE = 0, 1, 2, 3
 ATTN_TC, ATTN_SIMT = 0, 1
 
 EXPORTS = [
-    "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm",
+    "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_fill_identity",
     "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
@@ -33,7 +33,7 @@ class IgemmDesc(C.Structure):
         ("wgt", C.c_void_p), ("ldw", C.c_longlong), ("n", C.c_int),
         ("out", C.c_void_p), ("ldo", C.c_longlong),
         ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int),
-        ("residual", C.c_void_p), ("ldr", C.c_longlong),
+        ("residual", C.c_void_p), ("ldr", C.c_longlong), ("identity", C.c_void_p),
         ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
     ]
 
@@ -65,6 +65,7 @@ def load() -> C.CDLL:
             lib.dl_groupnorm_workspace_bytes.restype = C.c_size_t
             lib.dl_groupnorm_workspace_bytes.argtypes = [C.c_int, C.c_int]
             lib.dl_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+            lib.dl_fill_identity.argtypes = [C.c_void_p, C.c_void_p]
             lib.dl_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
@@ -117,6 +118,23 @@ def _stream() -> int:
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
+
+
+_identity = {}
+
+
+def identity_matrix(device) -> "torch.Tensor":
+    """Per-device 256x256 bf16 identity: B operand of the tensor-core residual add."""
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    t = _identity.get(key)
+    if t is None:
+        with torch.cuda.device(key):
+            t = torch.empty(256, 256, device=f"cuda:{key}", dtype=torch.bfloat16)
+            _check(load().dl_fill_identity(t.data_ptr(), _stream()), "fill_identity")
+            torch.cuda.current_stream().synchronize()
+        _identity[key] = t
+    return t
 
 
 def _count(n=1):
@@ -203,6 +221,7 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.ld_rowadd = rowadd.stride(0) if rowadd is not None else 0
     d.residual = _ptr(residual)
     d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
+    d.identity = identity_matrix(residual.device).data_ptr() if residual is not None else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
     with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1),
                 tag=f"M={nimg * h * w} ({nimg}x{h}x{w}) N={n} K={taps}x{d.c0 + d.c1} mode={mode}"

@@ -33,8 +33,8 @@ def rand(*shape, seed=0, scale=1.0):
 
 # ------------------------------------------------------------------ igemm: linear
 @pytest.mark.parametrize("M,K,N,bn", [
-    (256, 320, 320, 0), (128, 64, 16, 16), (154, 768, 640, 0), (4096, 320, 960, 160),
-    (1000, 1280, 1280, 256), (300, 5120, 1280, 64), (512, 640, 1920, 0), (128, 128, 48, 48),
+    (256, 320, 320, 0), (128, 64, 32, 32), (154, 768, 640, 0), (4096, 320, 960, 160),
+    (1000, 1280, 1280, 256), (300, 5120, 1280, 64), (512, 640, 1920, 0), (128, 128, 96, 96),
     (8192, 320, 2560, 0),
 ])
 def test_igemm_linear(M, K, N, bn):
@@ -61,10 +61,20 @@ def test_igemm_linear_epilogues():
     rowadd = rand(5, N, seed=5)
     out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
     lib.igemm(x.view(5, 1, 128, K), w, out, nimg=5, h=1, w=128, taps=1, n=N, bias=bias,
-              rowadd=rowadd, residual=res, alpha=0.5)
-    ref = 0.5 * (x.float() @ w.float().t()) + bias + rowadd.repeat_interleave(128, 0) + res.float()
+              rowadd=rowadd, residual=res)
+    ref = (x.float() @ w.float().t()) + bias + rowadd.repeat_interleave(128, 0) + res.float()
     torch.cuda.synchronize()
     assert rel_err(out, ref) < 1e-2
+    # residual into a 160-wide N tile (partial last 64-column identity chunk), odd M, alpha
+    for bn in (160, 96, 256):
+        o2 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+        lib.igemm(x[:600], w, o2[:600], nimg=1, h=1, w=600, taps=1, n=N, residual=res[:600], bn=bn)
+        torch.cuda.synchronize()
+        assert rel_err(o2[:600], x[:600].float() @ w.float().t() + res[:600].float()) < 1e-2, bn
+    o3 = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x, w, o3, nimg=1, h=1, w=M, taps=1, n=N, bias=bias, alpha=0.5)
+    torch.cuda.synchronize()
+    assert rel_err(o3, 0.5 * (x.float() @ w.float().t()) + bias) < 1e-2
     # fp32 output, N = 4 (UNet conv_out shape class)
     w4 = bf(rand(4, K, seed=6, scale=K ** -0.5))
     o4 = torch.zeros(M, 4, device=DEV, dtype=torch.float32)
@@ -104,6 +114,23 @@ def test_igemm_conv3x3(B, H, W, C0, C1, N):
     lib.igemm(x0, w_pack, out, nimg=B, h=H, w=W, taps=9, n=N, a1=x1, bias=bias)
     xin = x0 if x1 is None else torch.cat([x0, x1], -1)
     ref = F.conv2d(xin.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    assert e < 1e-2, f"rel err {e}"
+
+
+def test_igemm_conv3x3_residual_rowadd_partial_tiles():
+    lib = L()
+    B, H, W, C, N = 3, 24, 24, 128, 320          # 24x24: clipped tiles in x and y; N=320 -> BN 160
+    x = bf(rand(B, H, W, C, seed=1))
+    wt = bf(rand(N, C, 3, 3, seed=3, scale=(9 * C) ** -0.5))
+    bias, rowadd = rand(N, seed=4), rand(B, N, seed=5)
+    res = bf(rand(B, H, W, N, seed=6))
+    w_pack = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.full((B, H, W, N), 7.0, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(x, w_pack, out, nimg=B, h=H, w=W, taps=9, n=N, bias=bias, rowadd=rowadd, residual=res)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1)
+    ref = ref + rowadd[:, None, None, :] + res.float()
     torch.cuda.synchronize()
     e = rel_err(out, ref)
     assert e < 1e-2, f"rel err {e}"
