@@ -33,7 +33,8 @@ constexpr int IGEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue 
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
 
 constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
-constexpr int EPI_STAGING_BYTES = 4 * EPI_BUF_BYTES;   // 2 epilogue halves x double buffer
+// staging ring per epilogue half: 2 buffers for long-K tiles, 4 for short-K tiles whose TMA
+// stores queue behind a deep load pipeline (the epilogue must not wait on each store)
 
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmB;
@@ -41,6 +42,7 @@ struct IgemmParams {
   CUtensorMap tmR;       // residual as an extra A source (box like tmA0)
   CUtensorMap tmI;       // 256x256 bf16 identity as its B operand (box {64, BN})
   int res_chunks;        // ceil(BN/64) when a residual is fused, else 0
+  int epi_nbuf;          // staging buffers per epilogue half (2 or 4)
   int tw_log2, th_log2;
   int tiles_x, tiles_y, tiles_n;
   int W, H, NIMG;
@@ -67,7 +69,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int b_tile_bytes = p.BN * BK * 2;
   const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;         // 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -193,7 +195,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     const int r = quad * 32 + lane;                  // row of the 128-row tile
     const bool leader = (threadIdx.x == 64 + 128 * half);
     const int bar_id = 1 + half;
-    uint8_t* my_staging = staging + half * 2 * EPI_BUF_BYTES;
+    uint8_t* my_staging = staging + half * p.epi_nbuf * EPI_BUF_BYTES;
     int sbuf = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -294,9 +296,11 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             const int out_col = (p.mode == DL_EPI_GEGLU) ? (col >> 1) : col;
             tma_store_4d(&p.tmOut, buf, out_col, x0, y0, n0);
             bulk_commit_group();
-            bulk_wait_group_read<1>();               // the other buffer's store has drained
+            // the buffer the NEXT chunk will overwrite must have been read out by its store
+            if (p.epi_nbuf == 4) bulk_wait_group_read<3>();
+            else bulk_wait_group_read<1>();
           }
-          sbuf ^= 1;
+          sbuf = (sbuf + 1 == p.epi_nbuf) ? 0 : sbuf + 1;
         } else if (valid && ncols > 0) {
           if (p.mode == DL_EPI_F32) {
             float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
@@ -339,19 +343,19 @@ static int ilog2_exact(int v) {
   return l;
 }
 
-static int pick_bn(int N, long long m_tiles, int sms) {
+static int pick_bn(int N, long long m_tiles, int sms, int mult) {
   static const int cands[] = {256, 192, 160, 128, 96, 64, 32};   // multiples of the 32-col store chunk
   if (N <= 16) return 16;
   int smallest_ge64 = 0, smallest = 0;
   for (int bn : cands) {
-    if (bn > N || N % bn != 0) continue;
+    if (bn > N || N % bn != 0 || bn % mult != 0) continue;
     if (m_tiles * (N / bn) >= sms) return bn;        // largest divisor that still fills the GPU
     smallest = bn;
     if (bn >= 64) smallest_ge64 = bn;
   }
   if (smallest_ge64) return smallest_ge64;           // cannot fill: most tiles at a sane width
   if (smallest) return smallest;
-  return (N >= 128) ? 128 : ((N + 31) / 32) * 32;    // no divisor: clipped tail tile
+  return (N >= 128) ? 128 : ((N + mult - 1) / mult) * mult;    // no divisor: clipped tail tile
 }
 
 // largest power-of-two tile extent <= cap with the least padding of `extent`
@@ -402,14 +406,17 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   p.N = d->n;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
   const int sms = num_sms();
-  int bn = d->bn > 0 ? d->bn : pick_bn(d->n, p.m_tiles, sms);
+  int bn = d->bn > 0 ? d->bn : pick_bn(d->n, p.m_tiles, sms, d->mode == DL_EPI_GEGLU ? 64 : 32);
   DL_CHECK_ARG(bn % 16 == 0 && bn >= 16 && bn <= 256, "igemm: bn=%d must be a multiple of 16 in [16,256]", bn);
   if (d->mode == DL_EPI_BF16) DL_CHECK_ARG(bn % 32 == 0, "igemm: bf16 output needs bn %% 32 == 0 (got %d)", bn);
   if (d->mode == DL_EPI_GEGLU) DL_CHECK_ARG(bn % 64 == 0, "igemm: GEGLU needs bn %% 64 == 0 (got %d)", bn);
   p.BN = bn;
   p.n_tiles = (d->n + bn - 1) / bn;
   const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
-  p.stages = (SMEM_BUDGET - EPI_STAGING_BYTES) / stage_bytes;
+  const int base_kb = d->taps * ((d->c0 + d->c1) / BK);
+  p.epi_nbuf = (base_kb <= 20) ? 4 : 2;
+  const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES;
+  p.stages = (SMEM_BUDGET - staging_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   p.res_chunks = d->residual ? (bn + BK - 1) / BK : 0;
   const int num_kb = p.taps * (p.kc0 + p.kc1) + p.res_chunks;
@@ -468,7 +475,7 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
     if (make_tmap_bf16(&p.tmI, d->identity, 2, idims, istr, ibox)) return 1;
   }
 
-  const int smem_bytes = p.stages * stage_bytes + EPI_STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  const int smem_bytes = p.stages * stage_bytes + staging_bytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
