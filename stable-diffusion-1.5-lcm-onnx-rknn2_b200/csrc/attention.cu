@@ -7,7 +7,7 @@
 //   warp 0  TMA producer   Q once, then K_j / V_j tiles (128 keys) through an mbarrier ring
 //   warp 1  MMA issuer     S_j = Q K_j^T  (SS, M=128 N=128 K=d16)   -> TMEM S[j&1]
 //                          O  += P_j V_j  (TS: A = P_j in TMEM, B = V_j MN-major smem)
-//   warps 2-5 softmax      one query row per thread: tcgen05.ld S row, online softmax in fp32
+//   warps 2-9 softmax      two threads per query row (64 key columns each): tcgen05.ld, online softmax in fp32
 //                          (exp2, scale*log2e folded), P_j written back to TMEM as packed bf16
 //                          over the S_j columns it was read from, O rescaled in TMEM when the
 //                          running max moved; final O / l -> bf16 global.
@@ -23,7 +23,7 @@ int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk,
                      long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                      int skv, int heads, int d, float scale, cudaStream_t stream);
 
-constexpr int AT_THREADS = 192;
+constexpr int AT_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_TILE = 128;                 // queries per CTA and keys per KV tile
 constexpr int AT_CHUNK_BYTES = AT_TILE * 128;   // one [128 rows x 64 bf16] swizzled block
 
@@ -46,6 +46,7 @@ struct AttnParams {
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ float xch[2][AT_TILE];                 // row-max / row-sum exchange between halves
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
@@ -75,7 +76,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 8); }
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
@@ -168,7 +169,10 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     }
   } else {
     // ============================ softmax + epilogue ============================
+    // 8 warps: two per TMEM lane quadrant; a query row is shared by two threads, each owning
+    // 64 of the tile's 128 key columns (halves the serial TMEM-load -> exp chain per tile).
     const int quad = warp & 3;
+    const int ch = (warp - 2) >> 2;                  // column half owned by this thread
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t o_tmem = tmem_base + lane_off + o_col;
@@ -178,14 +182,14 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * AT_TILE);
       mbar_wait(&s_full[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
-      const int kbase = j * AT_TILE;
-      const bool need_mask = (kbase + AT_TILE > p.skv);        // only the last tile (warp-uniform)
-      // pass 1: row max
+      const int kbase = j * AT_TILE + ch * 64;
+      const bool need_mask = (j * AT_TILE + AT_TILE > p.skv);  // only the last tile (warp-uniform)
+      // pass 1: row max over my 64 columns, then exchange with the partner thread of this row
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t rr[32];
-        tmem_ld32(s_tmem + (uint32_t)(c * 32), rr);
+        tmem_ld32(s_tmem + (uint32_t)(ch * 64 + c * 32), rr);
         tmem_ld_wait();
         if (need_mask) {
 #pragma unroll
@@ -203,16 +207,19 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
         }
       }
+      xch[ch][r] = mx;
+      named_bar_sync(1, 256);
+      mx = fmaxf(mx, xch[ch ^ 1][r]);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float corr = fast_exp2(m_run - m_new);
-      // pass 2: p = exp2(s*scale - m), write packed bf16 P over the S columns already consumed
+      // pass 2: p = exp2(s*scale - m) for my 64 columns, packed to bf16
       float lsum0 = 0.f, lsum1 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t rr[32];
-        tmem_ld32(s_tmem + (uint32_t)(c * 32), rr);
+        tmem_ld32(s_tmem + (uint32_t)(ch * 64 + c * 32), rr);
         tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float p0 = fast_exp2(fmaf(__uint_as_float(rr[2 * i]), p.scale_log2, -m_new));
@@ -229,9 +236,19 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             lsum0 += pf.x;
             lsum1 += pf.y;
           }
-          pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
+          pk[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
-        tmem_st16(s_tmem + (uint32_t)(c * 16), pk);
+      }
+      // P overlays the S columns [0,64): nobody may still be reading them
+      named_bar_sync(2, 256);
+      {
+        uint32_t t16[16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) t16[i] = pk[c * 16 + i];
+          tmem_st16(s_tmem + (uint32_t)(ch * 32 + c * 16), t16);
+        }
       }
       l_run = l_run * corr + (lsum0 + lsum1);
       m_run = m_new;
@@ -242,7 +259,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         tc_fence_after();
         if (__any_sync(0xffffffffu, corr != 1.0f)) {
 #pragma unroll 1
-          for (int c = 0; c < p.dv; c += 16) {
+          for (int c = ch * 16; c < p.dv; c += 32) {
             uint32_t oo[16];
             tmem_ld16(o_tmem + (uint32_t)c, oo);
             tmem_ld_wait();
@@ -270,12 +287,17 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       for (int i = 0; i < 16; ++i)
         if (i == (p.l_col & 15)) lv = __uint_as_float(oo[i]);
       l_run = lv;
+    } else {
+      named_bar_sync(2, 256);                        // xch is free again
+      xch[ch][r] = l_run;
+      named_bar_sync(1, 256);
+      l_run += xch[ch ^ 1][r];
     }
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + r) < p.sq;
     __nv_bfloat16* orow = p.out + ((long long)b * p.sq + q0 + r) * p.ldo + h * p.d;
 #pragma unroll 1
-    for (int c = 0; c < p.d; c += 16) {
+    for (int c = ch * 16; c < p.d; c += 32) {
       uint32_t oo[16];
       tmem_ld16(o_tmem + (uint32_t)c, oo);
       tmem_ld_wait();
@@ -330,7 +352,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   p.scale_log2 = scale * 1.4426950408889634f;
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
   const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
-  const int overhead = 1024 + 256;
+  const int overhead = 1024 + 256 + 1024;          // alignment slack, barriers, static xch
   const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
   const int full_budget = 227 * 1024;
   if (p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
