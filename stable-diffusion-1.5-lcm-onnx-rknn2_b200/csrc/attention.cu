@@ -354,7 +354,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
   const int overhead = 1024 + 256 + 1024;          // alignment slack, barriers, static xch
   const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
-  const int full_budget = 227 * 1024;
+  const int full_budget = 227 * 1024 - 2048;
   if (p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
     // small heads: 2 CTAs/SM interleave (one softmaxes while the other's MMAs run)
     p.sbuf = 1;
@@ -389,7 +389,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+                                         227 * 1024 - 2048);   // minus the static xch buffer
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }

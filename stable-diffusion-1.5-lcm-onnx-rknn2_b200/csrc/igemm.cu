@@ -343,19 +343,26 @@ static int ilog2_exact(int v) {
   return l;
 }
 
+// N-tile choice by a small cost model (cycles per 64-deep k-block of one CTA, times waves):
+// the tensor core needs 2*BN cycles per k-block (M=128), the TMA/L2 path delivers the
+// 16 KB A tile + 128*BN bytes of B at ~94 B/cycle (measured on the large convs).
 static int pick_bn(int N, long long m_tiles, int sms, int mult) {
   static const int cands[] = {256, 192, 160, 128, 96, 64, 32};   // multiples of the 32-col store chunk
   if (N <= 16) return 16;
-  int smallest_ge64 = 0, smallest = 0;
+  int best = 0;
+  double best_cost = 0.0;
   for (int bn : cands) {
-    if (bn > N || N % bn != 0 || bn % mult != 0) continue;
-    if (m_tiles * (N / bn) >= sms) return bn;        // largest divisor that still fills the GPU
-    smallest = bn;
-    if (bn >= 64) smallest_ge64 = bn;
+    if (bn % mult != 0) continue;
+    if (bn > N && bn - N >= 32) continue;              // do not over-pad small N
+    const long long n_tiles = (N + bn - 1) / bn;
+    const long long waves = (m_tiles * n_tiles + sms - 1) / sms;
+    const double mma = 2.0 * bn, load = (16384.0 + 128.0 * bn) / 94.0;
+    double cost = (double)waves * (mma > load ? mma : load);
+    cost *= (double)(n_tiles * bn) / (double)N;       // columns computed vs columns needed
+    if (best == 0 || cost < best_cost * 0.999) { best = bn; best_cost = cost; }
   }
-  if (smallest_ge64) return smallest_ge64;           // cannot fill: most tiles at a sane width
-  if (smallest) return smallest;
-  return (N >= 128) ? 128 : ((N + mult - 1) / mult) * mult;    // no divisor: clipped tail tile
+  if (best == 0) best = ((N + mult - 1) / mult) * mult;
+  return best;
 }
 
 // largest power-of-two tile extent <= cap with the least padding of `extent`
