@@ -21,6 +21,8 @@
 //     TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
 //   * BN is a runtime parameter (any multiple of 16 up to 256): UMMA N is encoded in the
 //     runtime instruction descriptor, the box size in the tensor map.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dreamlab_b200.h"
 
@@ -33,6 +35,7 @@ constexpr int IGEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue 
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
 
 constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
+constexpr int EPI_SLAB_BYTES = 2 * 2 * 256 * 4;    // (bias + row add) slab: [tile parity][image 0/1][256 cols]
 // staging ring per epilogue half: 2 buffers for long-K tiles, 4 for short-K tiles whose TMA
 // stores queue behind a deep load pipeline (the epilogue must not wait on each store)
 
@@ -69,7 +72,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int b_tile_bytes = p.BN * BK * 2;
   const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;         // 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -193,139 +196,168 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;                  // row of the 128-row tile
+    const int et = threadIdx.x - 64;                 // epilogue thread id 0..255
     const bool leader = (threadIdx.x == 64 + 128 * half);
     const int bar_id = 1 + half;
     uint8_t* my_staging = staging + half * p.epi_nbuf * EPI_BUF_BYTES;
-    int sbuf = 0;
+    float* slab = reinterpret_cast<float*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tw_mask = (1 << p.tw_log2) - 1;
     const int th_mask = (1 << p.th_log2) - 1;
+    const int img_shift = p.tw_log2 + p.th_log2;
+    const int imgs_per_tile = 1 << (7 - img_shift);
     const bool staged = (p.mode == DL_EPI_BF16 || p.mode == DL_EPI_GEGLU);
     const int step = (p.mode == DL_EPI_GEGLU) ? 64 : 32;       // accumulator columns per chunk
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const bool slab_rowadd = (p.rowadd != nullptr) && imgs_per_tile <= 2;
+    int tile_iter = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_iter) {
       const int n_blk = t % p.n_tiles;
       int m = t / p.n_tiles;
       const int tx = m % p.tiles_x;
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
       const int tn = m / p.tiles_y;
-      const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << (7 - p.tw_log2 - p.th_log2);
+      const int x0 = tx << p.tw_log2, y0 = ty << p.th_log2, n0 = tn << (7 - img_shift);
       const int x = x0 + (r & tw_mask);
       const int y = y0 + ((r >> p.tw_log2) & th_mask);
-      const int n = n0 + (r >> (p.tw_log2 + p.th_log2));
+      const int n = n0 + (r >> img_shift);
       const bool valid = (x < p.W) && (y < p.H) && (n < p.NIMG);
       const long long row = ((long long)n * p.H + y) * p.W + x;
       const int col0 = n_blk * p.BN;
-      const float* ra_row = (p.rowadd && n < p.NIMG) ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
+
+      // per-tile slab of (bias + time-embedding row add) in smem: [image-in-tile 0/1][256 cols].
+      // Filled while the tile's MMAs are still running; the chunks then read it with
+      // broadcast LDS instead of dependent global loads.
+      float* sl = slab + (tile_iter & 1) * 512;
+      for (int idx = et; idx < 512; idx += 256) {
+        const int i = idx >> 8, c = idx & 255, col = col0 + c;
+        float vs = 0.f;
+        if (c < p.BN && col < p.N) {
+          if (p.bias != nullptr) vs = __ldg(p.bias + col);
+          if (slab_rowadd && n0 + i < p.NIMG) vs += __ldg(p.rowadd + (long long)(n0 + i) * p.ld_rowadd + col);
+        }
+        sl[idx] = vs;
+      }
+      named_bar_sync(3, 256);
+      const float* sl_row = sl + (slab_rowadd ? min(r >> img_shift, 1) : 0) * 256;
+      const float* ra_row = (p.rowadd && !slab_rowadd && n < p.NIMG)
+                                ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int c = half * step; c < p.BN; c += 2 * step) {
-        float v[64];
-        {
-          uint32_t rr[32];
-          tmem_ld32(t_row + (uint32_t)c, rr);        // may read past BN: still inside the allocation
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
-          if (step == 64) {
-            tmem_ld32(t_row + (uint32_t)(c + 32), rr);
+      int c = half * step;
+      while (c < p.BN) {
+        const int c_group = c;
+        int g = 0;
+        if (staged) {
+          // staging buffers of the previous group / tile must have been read out by their stores
+          if (leader) bulk_wait_group_read<0>();
+          named_bar_sync(bar_id, 128);
+        }
+        for (; g < (staged ? p.epi_nbuf : 1) && c < p.BN; ++g, c += 2 * step) {
+          float v[64];
+          {
+            uint32_t rr[32];
+            tmem_ld32(t_row + (uint32_t)c, rr);      // may read past BN: still inside the allocation
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(rr[j]) * p.alpha;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.alpha;
+            if (step == 64) {
+              tmem_ld32(t_row + (uint32_t)(c + 32), rr);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[32 + j] = __uint_as_float(rr[j]) * p.alpha;
+            }
           }
-        }
-        const int col = col0 + c;
-        const int ncols = min(min(step, p.BN - c), p.N - col);
-        if (ncols > 0) {
+          const int col = col0 + c;
+          const int ncols = min(min(step, p.BN - c), p.N - col);
 #pragma unroll
           for (int j4 = 0; j4 < 16; ++j4) {
             if (j4 * 4 >= step) break;
-            if (j4 * 4 + 4 <= ncols) {
-              if (p.bias != nullptr) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + j4 * 4));
-                v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
-              }
-              if (ra_row != nullptr) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(ra_row + col + j4 * 4));
-                v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+            const float4 bv = *reinterpret_cast<const float4*>(sl_row + c + j4 * 4);   // zeros past N
+            v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+          }
+          if (ra_row != nullptr) {       // rare: more than two images per tile (tiny spatial dims)
+#pragma unroll
+            for (int j = 0; j < 64; ++j)
+              if (j < ncols) v[j] += __ldg(ra_row + col + j);
+          }
+          if (staged) {
+            uint4 ov[4];
+            if (p.mode == DL_EPI_GEGLU) {
+              // interleaved columns: even = value, odd = gate -> 32 outputs from 64 accumulators
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                float gg[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  gg[j] = v[q4 * 16 + 2 * j] * gelu_erf_f(v[q4 * 16 + 2 * j + 1]);
+                ov[q4] = make_uint4(pack_bf16x2(gg[0], gg[1]), pack_bf16x2(gg[2], gg[3]),
+                                    pack_bf16x2(gg[4], gg[5]), pack_bf16x2(gg[6], gg[7]));
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j4 * 4 + j < ncols) {
-                  if (p.bias != nullptr) v[j4 * 4 + j] += __ldg(p.bias + col + j4 * 4 + j);
-                  if (ra_row != nullptr) v[j4 * 4 + j] += __ldg(ra_row + col + j4 * 4 + j);
+              for (int q4 = 0; q4 < 4; ++q4)
+                ov[q4] = make_uint4(pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]),
+                                    pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]),
+                                    pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
+                                    pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+            }
+            uint8_t* buf = my_staging + g * EPI_BUF_BYTES;
+            const int sw = (r >> 1) & 3;             // 64B-swizzle phase of this 64-byte row
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ sw) << 4)) = ov[q4];
+          } else if (valid && ncols > 0) {
+            if (p.mode == DL_EPI_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[j] = v[j];
+            } else if (p.mode == DL_EPI_U8_IMAGE) {
+              // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
+              uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) {
+                  // image is bf16-rounded first (the decoder output dtype), like the reference's
+                  // dtype-typed vae output
+                  const float xb = __bfloat162float(__float2bfloat16(v[j]));
+                  const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
+                  o[j] = (uint8_t)__float2int_rn(f);
                 }
             }
           }
+          __syncwarp();
+        }
+        if (c >= p.BN) {
+          // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[acc]);
         }
         if (staged) {
-          uint4 ov[4];
-          if (p.mode == DL_EPI_GEGLU) {
-            // interleaved columns: even = value, odd = gate -> 32 outputs from 64 accumulators
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              float g[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                g[j] = v[q4 * 16 + 2 * j] * gelu_erf_f(v[q4 * 16 + 2 * j + 1]);
-              ov[q4] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]),
-                                  pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
-            }
-          } else {
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4)
-              ov[q4] = make_uint4(pack_bf16x2(v[q4 * 8 + 0], v[q4 * 8 + 1]),
-                                  pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]),
-                                  pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
-                                  pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
-          }
-          // the leader only gets here after the TMA store that last read this buffer finished
-          named_bar_sync(bar_id, 128);
-          uint8_t* buf = my_staging + sbuf * EPI_BUF_BYTES;
-          const int sw = (r >> 1) & 3;               // 64B-swizzle phase of this 64-byte row
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4)
-            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ sw) << 4)) = ov[q4];
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
           if (leader) {
-            const int out_col = (p.mode == DL_EPI_GEGLU) ? (col >> 1) : col;
-            tma_store_4d(&p.tmOut, buf, out_col, x0, y0, n0);
+#pragma unroll 1
+            for (int gg = 0; gg < g; ++gg) {
+              const int cc = col0 + c_group + gg * 2 * step;
+              const int out_col = (p.mode == DL_EPI_GEGLU) ? (cc >> 1) : cc;
+              tma_store_4d(&p.tmOut, my_staging + gg * EPI_BUF_BYTES, out_col, x0, y0, n0);
+            }
             bulk_commit_group();
-            // the buffer the NEXT chunk will overwrite must have been read out by its store
-            if (p.epi_nbuf == 4) bulk_wait_group_read<3>();
-            else bulk_wait_group_read<1>();
-          }
-          sbuf = (sbuf + 1 == p.epi_nbuf) ? 0 : sbuf + 1;
-        } else if (valid && ncols > 0) {
-          if (p.mode == DL_EPI_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) o[j] = v[j];
-          } else if (p.mode == DL_EPI_U8_IMAGE) {
-            // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
-            uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) {
-                // image is bf16-rounded first (the decoder output dtype), like the reference's
-                // dtype-typed vae output
-                const float xb = __bfloat162float(__float2bfloat16(v[j]));
-                const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
-                o[j] = (uint8_t)__float2int_rn(f);
-              }
           }
         }
-        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (half * step >= p.BN) {
+        // this half owns no chunk of a narrow tile: still release the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
       if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
     }
@@ -422,7 +454,7 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
   const int base_kb = d->taps * ((d->c0 + d->c1) / BK);
   p.epi_nbuf = (base_kb <= 20) ? 4 : 2;
-  const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES;
+  const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES;
   p.stages = (SMEM_BUDGET - staging_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   p.res_chunks = d->residual ? (bn + BK - 1) / BK : 0;
@@ -438,6 +470,7 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
   p.mode = d->mode;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+
 
   // ---- tensor maps ----
   {
