@@ -132,7 +132,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_image,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "SD1.5-LCM arch (random-init seed 0) 512x512, 4 steps, guidance 1.0, batch 1 on host CPU"},
+        "config": {"workload": f"SD1.5-LCM arch (random-init seed 0) {args.size}x{args.size}, {args.lcm_steps} LCM steps, "
+                               f"guidance 1.0, batch {args.batch} per GPU (UNet x{args.lcm_steps} + scheduler + VAE decode)",
+                   "note": "reference arm = fp32 CPU port of the diffusers path on the host cores; each step is a "
+                           "bounded sample of the workload (see cpu_baseline.sample), rate is per image"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_TXT},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

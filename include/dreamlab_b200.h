@@ -54,12 +54,17 @@ typedef struct dl_igemm_desc {
   long long a1_pix_stride;
   int c1;                    /* 0 or multiple of 64                                           */
   int nimg, h, w;            /* activation extent; Linear over M rows: nimg=1, h=1, w=M       */
-  int taps;                  /* 9: conv3x3 stride 1 pad 1;  1: conv1x1 / Linear               */
+  int taps;                  /* 9: conv3x3 stride 1 pad 1;  1: conv1x1 / Linear;  4: one phase of
+                                the nearest-2x-upsample+conv3x3 fold (see tap_phase)           */
+  int tap_phase;             /* taps == 4: phase 2a+b -> output pixel (2y+a, 2x+b); else -1   */
   const void* wgt;           /* bf16 [n, taps*(c0+c1)], K index = tap*(c0+c1) + channel       */
   long long ldw;             /* weight row stride in elements; 0 = dense                      */
   int n;                     /* output channels                                               */
   void* out;
   long long ldo;             /* output row stride in elements                                 */
+  long long out_x_stride;    /* optional strided output view (elements): between x neighbours, */
+  long long out_y_stride;    /*   between rows, between images; 0 = dense (ldo, ldo*w, ldo*w*h) */
+  long long out_img_stride;
   const float* bias;         /* [n] or NULL                                                   */
   const float* rowadd;       /* [nimg, ld_rowadd] per-image channel add (time emb) or NULL    */
   int ld_rowadd;

@@ -50,6 +50,7 @@ struct IgemmParams {
   int tiles_x, tiles_y, tiles_n;
   int W, H, NIMG;
   int taps, kc0, kc1;
+  signed char tdy[9], tdx[9];   // per-tap input offsets (3x3: -1..1; folded upsample: 2x2 phase taps)
   int N, BN, n_tiles, m_tiles;
   int stages, tmem_cols, acc_bufs;
   void* out;
@@ -127,8 +128,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-          const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
+          const int dy = p.tdy[tap];
+          const int dx = p.tdx[tap];
           for (int c = 0; c < kc; ++c, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
@@ -410,12 +411,15 @@ static int pick_extent(int extent, int cap) {
 
 int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   DL_CHECK_ARG(d->a0 && d->wgt && d->out, "igemm: null pointer");
-  DL_CHECK_ARG(d->taps == 1 || d->taps == 9, "igemm: taps must be 1 or 9 (got %d)", d->taps);
+  DL_CHECK_ARG(d->taps == 1 || d->taps == 9 || (d->taps == 4 && d->tap_phase >= 0 && d->tap_phase < 4),
+               "igemm: taps must be 1, 9, or 4 with tap_phase in [0,4) (got %d)", d->taps);
   DL_CHECK_ARG(d->c0 > 0 && d->c0 % BK == 0, "igemm: c0=%d must be a positive multiple of 64", d->c0);
   DL_CHECK_ARG(d->c1 >= 0 && d->c1 % BK == 0, "igemm: c1=%d must be a multiple of 64", d->c1);
   DL_CHECK_ARG(d->c1 == 0 || d->a1 != nullptr, "igemm: c1>0 needs a1");
   DL_CHECK_ARG(d->n > 0 && d->nimg > 0 && d->h > 0 && d->w > 0, "igemm: bad dims");
   DL_CHECK_ARG(d->mode >= 0 && d->mode <= DL_EPI_U8_IMAGE, "igemm: bad epilogue mode %d", d->mode);
+  if (d->out_x_stride > 0 || d->out_y_stride > 0 || d->out_img_stride > 0)
+    DL_CHECK_ARG(d->mode == DL_EPI_BF16 && !d->residual, "igemm: strided output needs DL_EPI_BF16 without residual");
   if (d->mode == DL_EPI_BF16)
     DL_CHECK_ARG(d->n % 8 == 0 && d->ldo % 8 == 0, "igemm: bf16 output needs n, ldo multiples of 8");
   if (d->mode == DL_EPI_GEGLU)
@@ -440,6 +444,15 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   p.tiles_n = (d->nimg + tn - 1) / tn;
   p.W = d->w; p.H = d->h; p.NIMG = d->nimg;
   p.taps = d->taps;
+  for (int t = 0; t < 9; ++t) { p.tdy[t] = 0; p.tdx[t] = 0; }
+  if (d->taps == 9) {
+    for (int t = 0; t < 9; ++t) { p.tdy[t] = (signed char)(t / 3 - 1); p.tdx[t] = (signed char)(t % 3 - 1); }
+  } else if (d->taps == 4) {
+    // nearest-2x upsample folded into the conv: output pixel (2y+a, 2x+b) sees the low-res
+    // 2x2 neighbourhood rows {y-1+a, y+a}, cols {x-1+b, x+b}
+    const int a = d->tap_phase >> 1, b = d->tap_phase & 1;
+    for (int t = 0; t < 4; ++t) { p.tdy[t] = (signed char)((t >> 1) - 1 + a); p.tdx[t] = (signed char)((t & 1) - 1 + b); }
+  }
   p.kc0 = d->c0 / BK;
   p.kc1 = d->c1 / BK;
   p.N = d->n;
@@ -498,8 +511,11 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   if (d->mode == DL_EPI_BF16 || d->mode == DL_EPI_GEGLU) {
     const uint64_t ncols = d->mode == DL_EPI_GEGLU ? (uint64_t)d->n / 2 : (uint64_t)d->n;
     const uint64_t dims[4] = {ncols, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
-    const uint64_t ps = (uint64_t)d->ldo * 2;
-    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    // default: dense NHWC; a caller may scatter into a strided view (folded upsample phases)
+    const uint64_t xs = (uint64_t)(d->out_x_stride > 0 ? d->out_x_stride : d->ldo) * 2;
+    const uint64_t ys = d->out_y_stride > 0 ? (uint64_t)d->out_y_stride * 2 : xs * d->w;
+    const uint64_t is = d->out_img_stride > 0 ? (uint64_t)d->out_img_stride * 2 : ys * d->h;
+    const uint64_t strides[3] = {xs, ys, is};
     const uint32_t box[4] = {32, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (make_tmap_bf16(&p.tmOut, d->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
   }

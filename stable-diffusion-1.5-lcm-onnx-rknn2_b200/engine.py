@@ -135,10 +135,17 @@ def downsample(ctx, x, p: Packed):
 
 
 def upsample(ctx, x, p: Packed):
+    """Upsample2D = nearest-2x + conv3x3, folded: four 2x2-tap convs on the low-res input, one
+    per output phase, each TMA-storing into its strided quarter of the output."""
     B, H, W, C = x.shape
-    up = ctx.empty(B, 2 * H, 2 * W, C)
-    lib.upsample2x(x, up, nimg=B, h=H, w=W)
-    return conv3x3(ctx, up, p["w"], p["b"], C)
+    out = ctx.empty(B, 2 * H, 2 * W, C)
+    strides = (2 * C, 4 * W * C, 4 * H * W * C)            # x, row, image strides of a phase view
+    for ph in range(4):
+        a, b = ph >> 1, ph & 1
+        view = out[:, a:, b:, :]                            # base pointer of phase (a, b)
+        lib.igemm(x, p["w"][ph], view, nimg=B, h=H, w=W, taps=4, n=C, bias=p["b"], tap_phase=ph,
+                  ldo=C, out_strides=strides)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

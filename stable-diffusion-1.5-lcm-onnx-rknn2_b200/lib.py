@@ -29,9 +29,10 @@ class IgemmDesc(C.Structure):
     _fields_ = [
         ("a0", C.c_void_p), ("a0_pix_stride", C.c_longlong), ("c0", C.c_int),
         ("a1", C.c_void_p), ("a1_pix_stride", C.c_longlong), ("c1", C.c_int),
-        ("nimg", C.c_int), ("h", C.c_int), ("w", C.c_int), ("taps", C.c_int),
+        ("nimg", C.c_int), ("h", C.c_int), ("w", C.c_int), ("taps", C.c_int), ("tap_phase", C.c_int),
         ("wgt", C.c_void_p), ("ldw", C.c_longlong), ("n", C.c_int),
-        ("out", C.c_void_p), ("ldo", C.c_longlong),
+        ("out", C.c_void_p), ("ldo", C.c_longlong), ("out_x_stride", C.c_longlong),
+        ("out_y_stride", C.c_longlong), ("out_img_stride", C.c_longlong),
         ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_longlong), ("identity", C.c_void_p),
         ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
@@ -200,7 +201,7 @@ def require_cuda():
 # ------------------------------------------------------------------------------------------------
 def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
           a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
-          mode=EPI_BF16, alpha=1.0, bn=0):
+          mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None):
     """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
     nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
     d = IgemmDesc()
@@ -211,7 +212,9 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
         c1 = a1.shape[-1] if not c1 else c1
         d.a1, d.c1 = a1.data_ptr(), c1
         d.a1_pix_stride = a1.stride(-2) if a1_stride is None else a1_stride
-    d.nimg, d.h, d.w, d.taps = nimg, h, w, taps
+    d.nimg, d.h, d.w, d.taps, d.tap_phase = nimg, h, w, taps, tap_phase
+    if out_strides is not None:
+        d.out_x_stride, d.out_y_stride, d.out_img_stride = out_strides
     d.wgt, d.n = wgt.data_ptr(), n
     d.ldw = wgt.stride(0) if wgt.dim() == 2 and wgt.stride(0) != wgt.shape[1] else 0
     d.out = out.data_ptr()

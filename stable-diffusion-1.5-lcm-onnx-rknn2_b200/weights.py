@@ -39,6 +39,27 @@ def pack_conv3x3(w: torch.Tensor, device, pad_in_to: int = 0) -> torch.Tensor:
     return _bf(w.reshape(o, -1), device)
 
 
+def pack_upsample_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
+    """Nearest-2x upsample followed by conv3x3 == four 2x2 convs on the low-res input, one per
+    output phase (a, b) = (row parity, column parity), with the 3x3 taps that land on the same
+    low-res pixel pre-summed (in fp32): 2.25x fewer MACs and no upsampled tensor in HBM.
+    Returns bf16 [4, O, 4*I]: phase 2a+b, K index = (ty*2+tx)*I + i."""
+    o, i = w.shape[0], w.shape[1]
+    w = w.float()
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}       # parity -> (taps of low-res -1+p, of +p)
+    out = torch.zeros(4, o, 2, 2, i)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = torch.zeros(o, i)
+                    for ky in groups[a][ty]:
+                        for kx in groups[b][tx]:
+                            acc += w[:, :, ky, kx]
+                    out[2 * a + b, :, ty, tx] = acc
+    return _bf(out.reshape(4, o, 4 * i), device)
+
+
 def pack_conv1x1(w: torch.Tensor, device) -> torch.Tensor:
     return _bf(w.reshape(w.shape[0], -1), device)
 
@@ -169,7 +190,7 @@ def pack_unet(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
                 blk["attns"].append(pack_transformer(sd, f"up_blocks.{i}.attentions.{j}.", heads, device))
         if i != len(ch) - 1:
             k = f"up_blocks.{i}.upsamplers.0.conv."
-            blk["up"] = Packed(w=pack_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))
+            blk["up"] = Packed(w=pack_upsample_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))
         P["up"].append(blk)
     # all ResnetBlock2D.time_emb_proj fused into one [sum(cout), temb] matrix: one launch per step
     P["temb_w"] = _bf(torch.cat([sd[r["prefix"] + "time_emb_proj.weight"].float() for r in resnets], 0), device)
@@ -213,7 +234,7 @@ def pack_vae_decoder(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
                               for j in range(cfg.layers_per_block + 1)], up=None)
         k = d + f"up_blocks.{i}.upsamplers.0.conv."
         if k + "weight" in sd:
-            blk["up"] = Packed(w=pack_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))
+            blk["up"] = Packed(w=pack_upsample_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))
         P["up"].append(blk)
     P["norm_out_w"], P["norm_out_b"] = _f32(sd[d + "conv_norm_out.weight"], device), _f32(sd[d + "conv_norm_out.bias"], device)
     P["conv_out_w"] = pack_conv3x3(sd[d + "conv_out.weight"], device)

@@ -136,6 +136,27 @@ def test_igemm_conv3x3_residual_rowadd_partial_tiles():
     assert e < 1e-2, f"rel err {e}"
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (1, 64, 64, 256), (3, 8, 8, 1280), (1, 24, 40, 128)])
+def test_igemm_upsample_fold(B, H, W, C):
+    """nearest-2x + conv3x3 as four 2x2-tap phase convs (weights pre-summed in fp32)."""
+    lib = L()
+    from dreamlab_b200.weights import pack_upsample_conv3x3
+    x = bf(rand(B, H, W, C, seed=1))
+    wt = rand(C, C, 3, 3, seed=2, scale=(9 * C) ** -0.5)
+    bias = rand(C, seed=3)
+    wp = pack_upsample_conv3x3(wt, DEV)
+    out = torch.zeros(B, 2 * H, 2 * W, C, device=DEV, dtype=torch.bfloat16)
+    strides = (2 * C, 4 * W * C, 4 * H * W * C)
+    for ph in range(4):
+        lib.igemm(x, wp[ph], out[:, ph >> 1:, ph & 1:, :], nimg=B, h=H, w=W, taps=4, n=C, bias=bias,
+                  tap_phase=ph, ldo=C, out_strides=strides)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, wt.bfloat16().float(), bias, padding=1).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    assert e < 1.5e-2, f"rel err {e}"
+
+
 def test_igemm_u8_image_tail():
     lib = L()
     B, H, W, C = 1, 64, 64, 128
