@@ -14,6 +14,8 @@
 // S is double-buffered so the tensor core computes S_{j+1} while the softmax warps work on
 // S_j.  Head dims that are not a multiple of 16 (SD1.5: 40) are laid out by the QKV projection
 // with a zero-padded per-head stride (dh_stride = 48), so the padded K-steps contribute 0.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dreamlab_b200.h"
 
@@ -355,7 +357,9 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   const int overhead = 1024 + 256 + 1024;          // alignment slack, barriers, static xch
   const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
   const int full_budget = 227 * 1024 - 2048;
-  if (p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
+  static int force_mode = -1;
+  if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
+  if (force_mode != 1 && p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
     // small heads: 2 CTAs/SM interleave (one softmaxes while the other's MMAs run)
     p.sbuf = 1;
     p.tmem_cols = 256;

@@ -23,7 +23,7 @@ constexpr int GN_MAX_C = 2560;
 constexpr int GN_MAX_GROUPS = 64;
 constexpr int GN_STAGES = 6;
 constexpr int GN_CHUNK_BYTES = 16 * 1024;
-constexpr long long GN_WAVE_BYTES = 40ll << 20;     // input bytes per wave (L2-resident)
+constexpr long long GN_WAVE_BYTES = 24ll << 20;     // input bytes per wave of 148 CTAs (L2-resident)
 
 struct GnParams {
   const __nv_bfloat16* x0; int c0;
@@ -339,17 +339,20 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
   int grid = num_sms();                       // 1 CTA/SM (launch bounds + 33 KB smem): co-resident
   if (grid > 1024) grid = 1024;
+  // Slabs per image depend ONLY on the image size (never on the batch): a request normalises
+  // bit-identically alone or inside any batch (reduction tree shape is a function of hw, C).
   const long long img_bytes = (long long)hw * C * 2;
-  long long wave = GN_WAVE_BYTES / (img_bytes > 0 ? img_bytes : 1);
-  if (wave < 1) wave = 1;
+  long long slabs = ((long long)grid * img_bytes + GN_WAVE_BYTES / 2) / GN_WAVE_BYTES;
+  const int max_slabs = (hw + p.L - 1) / p.L;          // at least one pixel per lane row
+  if (slabs > grid) slabs = grid;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  p.slabs = (int)slabs;
+  long long wave = grid / p.slabs;                     // images that fit one wave of CTAs
   if (wave > nimg) wave = nimg;
-  if (wave > grid) wave = grid;
   const long long n_waves = (nimg + wave - 1) / wave;
   wave = (nimg + n_waves - 1) / n_waves;               // balance the waves (16 -> 8+8, not 15+1)
   p.wave_imgs = (int)wave;
-  p.slabs = grid / p.wave_imgs;
-  const int max_slabs = (hw + p.L - 1) / p.L;          // at least one pixel per lane row
-  if (p.slabs > max_slabs) p.slabs = max_slabs < 1 ? 1 : max_slabs;
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(unsigned int), stream);
   if (e != cudaSuccess) { set_error("groupnorm: memset: %s", cudaGetErrorString(e)); return 2; }
   cudaLaunchConfig_t cfg = {};
