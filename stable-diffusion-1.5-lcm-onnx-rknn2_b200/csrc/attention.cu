@@ -48,7 +48,7 @@ struct AttnParams {
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  __shared__ float xch[2][AT_TILE];                 // row-max / row-sum exchange between halves
+  __shared__ float xch[2][2][AT_TILE];              // [tile parity][half][row] max / sum exchange
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
@@ -186,51 +186,48 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tc_fence_after();
       const int kbase = j * AT_TILE + ch * 64;
       const bool need_mask = (j * AT_TILE + AT_TILE > p.skv);  // only the last tile (warp-uniform)
-      // pass 1: row max over my 64 columns, then exchange with the partner thread of this row
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(s_tmem + (uint32_t)(ch * 64 + c * 32), rr);
-        tmem_ld_wait();
-        if (need_mask) {
+      // my 64 S columns -> registers with ONE TMEM round trip (both loads in flight together);
+      // they serve the max pass and the exp pass, so S is never re-read
+      uint32_t sa[32], sb32[32];
+      tmem_ld32(s_tmem + (uint32_t)(ch * 64), sa);
+      tmem_ld32(s_tmem + (uint32_t)(ch * 64 + 32), sb32);
+      tmem_ld_wait();
+      if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kbase + c * 32 + i < p.skv) mx = fmaxf(mx, __uint_as_float(rr[i]));
-        } else {
-          float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m0 = fmaxf(m0, __uint_as_float(rr[i]));
-            m1 = fmaxf(m1, __uint_as_float(rr[i + 1]));
-            m2 = fmaxf(m2, __uint_as_float(rr[i + 2]));
-            m3 = fmaxf(m3, __uint_as_float(rr[i + 3]));
-          }
-          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        for (int i = 0; i < 32; ++i) {
+          if (kbase + i >= p.skv) sa[i] = 0xff800000u;          // -inf: exp2 -> 0, max ignores
+          if (kbase + 32 + i >= p.skv) sb32[i] = 0xff800000u;
         }
       }
-      xch[ch][r] = mx;
+      float mx;
+      {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sb32[i])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(sa[i + 1]), __uint_as_float(sb32[i + 1])));
+          m2 = fmaxf(m2, fmaxf(__uint_as_float(sa[i + 2]), __uint_as_float(sb32[i + 2])));
+          m3 = fmaxf(m3, fmaxf(__uint_as_float(sa[i + 3]), __uint_as_float(sb32[i + 3])));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      }
+      // exchange the half-row maxima; after this barrier every thread of the CTA has its S
+      // values in registers, so P may overwrite the S columns right away
+      xch[j & 1][ch][r] = mx;
       named_bar_sync(1, 256);
-      mx = fmaxf(mx, xch[ch ^ 1][r]);
+      mx = fmaxf(mx, xch[j & 1][ch ^ 1][r]);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float corr = fast_exp2(m_run - m_new);
-      // pass 2: p = exp2(s*scale - m) for my 64 columns, packed to bf16
       float lsum0 = 0.f, lsum1 = 0.f;
-      uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t rr[32];
-        tmem_ld32(s_tmem + (uint32_t)(ch * 64 + c * 32), rr);
-        tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(rr[2 * i]), p.scale_log2, -m_new));
-          float p1 = fast_exp2(fmaf(__uint_as_float(rr[2 * i + 1]), p.scale_log2, -m_new));
-          if (need_mask) {
-            const int k0 = kbase + c * 32 + 2 * i;
-            if (k0 >= p.skv) p0 = 0.f;
-            if (k0 + 1 >= p.skv) p1 = 0.f;
-          }
+          const uint32_t u0 = c == 0 ? sa[2 * i] : sb32[2 * i];
+          const uint32_t u1 = c == 0 ? sa[2 * i + 1] : sb32[2 * i + 1];
+          const float p0 = fast_exp2(fmaf(__uint_as_float(u0), p.scale_log2, -m_new));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(u1), p.scale_log2, -m_new));
           const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
           if (p.l_col < 0) {
             // no ones column in V: sum what the tensor core will multiply (bf16-rounded P)
@@ -238,19 +235,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             lsum0 += pf.x;
             lsum1 += pf.y;
           }
-          pk[c * 16 + i] = *reinterpret_cast<const uint32_t*>(&pb);
+          pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
-      }
-      // P overlays the S columns [0,64): nobody may still be reading them
-      named_bar_sync(2, 256);
-      {
-        uint32_t t16[16];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) t16[i] = pk[c * 16 + i];
-          tmem_st16(s_tmem + (uint32_t)(ch * 32 + c * 16), t16);
-        }
+        tmem_st16(s_tmem + (uint32_t)(ch * 32 + c * 16), pk);
       }
       l_run = l_run * corr + (lsum0 + lsum1);
       m_run = m_new;
@@ -291,9 +278,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       l_run = lv;
     } else {
       named_bar_sync(2, 256);                        // xch is free again
-      xch[ch][r] = l_run;
+      xch[0][ch][r] = l_run;
       named_bar_sync(1, 256);
-      l_run += xch[ch ^ 1][r];
+      l_run += xch[0][ch ^ 1][r];
     }
     const float inv_l = 1.0f / l_run;
     const bool valid = (q0 + r) < p.sq;
@@ -354,9 +341,9 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   p.scale_log2 = scale * 1.4426950408889634f;
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
   const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
-  const int overhead = 1024 + 256 + 1024;          // alignment slack, barriers, static xch
+  const int overhead = 1024 + 256 + 2048;          // alignment slack, barriers, static xch
   const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
-  const int full_budget = 227 * 1024 - 2048;
+  const int full_budget = 227 * 1024 - 3072;
   static int force_mode = -1;
   if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
   if (force_mode != 1 && p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
@@ -393,7 +380,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 2048);   // minus the static xch buffer
+                                         227 * 1024 - 3072);   // minus the static xch buffer
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
