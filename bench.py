@@ -271,7 +271,7 @@ def run_b200(args):
                        "cuda_graph": True, "parallelism": f"replicas x{world} (no collective)"},
             "p50_latency_ms_per_batch": statistics.median(step_ms),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": gr.launches * args.steps,
+            "gpu_launches": gr.launches * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:
