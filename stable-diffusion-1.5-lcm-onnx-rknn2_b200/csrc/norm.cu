@@ -25,6 +25,14 @@ constexpr int GN_STAGES = 6;
 constexpr int GN_CHUNK_BYTES = 16 * 1024;
 constexpr long long GN_WAVE_BYTES = 24ll << 20;     // input bytes per wave of 148 CTAs (L2-resident)
 
+__device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int c0,
+                                         const __nv_bfloat16* x1, int c1, long long pix, int v) {
+  // vector v covers channels [8v, 8v+8) of the virtual concat
+  const int ch = v * 8;
+  const __nv_bfloat16* p = (ch < c0) ? (x0 + pix * c0 + ch) : (x1 + pix * c1 + (ch - c0));
+  return *reinterpret_cast<const uint4*>(p);
+}
+
 struct GnParams {
   const __nv_bfloat16* x0; int c0;
   const __nv_bfloat16* x1; int c1;
@@ -241,6 +249,129 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
   }
 }
 
+// ---- small images (hw <= 1024): group-sliced GroupNorm, no grid barrier -----------------------
+// One CTA owns `gpc` whole groups (a contiguous channel slice) of one image, so the statistics
+// never leave the CTA: pass 1 reduces the slice, pass 2 re-reads it (L1/L2 hit) and writes.
+// grid = (groups/gpc, nimg); the partition depends only on (C, groups) => batch-invariant.
+constexpr int GNS_THREADS = 256;
+
+struct GnSlicedParams {
+  const __nv_bfloat16* x0; int c0;
+  const __nv_bfloat16* x1; int c1;
+  int hw, groups, gpc, Vs, L;
+  float eps;
+  const float* gamma; const float* beta;
+  int apply_silu;
+  __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(GNS_THREADS) gn_sliced_kernel(const GnSlicedParams p) {
+  __shared__ float s_sum[GNS_THREADS * 8];
+  __shared__ float s_sq[GNS_THREADS * 8];
+  __shared__ float s_mean[32];
+  __shared__ float s_rstd[32];
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const int Wc = p.gpc * cpg;                          // channels of this slice (multiple of 8)
+  const int ch0 = blockIdx.x * Wc;
+  const int img = blockIdx.y;
+  const int v = threadIdx.x % p.Vs;
+  const int l = threadIdx.x / p.Vs;
+  const bool lane_ok = l < p.L;
+  const int vg = (ch0 >> 3) + v;                        // vector index in the virtual concat
+  const long long base = (long long)img * p.hw;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (lane_ok) {
+    int px = l;
+    for (; px + 3 * p.L < p.hw; px += 4 * p.L) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, vg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t ww[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(ww[j]);
+          s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+          s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+        }
+      }
+    }
+    for (; px < p.hw; px += p.L) {
+      const uint4 u = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, vg);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(ww[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_sum[l * Wc + v * 8 + j] = s[j];
+      s_sq[l * Wc + v * 8 + j] = q[j];
+    }
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nvals = p.L * cpg;
+    for (int g = warp; g < p.gpc; g += GNS_THREADS / 32) {
+      float ts = 0.f, tq = 0.f;
+      for (int i = lane; i < nvals; i += 32) {
+        const int ll = i / cpg, c = g * cpg + (i - ll * cpg);
+        ts += s_sum[ll * Wc + c];
+        tq += s_sq[ll * Wc + c];
+      }
+      ts = warp_sum(ts);
+      tq = warp_sum(tq);
+      if (lane == 0) {
+        const float cnt = (float)p.hw * (float)cpg;
+        const float mean = ts / cnt;
+        s_mean[g] = mean;
+        s_rstd[g] = rsqrtf(fmaxf(tq / cnt - mean * mean, 0.f) + p.eps);
+      }
+    }
+  }
+  __syncthreads();
+  if (lane_ok) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cl = v * 8 + j;                         // channel within the slice
+      const int g = cl / cpg;
+      sc[j] = s_rstd[g] * __ldg(p.gamma + ch0 + cl);
+      sh[j] = __ldg(p.beta + ch0 + cl) - s_mean[g] * sc[j];
+    }
+    auto emit = [&](const uint4& u, long long pix) {
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = unpack_bf16x2(ww[j]);
+        f.x = f.x * sc[2 * j] + sh[2 * j];
+        f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+        if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+        o[j] = pack_bf16x2(f.x, f.y);
+      }
+      *reinterpret_cast<uint4*>(p.out + pix * C + ch0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    int px = l;
+    for (; px + 3 * p.L < p.hw; px += 4 * p.L) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px + k * p.L, vg);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) emit(u[k], base + px + k * p.L);
+    }
+    for (; px < p.hw; px += p.L) emit(ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, vg), base + px);
+  }
+}
+
 // one warp per row; C <= 1280 (multiple of 8): each lane holds up to 5 vectors of 8
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
                                  float eps, const float* __restrict__ gamma,
@@ -319,6 +450,26 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   DL_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0,
                "groupnorm: bad groups=%d for C=%d", groups, C);
   DL_CHECK_ARG(C <= GN_MAX_C, "groupnorm: C=%d exceeds %d", C, GN_MAX_C);
+  if (hw <= 1024) {
+    // small images: group-sliced kernel (no grid barrier, ordinary launch)
+    const int cpg = C / groups;
+    int gpc = 0;
+    for (int g = 2; g <= groups; g <<= 1)
+      if (groups % g == 0 && (g * cpg) % 8 == 0 && g * cpg <= GNS_THREADS * 8 / 1) { gpc = g; break; }
+    if (gpc == 0 && cpg % 8 == 0) gpc = 1;
+    if (gpc > 0 && (gpc * cpg) / 8 <= GNS_THREADS) {
+      GnSlicedParams sp;
+      sp.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); sp.c0 = c0;
+      sp.x1 = reinterpret_cast<const __nv_bfloat16*>(x1); sp.c1 = c1;
+      sp.hw = hw; sp.groups = groups; sp.gpc = gpc;
+      sp.Vs = gpc * cpg / 8;
+      sp.L = GNS_THREADS / sp.Vs;
+      sp.eps = eps; sp.gamma = gamma; sp.beta = beta; sp.apply_silu = apply_silu;
+      sp.out = reinterpret_cast<__nv_bfloat16*>(out);
+      gn_sliced_kernel<<<dim3(groups / gpc, nimg), GNS_THREADS, 0, stream>>>(sp);
+      return check_launch("groupnorm(sliced)");
+    }
+  }
   GnParams p;
   p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.c0 = c0;
   p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1); p.c1 = c1;

@@ -177,7 +177,8 @@ def test_igemm_u8_image_tail():
 @pytest.mark.parametrize("B,HW,C0,C1,silu", [
     (2, 4096, 320, 0, True), (2, 1024, 640, 320, True), (3, 64, 1280, 1280, True),
     (1, 65536, 128, 0, True), (2, 256, 1280, 640, False), (1, 4096, 512, 0, False),
-    (2, 300, 256, 0, True),
+    (2, 300, 256, 0, True), (16, 64, 1280, 1280, True), (4, 1024, 640, 320, True), (3, 1024, 320, 0, False),
+    (2, 256, 1280, 640, True), (2, 16, 64, 0, True), (1, 4, 256, 128, True),
 ])
 def test_groupnorm(B, HW, C0, C1, silu):
     lib = L()
