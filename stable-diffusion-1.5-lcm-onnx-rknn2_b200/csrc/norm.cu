@@ -13,6 +13,8 @@
 // HBM traffic is therefore the algorithmic read-once + write-once (4 B/element).
 // Both phases accept two sources and emit the channel concat [x0 | x1] (UNet skip concat folded
 // into the norm: the concat tensor is never written in un-normalised form).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "dreamlab_b200.h"
 
@@ -21,9 +23,9 @@ namespace dl {
 constexpr int GN_THREADS = 512;
 constexpr int GN_MAX_C = 2560;
 constexpr int GN_MAX_GROUPS = 64;
-constexpr int GN_STAGES = 6;
+constexpr int GN_STAGES = 13;                       // 13 x 16 KB = 208 KB in flight per SM
 constexpr int GN_CHUNK_BYTES = 16 * 1024;
-constexpr long long GN_WAVE_BYTES = 24ll << 20;     // input bytes per wave of 148 CTAs (L2-resident)
+constexpr long long GN_WAVE_BYTES = 48ll << 20;     // input bytes per wave of 148 CTAs (L2-resident)
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int c0,
                                          const __nv_bfloat16* x1, int c1, long long pix, int v) {
@@ -106,7 +108,9 @@ __device__ __forceinline__ void gn_stream(const GnParams& p, uint8_t* ring, uint
 __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams p) {
   extern __shared__ __align__(128) uint8_t gn_smem[];
   uint8_t* ring = gn_smem;                                                   // GN_STAGES x 16 KB
-  float* s_sum = reinterpret_cast<float*>(gn_smem + GN_STAGES * GN_CHUNK_BYTES);   // [512*8]
+  // the 2 x 16 KB reduction scratch aliases the first two ring buffers: it is only touched
+  // after a phase's last chunk has been consumed and before the next phase issues loads
+  float* s_sum = reinterpret_cast<float*>(gn_smem);                          // [512*8]
   float* s_sq = s_sum + GN_THREADS * 8;
   __shared__ float s_mean[GN_MAX_GROUPS];
   __shared__ float s_rstd[GN_MAX_GROUPS];
@@ -509,7 +513,7 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GN_THREADS);
-  const size_t dyn_smem = (size_t)GN_STAGES * GN_CHUNK_BYTES + (size_t)2 * GN_THREADS * 8 * sizeof(float);
+  const size_t dyn_smem = (size_t)GN_STAGES * GN_CHUNK_BYTES;
   {
     static bool attr_set[64] = {false};
     int dev = 0;
