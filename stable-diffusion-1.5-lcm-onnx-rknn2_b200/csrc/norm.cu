@@ -23,8 +23,8 @@ namespace dl {
 constexpr int GN_THREADS = 512;
 constexpr int GN_MAX_C = 2560;
 constexpr int GN_MAX_GROUPS = 64;
-constexpr int GN_STAGES = 13;                       // 13 x 16 KB = 208 KB in flight per SM
-constexpr int GN_CHUNK_BYTES = 16 * 1024;
+constexpr int GN_STAGES = 6;                        // 6 x 32 KB in flight per SM
+constexpr int GN_CHUNK_BYTES = 32 * 1024;
 constexpr long long GN_WAVE_BYTES = 48ll << 20;     // input bytes per wave of 148 CTAs (L2-resident)
 
 __device__ __forceinline__ uint4 ld_vec8(const __nv_bfloat16* x0, int c0,
@@ -60,20 +60,51 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
-// Streams pixels [p_begin, p_end) of image `img` through the smem ring and calls
-// f(vec, pixel) for this thread's (channel-vector v, pixel-lane l) elements.
+// Consumer side of the ring: waits for each chunk of the slab [p_begin, p_end) of image `img`
+// and calls f(vec, pixel) for this thread's (channel-vector v, pixel-lane l) elements.  The
+// chunks were requested by the producer warp (gn_produce) in exactly the same order.
 template <class F>
-__device__ __forceinline__ void gn_stream(const GnParams& p, uint8_t* ring, uint64_t* full,
-                                          uint32_t& chunk_base, int img, int p_begin, int p_end,
-                                          int v, int l, bool lane_ok, F&& f) {
-  const int C = p.c0 + p.c1;
+__device__ __forceinline__ void gn_consume(const GnParams& p, const uint8_t* ring, uint64_t* full,
+                                           uint64_t* empty, uint32_t& chunk_base, int img,
+                                           int p_begin, int p_end, int v, int l, bool lane_ok, F&& f) {
   const int npix = p_end - p_begin;
   const int n_chunks = (npix + p.P - 1) / p.P;
   const long long pix0 = (long long)img * p.hw + p_begin;
   const size_t part0 = (size_t)p.P * p.c0 * 2;          // bytes of source 0 in a full chunk buffer
-  auto issue = [&](int i) {
+  const bool from0 = v * 8 < p.c0;
+  const size_t my_off = from0 ? ((size_t)l * p.c0 + v * 8) * 2
+                              : part0 + ((size_t)l * p.c1 + (v * 8 - p.c0)) * 2;
+  const size_t my_step = (size_t)p.L * (from0 ? p.c0 : p.c1) * 2;
+  for (int i = 0; i < n_chunks; ++i) {
     const uint32_t g = chunk_base + (uint32_t)i;
     const int stage = (int)(g % GN_STAGES);
+    mbar_wait(&full[stage], (g / GN_STAGES) & 1);
+    const uint8_t* src = ring + (size_t)stage * GN_CHUNK_BYTES + my_off;
+    const int cp = min(p.P, npix - i * p.P);
+    if (lane_ok) {
+      const long long pixc = pix0 + (long long)i * p.P;
+      for (int px = l; px < cp; px += p.L, src += my_step)
+        f(*reinterpret_cast<const uint4*>(src), pixc + px);
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[stage]);     // this warp is done with the buffer
+  }
+  chunk_base += (uint32_t)n_chunks;
+}
+
+// Producer (one elected thread): requests the chunks of a slab; runs ahead of the consumers by
+// up to GN_STAGES buffers, across phase and wave boundaries (inputs are read-only).
+__device__ __forceinline__ void gn_produce(const GnParams& p, uint8_t* ring, uint64_t* full,
+                                           uint64_t* empty, uint32_t& chunk_base, int img,
+                                           int p_begin, int p_end) {
+  const int npix = p_end - p_begin;
+  const int n_chunks = (npix + p.P - 1) / p.P;
+  const long long pix0 = (long long)img * p.hw + p_begin;
+  const size_t part0 = (size_t)p.P * p.c0 * 2;
+  for (int i = 0; i < n_chunks; ++i) {
+    const uint32_t g = chunk_base + (uint32_t)i;
+    const int stage = (int)(g % GN_STAGES);
+    mbar_wait(&empty[stage], ((g / GN_STAGES) & 1) ^ 1);
     const int cp = min(p.P, npix - i * p.P);
     uint8_t* buf = ring + (size_t)stage * GN_CHUNK_BYTES;
     const uint32_t b0 = (uint32_t)cp * p.c0 * 2, b1 = (uint32_t)cp * p.c1 * 2;
@@ -81,54 +112,52 @@ __device__ __forceinline__ void gn_stream(const GnParams& p, uint8_t* ring, uint
     bulk_load_1d(buf, p.x0 + (pix0 + (long long)i * p.P) * p.c0, b0, &full[stage]);
     if (p.c1 > 0)
       bulk_load_1d(buf + part0, p.x1 + (pix0 + (long long)i * p.P) * p.c1, b1, &full[stage]);
-  };
-  if (threadIdx.x == 0)
-    for (int i = 0; i < min(GN_STAGES, n_chunks); ++i) issue(i);
-  const bool from0 = v * 8 < p.c0;
-  for (int i = 0; i < n_chunks; ++i) {
-    const uint32_t g = chunk_base + (uint32_t)i;
-    const int stage = (int)(g % GN_STAGES);
-    mbar_wait(&full[stage], (g / GN_STAGES) & 1);
-    const uint8_t* buf = ring + (size_t)stage * GN_CHUNK_BYTES;
-    const int cp = min(p.P, npix - i * p.P);
-    if (lane_ok) {
-      for (int px = l; px < cp; px += p.L) {
-        const uint8_t* src = from0 ? buf + ((size_t)px * p.c0 + v * 8) * 2
-                                   : buf + part0 + ((size_t)px * p.c1 + (v * 8 - p.c0)) * 2;
-        f(*reinterpret_cast<const uint4*>(src), pix0 + (long long)i * p.P + px);
-      }
-    }
-    __syncthreads();                                     // everyone is done with this buffer
-    if (threadIdx.x == 0 && i + GN_STAGES < n_chunks) issue(i + GN_STAGES);
   }
   chunk_base += (uint32_t)n_chunks;
-  (void)C;
 }
 
-__global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams p) {
+__global__ void __launch_bounds__(GN_THREADS + 32, 1) gn_fused_kernel(const GnParams p) {
   extern __shared__ __align__(128) uint8_t gn_smem[];
-  uint8_t* ring = gn_smem;                                                   // GN_STAGES x 16 KB
-  // the 2 x 16 KB reduction scratch aliases the first two ring buffers: it is only touched
-  // after a phase's last chunk has been consumed and before the next phase issues loads
-  float* s_sum = reinterpret_cast<float*>(gn_smem);                          // [512*8]
+  uint8_t* ring = gn_smem;                                                   // GN_STAGES x chunk
+  float* s_sum = reinterpret_cast<float*>(gn_smem + GN_STAGES * GN_CHUNK_BYTES);   // [512*8]
   float* s_sq = s_sum + GN_THREADS * 8;
   __shared__ float s_mean[GN_MAX_GROUPS];
   __shared__ float s_rstd[GN_MAX_GROUPS];
   __shared__ __align__(8) uint64_t full[GN_STAGES];
+  __shared__ __align__(8) uint64_t empty[GN_STAGES];
   const int C = p.c0 + p.c1;
   const int cpg = C / p.groups;
-  const int v = threadIdx.x % p.V;
-  const int l = threadIdx.x / p.V;
-  const bool lane_ok = l < p.L;                       // threads beyond V*L idle in the loops
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GN_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < GN_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], GN_THREADS / 32); }
     fence_barrier_init();
   }
   __syncthreads();
   uint32_t chunk_base = 0;
   const int num_waves = (p.nimg + p.wave_imgs - 1) / p.wave_imgs;
   const int pps = (p.hw + p.slabs - 1) / p.slabs;     // pixels per slab
+
+  if (warp == GN_THREADS / 32) {
+    // ============================ producer warp ============================
+    if (lane == 0) {
+      for (int w = 0; w < num_waves; ++w) {
+        const int item = blockIdx.x;
+        const int img = w * p.wave_imgs + item / p.slabs;
+        const int p_begin = (item % p.slabs) * pps;
+        const int p_end = min(p.hw, p_begin + pps);
+        const bool active = (item < p.wave_imgs * p.slabs) && (img < p.nimg) && (p_end > p_begin);
+        if (!active) continue;
+        gn_produce(p, ring, full, empty, chunk_base, img, p_begin, p_end);   // phase A stream
+        gn_produce(p, ring, full, empty, chunk_base, img, p_begin, p_end);   // phase B stream
+      }
+    }
+    return;
+  }
+
+  // ============================ 16 consumer warps ============================
+  const int v = threadIdx.x % p.V;
+  const int l = threadIdx.x / p.V;
+  const bool lane_ok = l < p.L;                       // threads beyond V*L idle in the loops
   for (int w = 0; w < num_waves; ++w) {
     const int item = blockIdx.x;
     const int img = w * p.wave_imgs + item / p.slabs;
@@ -142,16 +171,16 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
       float s[8], q[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-      gn_stream(p, ring, full, chunk_base, img, p_begin, p_end, v, l, lane_ok,
-                [&](const uint4& u, long long) {
-                  const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+      gn_consume(p, ring, full, empty, chunk_base, img, p_begin, p_end, v, l, lane_ok,
+                 [&](const uint4& u, long long) {
+                   const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float2 f = unpack_bf16x2(ww[j]);
-                    s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-                    s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-                  }
-                });
+                   for (int j = 0; j < 4; ++j) {
+                     const float2 f = unpack_bf16x2(ww[j]);
+                     s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+                     s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+                   }
+                 });
       if (lane_ok) {
         // layout [l][C]: channel-contiguous so the per-group gather below is a linear walk
 #pragma unroll
@@ -161,7 +190,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
         }
       }
     }
-    __syncthreads();
+    named_bar_sync(1, GN_THREADS);
     if (active) {
       // one warp per group (round-robin): lanes stride over the L x cpg partial sums, then a
       // fixed-order shuffle tree => deterministic
@@ -183,26 +212,44 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
         }
       }
     }
-    grid_barrier(p.counter, (unsigned int)(w + 1) * gridDim.x);
+    // grid barrier among the consumer threads of all CTAs (the producers keep prefetching)
+    named_bar_sync(1, GN_THREADS);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(p.counter, 1u);
+      const unsigned int target = (unsigned int)(w + 1) * gridDim.x;
+      while (*reinterpret_cast<volatile unsigned int*>(p.counter) < target) __nanosleep(32);
+      __threadfence();
+    }
+    named_bar_sync(1, GN_THREADS);
     // ---------------- phase B: merge my image's partials, normalise my slab ----------------
     if (active) {
       {
         // Chan merge of the image's slab partials: warp per group, lane i folds slabs
-        // i, i+32, ... (all loads issued up front), then a fixed shuffle tree => deterministic
+        // i, i+32, ... (loads issued together), then a fixed shuffle tree => deterministic
         const int first = (item / p.slabs) * p.slabs;
         for (int g = warp; g < p.groups; g += GN_THREADS / 32) {
+          float2 mm[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int sidx = lane + 32 * k;
+            mm[k] = make_float2(0.f, 0.f);
+            if (sidx < p.slabs)
+              mm[k] = __ldcg(reinterpret_cast<const float2*>(
+                  part + ((size_t)(first + sidx) * p.groups + g) * 2));
+          }
           float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
-          for (int sidx = lane; sidx < p.slabs; sidx += 32) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            const int sidx = lane + 32 * k;
             const int pb = sidx * pps;
             const int pe = min(p.hw, pb + pps);
-            if (pe <= pb) continue;
+            if (sidx >= p.slabs || pe <= pb) continue;
             const float n_b = (float)(pe - pb) * (float)cpg;
-            const float2 mm = __ldcg(reinterpret_cast<const float2*>(
-                part + ((size_t)(first + sidx) * p.groups + g) * 2));
             const float n_ab = n_a + n_b;
-            const float delta = mm.x - mean_a;
+            const float delta = mm[k].x - mean_a;
             mean_a += delta * (n_b / n_ab);
-            m2_a += mm.y + delta * delta * (n_a * n_b / n_ab);
+            m2_a += mm[k].y + delta * delta * (n_a * n_b / n_ab);
             n_a = n_ab;
           }
 #pragma unroll
@@ -224,7 +271,7 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
           }
         }
       }
-      __syncthreads();
+      named_bar_sync(2, GN_THREADS);
       float sc[8], sh[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -233,23 +280,23 @@ __global__ void __launch_bounds__(GN_THREADS, 1) gn_fused_kernel(const GnParams 
         sc[j] = s_rstd[g] * __ldg(p.gamma + c);
         sh[j] = __ldg(p.beta + c) - s_mean[g] * sc[j];
       }
-      gn_stream(p, ring, full, chunk_base, img, p_begin, p_end, v, l, lane_ok,
-                [&](const uint4& u, long long pix) {
-                  const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-                  uint32_t o[4];
+      __nv_bfloat16* outv = p.out + v * 8;
+      gn_consume(p, ring, full, empty, chunk_base, img, p_begin, p_end, v, l, lane_ok,
+                 [&](const uint4& u, long long pix) {
+                   const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+                   uint32_t o[4];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    float2 f = unpack_bf16x2(ww[j]);
-                    f.x = f.x * sc[2 * j] + sh[2 * j];
-                    f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
-                    if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
-                    o[j] = pack_bf16x2(f.x, f.y);
-                  }
-                  *reinterpret_cast<uint4*>(p.out + pix * C + v * 8) =
-                      make_uint4(o[0], o[1], o[2], o[3]);
-                });
+                   for (int j = 0; j < 4; ++j) {
+                     float2 f = unpack_bf16x2(ww[j]);
+                     f.x = f.x * sc[2 * j] + sh[2 * j];
+                     f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+                     if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+                     o[j] = pack_bf16x2(f.x, f.y);
+                   }
+                   *reinterpret_cast<uint4*>(outv + pix * C) = make_uint4(o[0], o[1], o[2], o[3]);
+                 });
     }
-    __syncthreads();      // s_sum / s_mean are reused by the next wave
+    named_bar_sync(1, GN_THREADS);      // s_sum / s_mean are reused by the next wave
   }
 }
 
@@ -502,6 +549,7 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   if (slabs > grid) slabs = grid;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
+  if (slabs > 160) slabs = 160;                       // merge step folds <= 5 x 32 partials per group
   p.slabs = (int)slabs;
   long long wave = grid / p.slabs;                     // images that fit one wave of CTAs
   if (wave > nimg) wave = nimg;
@@ -512,8 +560,8 @@ extern "C" int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int 
   if (e != cudaSuccess) { set_error("groupnorm: memset: %s", cudaGetErrorString(e)); return 2; }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(GN_THREADS);
-  const size_t dyn_smem = (size_t)GN_STAGES * GN_CHUNK_BYTES;
+  cfg.blockDim = dim3(GN_THREADS + 32);            // 16 consumer warps + 1 producer warp
+  const size_t dyn_smem = (size_t)GN_STAGES * GN_CHUNK_BYTES + (size_t)2 * GN_THREADS * 8 * sizeof(float);
   {
     static bool attr_set[64] = {false};
     int dev = 0;
