@@ -287,6 +287,12 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ---- small numeric helpers ----
+// two exp2 per MUFU instruction: packed bf16 in, packed bf16 out
+__device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t packed) {
+  uint32_t r;
+  asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(packed));
+  return r;
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
