@@ -45,6 +45,10 @@ struct AttnParams {
   float scale_log2;
 };
 
+// kOnes: V carries a ones column, the PV MMA accumulates the softmax denominator (product path).
+// A compile-time flag: as a runtime branch the unused row-sum code still cost ~190 predicated
+// instructions per thread and tile in the exp loop.
+template <bool kOnes>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -229,7 +233,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           const float p0 = fast_exp2(fmaf(__uint_as_float(u0), p.scale_log2, -m_new));
           const float p1 = fast_exp2(fmaf(__uint_as_float(u1), p.scale_log2, -m_new));
           const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-          if (p.l_col < 0) {
+          if (!kOnes) {
             // no ones column in V: sum what the tensor core will multiply (bf16-rounded P)
             const float2 pf = __bfloat1622float2(pb);
             lsum0 += pf.x;
@@ -266,7 +270,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // epilogue: O / l
     mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
     tc_fence_after();
-    if (p.l_col >= 0) {
+    if (kOnes) {
       // the ones column of V made the tensor core accumulate l = sum_j P_j (rescaled with O)
       uint32_t oo[16];
       tmem_ld16(o_tmem + (uint32_t)(p.l_col & ~15), oo);
@@ -379,13 +383,17 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024 - 3072);   // minus the static xch buffer
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               227 * 1024 - 3072);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
   dim3 grid((sq + AT_TILE - 1) / AT_TILE, heads, batch);
-  attn_tc_kernel<<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  if (p.l_col >= 0) attn_tc_kernel<true><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  else attn_tc_kernel<false><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   return check_launch("attention(tc)");
 }
 
