@@ -106,6 +106,10 @@ int dl_attention(const void* q, long long ldq, const void* k, long long ldk, con
                  long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                  int skv, int heads, int d, float scale, int impl, int v_ones, void* stream);
 
+/* debug aid: CTA (0,0,0) of the tcgen05 attention kernel writes per-tile clock stamps of its MMA
+ * and softmax warps into this device buffer of 256 int64 (NULL switches tracing off).          */
+int dl_debug_attention_trace(void* device_buf_i64_256);
+
 /* ---- time / guidance embedding pieces (diffusers Timesteps + TimestepEmbedding, K9) ------- */
 /* out[b, :] = [cos(t_b f_i), sin(t_b f_i)], f_i = exp(-ln(1e4) i/half)  (flip_sin_to_cos)     */
 int dl_timestep_sinusoid(const float* t, int batch, int dim, float* out, void* stream);

@@ -42,6 +42,7 @@ struct AttnParams {
   int stages;        // K/V smem ring depth
   int sbuf;          // S/P TMEM buffers (2: S_{j+1} overlaps softmax_j; 1: two CTAs per SM)
   int tmem_cols;
+  long long* trace;  // debug: per-tile clock stamps of CTA (0,0,0), or NULL
   float scale_log2;
 };
 
@@ -150,6 +151,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         const int sb = j % p.sbuf;
         mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
         tc_fence_after();
+        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16;
+        if (tr) p.trace[j * 16 + 0] = clock64();
         {
           const uint32_t sv_addr = smem_u32(sKV + (size_t)stage * kv_bytes + k_bytes);
           const uint32_t p_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
@@ -162,12 +165,15 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           }
           umma_commit(&kv_empty[stage]);
           umma_commit(pv_done);
+          if (tr) p.trace[j * 16 + 1] = clock64();
         }
         if (!prefetch_s && j + 1 < n_tiles) {
           // in-order tensor pipe: S_{j+1} may overwrite the S/P buffer right behind PV_j
           mbar_wait(&kv_full[nstage], nphase);
           tc_fence_after();
+          if (tr) p.trace[j * 16 + 2] = clock64();
           issue_s(j + 1, nstage);
+          if (tr) p.trace[j * 16 + 3] = clock64();
         }
         stage = nstage;
         phase = nphase;
@@ -188,6 +194,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * AT_TILE);
       mbar_wait(&s_full[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 &&
+                      threadIdx.x == 64;
+      if (tr) p.trace[j * 16 + 4] = clock64();
       const int kbase = j * AT_TILE + ch * 64;
       const bool need_mask = (j * AT_TILE + AT_TILE > p.skv);  // only the last tile (warp-uniform)
       // my 64 S columns -> registers with ONE TMEM round trip (both loads in flight together);
@@ -196,6 +205,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tmem_ld32(s_tmem + (uint32_t)(ch * 64), sa);
       tmem_ld32(s_tmem + (uint32_t)(ch * 64 + 32), sb32);
       tmem_ld_wait();
+      if (tr) p.trace[j * 16 + 5] = clock64();
       if (need_mask) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -218,7 +228,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       // exchange the half-row maxima; after this barrier every thread of the CTA has its S
       // values in registers, so P may overwrite the S columns right away
       xch[j & 1][ch][r] = mx;
+      if (tr) p.trace[j * 16 + 6] = clock64();
       named_bar_sync(1, 256);
+      if (tr) p.trace[j * 16 + 7] = clock64();
       mx = fmaxf(mx, xch[j & 1][ch ^ 1][r]);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float corr = fast_exp2(m_run - m_new);
@@ -245,7 +257,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       l_run = l_run * corr + (lsum0 + lsum1);
       m_run = m_new;
+      if (tr) p.trace[j * 16 + 8] = clock64();
       tmem_st_wait();
+      if (tr) p.trace[j * 16 + 9] = clock64();
       if (j > 0) {
         // O must hold PV_{j-1} before it is rescaled and before PV_j accumulates on top
         mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
@@ -266,6 +280,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[sb]);
+      if (tr) p.trace[j * 16 + 10] = clock64();
     }
     // epilogue: O / l
     mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
@@ -315,6 +330,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
+static long long* g_attn_trace = nullptr;
+
 static int attn_tc_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                           long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                           int skv, int heads, int d, float scale, int v_ones, cudaStream_t stream) {
@@ -343,6 +360,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   DL_CHECK_ARG(p.dv <= 256, "attention(tc): head dim %d > 240 unsupported (use the GEMM path)", d);
   p.nchunk_v = (p.dv + 63) / 64;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
   const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
   const int overhead = 1024 + 256 + 2048;          // alignment slack, barriers, static xch
@@ -398,6 +416,11 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
 }
 
 }  // namespace dl
+
+extern "C" int dl_debug_attention_trace(void* device_buf_i64_256) {
+  dl::g_attn_trace = reinterpret_cast<long long*>(device_buf_i64_256);
+  return 0;
+}
 
 extern "C" int dl_attention(const void* q, long long ldq, const void* k, long long ldk,
                             const void* v, long long ldv, int dh_stride, void* out, long long ldo,

@@ -113,7 +113,11 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop (all address/coordinate math stays warp-uniform, i.e. in
+    // uniform registers); only the issue instructions are predicated on one lane.  Running the
+    // loop on a single divergent lane cost ~100 cycles per TMA/MMA issue (R2UR round trips).
+    {
+      const bool issuer = (lane == 0);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -134,12 +138,15 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
             uint8_t* sb = sa + A_TILE_BYTES;
-            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-            if (c < p.kc0)
-              tma_load_4d(sa, &p.tmA0, &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
-            else
-              tma_load_4d(sa, &p.tmA1, &full_bar[stage], (c - p.kc0) * BK, x0 + dx, y0 + dy, n0);
-            tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, n_blk * p.BN);
+            if (issuer) {
+              mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+              if (c < p.kc0)
+                tma_load_4d(sa, &p.tmA0, &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
+              else
+                tma_load_4d(sa, &p.tmA1, &full_bar[stage], (c - p.kc0) * BK, x0 + dx, y0 + dy, n0);
+              tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, n_blk * p.BN);
+            }
+            __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -149,17 +156,24 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + A_TILE_BYTES;
-          mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_4d(sa, &p.tmR, &full_bar[stage], n_blk * p.BN + rc * BK, x0, y0, n0);
-          tma_load_2d(sb, &p.tmI, &full_bar[stage], rc * BK, 0);
+          if (issuer) {
+            mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+            tma_load_4d(sa, &p.tmR, &full_bar[stage], n_blk * p.BN + rc * BK, x0, y0, n0);
+            tma_load_2d(sb, &p.tmI, &full_bar[stage], rc * BK, 0);
+          }
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Warp-uniform loop; one lane issues tcgen05.mma / tcgen05.commit.
+    {
+      const bool issuer = (lane == 0);
       const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.BN);
+      const uint32_t desc_hi = umma_desc_hi_sw128(1024);
+      const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -171,20 +185,23 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         for (int kb = 0; kb < num_kb + p.res_chunks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + A_TILE_BYTES;
-          const uint64_t adesc = umma_desc_kmajor_sw128(sa, 1024);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(sb, 1024);
+          const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes);
+          const uint32_t a_lo = umma_desc_lo(sa);
+          const uint32_t b_lo = umma_desc_lo(sa + A_TILE_BYTES);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
-            umma_ss(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                    (kb > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
+              umma_ss_lohi(d_tmem, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), desc_hi, idesc,
+                           (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);          // frees the smem slot when MMAs retire
           }
-          umma_commit(&empty_bar[stage]);            // frees the smem slot when MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);                // accumulator ready for the epilogue
+        if (issuer) umma_commit(&tfull_bar[acc]);    // accumulator ready for the epilogue
+        __syncwarp();
         if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
         else acc_phase ^= 1;
       }

@@ -20,6 +20,7 @@ ATTN_TC, ATTN_SIMT = 0, 1
 EXPORTS = [
     "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_fill_identity",
     "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention",
+    "dl_debug_attention_trace",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
 ]
