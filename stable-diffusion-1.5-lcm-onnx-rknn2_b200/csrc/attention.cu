@@ -95,89 +95,106 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
-      const int col0 = h * p.dh_stride;
+    // warp-uniform loop, one lane issues (see igemm.cu: a loop on a single divergent lane pays
+    // ~100 cycles of R2UR round trips per TMA / MMA issue)
+    const bool issuer = (lane == 0);
+    const int col0 = h * p.dh_stride;
+    if (issuer) {
       mbar_expect_tx(q_full, (uint32_t)q_bytes);
       for (int c = 0; c < p.nchunk_qk; ++c)
         tma_load_2d(sQ + c * AT_CHUNK_BYTES, &p.tmQ, q_full, col0 + c * 64, b * p.sq + q0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sK = sKV + (size_t)stage * kv_bytes;
-        uint8_t* sV = sK + k_bytes;
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      uint8_t* sK = sKV + (size_t)stage * kv_bytes;
+      uint8_t* sV = sK + k_bytes;
+      const int row = b * p.skv + j * AT_TILE;
+      if (issuer) {
         mbar_expect_tx(&kv_full[stage], (uint32_t)kv_bytes);
-        const int row = b * p.skv + j * AT_TILE;
         for (int c = 0; c < p.nchunk_qk; ++c)
           tma_load_2d(sK + c * AT_CHUNK_BYTES, &p.tmK, &kv_full[stage], col0 + c * 64, row);
         for (int c = 0; c < p.nchunk_v; ++c)
           tma_load_2d(sV + c * AT_CHUNK_BYTES, &p.tmV, &kv_full[stage], col0 + c * 64, row);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);             // Q K^T
-      const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv, 0, 1);  // P V (B MN-major)
-      const uint32_t sq_addr = smem_u32(sQ);
-      auto issue_s = [&](int j, int stage) {
-        const uint32_t sk_addr = smem_u32(sKV + (size_t)stage * kv_bytes);
-        const int sb = j % p.sbuf;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+    const bool issuer = (lane == 0);
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);             // Q K^T
+    const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv, 0, 1);  // P V (B MN-major)
+    const uint32_t hi_k = umma_desc_hi_sw128(1024);                       // K-major operands
+    const uint32_t sq_addr = smem_u32(sQ);
+    const uint32_t skv_addr = smem_u32(sKV);
+    auto issue_s = [&](int j, int stage) {
+      const uint32_t sk_addr = skv_addr + (uint32_t)(stage * kv_bytes);
+      const int sb = j % p.sbuf;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+      if (issuer) {
         for (int ks = 0; ks < p.ksteps; ++ks) {
           const uint32_t off = (uint32_t)((ks >> 2) * AT_CHUNK_BYTES + (ks & 3) * 32);
-          umma_ss(d_tmem, umma_desc_kmajor_sw128(sq_addr + off, 1024),
-                  umma_desc_kmajor_sw128(sk_addr + off, 1024), idesc_s, ks > 0 ? 1u : 0u);
+          umma_ss_lohi(d_tmem, umma_desc_lo(sq_addr + off), umma_desc_lo(sk_addr + off), hi_k, idesc_s,
+                       ks > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[sb]);
-      };
-      const bool prefetch_s = (p.sbuf == 2 && p.stages >= 2);
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
-        if (prefetch_s && j + 1 < n_tiles) {
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          issue_s(j + 1, nstage);
-        }
-        const int sb = j % p.sbuf;
-        mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
+      }
+      __syncwarp();
+    };
+    const bool prefetch_s = (p.sbuf == 2 && p.stages >= 2);
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      int nstage = stage + 1;
+      uint32_t nphase = phase;
+      if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
+      if (prefetch_s && j + 1 < n_tiles) {
+        mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
-        const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16;
-        if (tr) p.trace[j * 16 + 0] = clock64();
-        {
-          const uint32_t sv_addr = smem_u32(sKV + (size_t)stage * kv_bytes + k_bytes);
-          const uint32_t p_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
-          const uint32_t o_tmem = tmem_base + o_col;
+        issue_s(j + 1, nstage);
+      }
+      const int sb = j % p.sbuf;
+      mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
+      tc_fence_after();
+      const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 && issuer;
+      if (tr) p.trace[j * 16 + 0] = clock64();
+      {
+        const uint32_t sv_addr = skv_addr + (uint32_t)(stage * kv_bytes + k_bytes);
+        const uint32_t p_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+        const uint32_t o_tmem = tmem_base + o_col;
+        // V is the MN-major B operand: LBO = stride between 64-wide d chunks, SBO = 8-key groups
+        const uint32_t v_lo = umma_desc_lo(sv_addr, AT_CHUNK_BYTES);
+        if (issuer) {
+#pragma unroll
           for (int ks = 0; ks < AT_TILE / 16; ++ks) {
-            // 16 keys = two 8-row swizzle atoms = 2048 B; P advances 8 packed columns
-            umma_ts(o_tmem, p_tmem + (uint32_t)(ks * 8),
-                    umma_desc_mnmajor_sw128(sv_addr + (uint32_t)(ks * 2048), AT_CHUNK_BYTES, 1024),
-                    idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+            // 16 keys = two 8-row swizzle atoms = 2048 B (+128 in 16-byte units); P advances 8
+            // packed columns
+            umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
+                         (j > 0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(&kv_empty[stage]);
           umma_commit(pv_done);
-          if (tr) p.trace[j * 16 + 1] = clock64();
         }
-        if (!prefetch_s && j + 1 < n_tiles) {
-          // in-order tensor pipe: S_{j+1} may overwrite the S/P buffer right behind PV_j
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          if (tr) p.trace[j * 16 + 2] = clock64();
-          issue_s(j + 1, nstage);
-          if (tr) p.trace[j * 16 + 3] = clock64();
-        }
-        stage = nstage;
-        phase = nphase;
+        __syncwarp();
+        if (tr) p.trace[j * 16 + 1] = clock64();
       }
+      if (!prefetch_s && j + 1 < n_tiles) {
+        // in-order tensor pipe: S_{j+1} may overwrite the S/P buffer right behind PV_j
+        mbar_wait(&kv_full[nstage], nphase);
+        tc_fence_after();
+        if (tr) p.trace[j * 16 + 2] = clock64();
+        issue_s(j + 1, nstage);
+        if (tr) p.trace[j * 16 + 3] = clock64();
+      }
+      stage = nstage;
+      phase = nphase;
     }
   } else {
     // ============================ softmax + epilogue ============================
