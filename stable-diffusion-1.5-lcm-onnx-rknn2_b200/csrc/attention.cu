@@ -97,7 +97,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // ============================ TMA producer ============================
     // warp-uniform loop, one lane issues (see igemm.cu: a loop on a single divergent lane pays
     // ~100 cycles of R2UR round trips per TMA / MMA issue)
-    const bool issuer = (lane == 0);
+    const bool issuer = elect_one();   // elect.sync: the compiler keeps the issue path uniform
     const int col0 = h * p.dh_stride;
     if (issuer) {
       mbar_expect_tx(q_full, (uint32_t)q_bytes);
@@ -124,7 +124,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
-    const bool issuer = (lane == 0);
+    const bool issuer = elect_one();   // elect.sync: the compiler keeps the issue path uniform
     const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);             // Q K^T
     const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv, 0, 1);  // P V (B MN-major)
     const uint32_t hi_k = umma_desc_hi_sw128(1024);                       // K-major operands

@@ -117,7 +117,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     // uniform registers); only the issue instructions are predicated on one lane.  Running the
     // loop on a single divergent lane cost ~100 cycles per TMA/MMA issue (R2UR round trips).
     {
-      const bool issuer = (lane == 0);
+      const bool issuer = elect_one();   // elect.sync: the compiler keeps the issue path uniform
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -170,7 +170,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     // ===================== MMA issuer =====================
     // Warp-uniform loop; one lane issues tcgen05.mma / tcgen05.commit.
     {
-      const bool issuer = (lane == 0);
+      const bool issuer = elect_one();   // elect.sync: the compiler keeps the issue path uniform
       const uint32_t idesc = umma_idesc_bf16(BM, (uint32_t)p.BN);
       const uint32_t desc_hi = umma_desc_hi_sw128(1024);
       const uint32_t smem_base = smem_u32(smem);
