@@ -49,7 +49,7 @@ struct AttnParams {
 // kOnes: V carries a ones column, the PV MMA accumulates the softmax denominator (product path).
 // A compile-time flag: as a runtime branch the unused row-sum code still cost ~190 predicated
 // instructions per thread and tile in the exp loop.
-template <bool kOnes>
+template <bool kOnes, bool kBf16Exp>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -134,11 +134,15 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const uint32_t sk_addr = skv_addr + (uint32_t)(stage * kv_bytes);
       const int sb = j % p.sbuf;
       const uint32_t d_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+      const uint32_t q_lo = umma_desc_lo(sq_addr), k_lo = umma_desc_lo(sk_addr);
       if (issuer) {
-        for (int ks = 0; ks < p.ksteps; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * AT_CHUNK_BYTES + (ks & 3) * 32);
-          umma_ss_lohi(d_tmem, umma_desc_lo(sq_addr + off), umma_desc_lo(sk_addr + off), hi_k, idesc_s,
-                       ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 12; ++ks) {               // d <= 192: at most 12 K-steps of 16
+          if (ks < p.ksteps) {
+            // next 64-wide chunk every 4 steps (16 KB = 1024 x 16 B), 32 B = 2 units inside a row
+            const uint32_t off = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
+            umma_ss_lohi(d_tmem, q_lo + off, k_lo + off, hi_k, idesc_s, ks > 0 ? 1u : 0u);
+          }
         }
         umma_commit(&s_full[sb]);
       }
@@ -249,7 +253,11 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       named_bar_sync(1, 256);
       if (tr) p.trace[j * 16 + 7] = clock64();
       mx = fmaxf(mx, xch[j & 1][ch ^ 1][r]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      // lazy running max: only move it when the tile max exceeds it by more than 2^8 — P then
+      // stays <= 256 (exact in bf16/fp32 range), the O rescale becomes rare instead of
+      // per-tile, and the final O / l is unchanged because l sees the same P
+      const float m_tile = mx * p.scale_log2;
+      const float m_new = (m_tile > m_run + 8.0f) ? m_tile : m_run;
       const float corr = fast_exp2(m_run - m_new);
       float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
@@ -259,9 +267,18 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         for (int i = 0; i < 16; ++i) {
           const uint32_t u0 = c == 0 ? sa[2 * i] : sb32[2 * i];
           const uint32_t u1 = c == 0 ? sa[2 * i + 1] : sb32[2 * i + 1];
-          const float p0 = fast_exp2(fmaf(__uint_as_float(u0), p.scale_log2, -m_new));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(u1), p.scale_log2, -m_new));
-          const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+          const float x0 = fmaf(__uint_as_float(u0), p.scale_log2, -m_new);
+          const float x1 = fmaf(__uint_as_float(u1), p.scale_log2, -m_new);
+          __nv_bfloat162 pb;
+          if (kBf16Exp) {
+            // two exponentials per MUFU op; P is rounded to bf16 for the PV MMA anyway, and the
+            // denominator comes from the same P through V's ones column
+            const __nv_bfloat162 xb = __floats2bfloat162_rn(x0, x1);
+            const uint32_t e = ex2_bf16x2(*reinterpret_cast<const uint32_t*>(&xb));
+            pb = *reinterpret_cast<const __nv_bfloat162*>(&e);
+          } else {
+            pb = __floats2bfloat162_rn(fast_exp2(x0), fast_exp2(x1));
+          }
           if (!kOnes) {
             // no ones column in V: sum what the tensor core will multiply (bf16-rounded P)
             const float2 pf = __bfloat1622float2(pb);
@@ -418,17 +435,17 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024 - 3072);   // minus the static xch buffer
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      e = cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                227 * 1024 - 3072);
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
   dim3 grid((sq + AT_TILE - 1) / AT_TILE, heads, batch);
-  if (p.l_col >= 0) attn_tc_kernel<true><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
-  else attn_tc_kernel<false><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  if (p.l_col >= 0) attn_tc_kernel<true, true><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  else attn_tc_kernel<false, false><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   return check_launch("attention(tc)");
 }
 

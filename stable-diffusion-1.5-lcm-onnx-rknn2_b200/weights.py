@@ -47,12 +47,12 @@ def pack_upsample_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
     o, i = w.shape[0], w.shape[1]
     w = w.float()
     groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}       # parity -> (taps of low-res -1+p, of +p)
-    out = torch.zeros(4, o, 2, 2, i)
+    out = torch.zeros(4, o, 2, 2, i, device=w.device)
     for a in (0, 1):
         for b in (0, 1):
             for ty in (0, 1):
                 for tx in (0, 1):
-                    acc = torch.zeros(o, i)
+                    acc = torch.zeros(o, i, device=w.device)
                     for ky in groups[a][ty]:
                         for kx in groups[b][tx]:
                             acc += w[:, :, ky, kx]
