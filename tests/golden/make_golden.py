@@ -25,16 +25,17 @@ def tiny():
                         final_latents=rec["latents"][-1].numpy(), image=img)
 
 
-def full(size=512, steps=4):
+def full(size=512, steps=4, tiling=False):
     """BASELINE config C1: SD1.5-LCM arch, random-init seed 0, 512x512, 4 steps, gs 1.0, B=1."""
     torch.set_num_threads(os.cpu_count())
     unet, vae = build_random_init(seed=0)
     pe, lat, noise = synthetic_inputs(1, size, size, steps)
     rec = {}
-    img = run_pipeline(unet, vae, pe, lat, noise, steps, 1.0, record=rec, tiling=False)
+    img = run_pipeline(unet, vae, pe, lat, noise, steps, 1.0, record=rec, tiling=tiling)
+    # noise_pred / latents as fp16 keep the fixture small (they are compared at 2e-2)
     np.savez_compressed(os.path.join(HERE, f"sd15_lcm_{size}_{steps}step.npz"),
-                        noise_pred=torch.stack(rec["noise_pred"]).numpy().astype(np.float32),
-                        latents=torch.stack(rec["latents"]).numpy().astype(np.float32),
+                        noise_pred=torch.stack(rec["noise_pred"]).numpy().astype(np.float32 if size <= 512 else np.float16),
+                        latents=torch.stack(rec["latents"]).numpy().astype(np.float32 if size <= 512 else np.float16),
                         image=img)
 
 
@@ -42,3 +43,5 @@ if __name__ == "__main__":
     tiny()
     if "--full" in sys.argv:
         full()
+    if "--c3" in sys.argv:
+        full(768, 8)          # BASELINE config C3 geometry (B=1), untiled VAE decode
