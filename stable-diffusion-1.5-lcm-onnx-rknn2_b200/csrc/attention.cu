@@ -39,6 +39,7 @@ struct AttnParams {
   int dv;            // PV MMA N = O columns (multiple of 16; includes the ones column if any)
   int nchunk_v;      // 64-column TMA boxes per V tile
   int l_col;         // O column that accumulates the softmax denominator (V ones column), or -1
+  int kt;            // keys per KV tile (128 / 96 / 64): S columns, PV depth, TMA box rows
   int stages;        // K/V smem ring depth
   int sbuf;          // S/P TMEM buffers (2: S_{j+1} overlaps softmax_j; 1: two CTAs per SM)
   int tmem_cols;
@@ -57,8 +58,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
-  const int k_bytes = q_bytes;
-  const int v_bytes = p.nchunk_v * AT_CHUNK_BYTES;
+  const int kchunk = p.kt * 128;                          // one [kt rows x 64 bf16] swizzled block
+  const int k_bytes = p.nchunk_qk * kchunk;
+  const int v_bytes = p.nchunk_v * kchunk;
   const int kv_bytes = k_bytes + v_bytes;
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + q_bytes;
@@ -74,8 +76,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_TILE;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = (p.skv + AT_TILE - 1) / AT_TILE;
-  const uint32_t o_col = (uint32_t)(p.sbuf * AT_TILE);   // TMEM: S/P buffers first, then O
+  const int n_tiles = (p.skv + p.kt - 1) / p.kt;
+  const uint32_t o_col = (uint32_t)(p.sbuf * p.kt);      // TMEM: S/P buffers first, then O
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -111,13 +113,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       mbar_wait(&kv_empty[stage], phase ^ 1);
       uint8_t* sK = sKV + (size_t)stage * kv_bytes;
       uint8_t* sV = sK + k_bytes;
-      const int row = b * p.skv + j * AT_TILE;
+      const int row = b * p.skv + j * p.kt;
       if (issuer) {
         mbar_expect_tx(&kv_full[stage], (uint32_t)kv_bytes);
         for (int c = 0; c < p.nchunk_qk; ++c)
-          tma_load_2d(sK + c * AT_CHUNK_BYTES, &p.tmK, &kv_full[stage], col0 + c * 64, row);
+          tma_load_2d(sK + c * kchunk, &p.tmK, &kv_full[stage], col0 + c * 64, row);
         for (int c = 0; c < p.nchunk_v; ++c)
-          tma_load_2d(sV + c * AT_CHUNK_BYTES, &p.tmV, &kv_full[stage], col0 + c * 64, row);
+          tma_load_2d(sV + c * kchunk, &p.tmV, &kv_full[stage], col0 + c * 64, row);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -125,7 +127,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     const bool issuer = elect_one();   // elect.sync: the compiler keeps the issue path uniform
-    const uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);             // Q K^T
+    const uint32_t idesc_s = umma_idesc_bf16(128, (uint32_t)p.kt, 0, 0);  // Q K^T
     const uint32_t idesc_o = umma_idesc_bf16(128, (uint32_t)p.dv, 0, 1);  // P V (B MN-major)
     const uint32_t hi_k = umma_desc_hi_sw128(1024);                       // K-major operands
     const uint32_t sq_addr = smem_u32(sQ);
@@ -133,15 +135,16 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     auto issue_s = [&](int j, int stage) {
       const uint32_t sk_addr = skv_addr + (uint32_t)(stage * kv_bytes);
       const int sb = j % p.sbuf;
-      const uint32_t d_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(sb * p.kt);
       const uint32_t q_lo = umma_desc_lo(sq_addr), k_lo = umma_desc_lo(sk_addr);
       if (issuer) {
 #pragma unroll
         for (int ks = 0; ks < 12; ++ks) {               // d <= 192: at most 12 K-steps of 16
           if (ks < p.ksteps) {
             // next 64-wide chunk every 4 steps (16 KB = 1024 x 16 B), 32 B = 2 units inside a row
-            const uint32_t off = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
-            umma_ss_lohi(d_tmem, q_lo + off, k_lo + off, hi_k, idesc_s, ks > 0 ? 1u : 0u);
+            const uint32_t qoff = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
+            const uint32_t koff = (uint32_t)((ks >> 2) * (kchunk >> 4) + (ks & 3) * 2);
+            umma_ss_lohi(d_tmem, q_lo + qoff, k_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
           }
         }
         umma_commit(&s_full[sb]);
@@ -171,17 +174,19 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       if (tr) p.trace[j * 16 + 0] = clock64();
       {
         const uint32_t sv_addr = skv_addr + (uint32_t)(stage * kv_bytes + k_bytes);
-        const uint32_t p_tmem = tmem_base + (uint32_t)(sb * AT_TILE);
+        const uint32_t p_tmem = tmem_base + (uint32_t)(sb * p.kt);
         const uint32_t o_tmem = tmem_base + o_col;
         // V is the MN-major B operand: LBO = stride between 64-wide d chunks, SBO = 8-key groups
-        const uint32_t v_lo = umma_desc_lo(sv_addr, AT_CHUNK_BYTES);
+        const uint32_t v_lo = umma_desc_lo(sv_addr, (uint32_t)kchunk);
+        const int pv_steps = p.kt >> 4;
         if (issuer) {
 #pragma unroll
           for (int ks = 0; ks < AT_TILE / 16; ++ks) {
             // 16 keys = two 8-row swizzle atoms = 2048 B (+128 in 16-byte units); P advances 8
             // packed columns
-            umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
-                         (j > 0 || ks > 0) ? 1u : 0u);
+            if (ks < pv_steps)
+              umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
+                           (j > 0 || ks > 0) ? 1u : 0u);
           }
           umma_commit(&kv_empty[stage]);
           umma_commit(pv_done);
@@ -212,19 +217,30 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j % p.sbuf;
-      const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * AT_TILE);
+      const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * p.kt);
       mbar_wait(&s_full[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 &&
                       threadIdx.x == 64;
       if (tr) p.trace[j * 16 + 4] = clock64();
-      const int kbase = j * AT_TILE + ch * 64;
-      const bool need_mask = (j * AT_TILE + AT_TILE > p.skv);  // only the last tile (warp-uniform)
-      // my 64 S columns -> registers with ONE TMEM round trip (both loads in flight together);
-      // they serve the max pass and the exp pass, so S is never re-read
+      const int hc = p.kt >> 1;                                 // my columns: 64 / 48 / 32
+      const int kbase = j * p.kt + ch * hc;
+      const bool need_mask = (j * p.kt + p.kt > p.skv);         // only the last tile (warp-uniform)
+      // my S columns -> registers with ONE TMEM round trip (loads in flight together); they
+      // serve the max pass and the exp pass, so S is never re-read
       uint32_t sa[32], sb32[32];
-      tmem_ld32(s_tmem + (uint32_t)(ch * 64), sa);
-      tmem_ld32(s_tmem + (uint32_t)(ch * 64 + 32), sb32);
+      tmem_ld32(s_tmem + (uint32_t)(ch * hc), sa);
+      if (hc == 64) {
+        tmem_ld32(s_tmem + (uint32_t)(ch * hc + 32), sb32);
+      } else if (hc == 48) {
+        uint32_t t16[16];
+        tmem_ld16(s_tmem + (uint32_t)(ch * hc + 32), t16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { sb32[i] = t16[i]; sb32[16 + i] = 0xff800000u; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sb32[i] = 0xff800000u;     // -inf: ignored by max, exp2 -> 0
+      }
       tmem_ld_wait();
       if (tr) p.trace[j * 16 + 5] = clock64();
       if (need_mask) {
@@ -262,9 +278,11 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (c == 1 && hc == 32) break;
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
+          if (c == 1 && hc == 48 && i >= 8) { pk[i] = 0u; continue; }
           const uint32_t u0 = c == 0 ? sa[2 * i] : sb32[2 * i];
           const uint32_t u1 = c == 0 ? sa[2 * i + 1] : sb32[2 * i + 1];
           const float x0 = fmaf(__uint_as_float(u0), p.scale_log2, -m_new);
@@ -287,7 +305,14 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           }
           pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
-        tmem_st16(s_tmem + (uint32_t)(ch * 32 + c * 16), pk);
+        if (c == 0 || hc == 64) {
+          tmem_st16(s_tmem + (uint32_t)(ch * (hc >> 1) + c * 16), pk);
+        } else if (hc == 48) {                                  // 16 more columns -> 8 packed
+          uint32_t p8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p8[i] = pk[i];
+          tmem_st8(s_tmem + (uint32_t)(ch * (hc >> 1) + 16), p8);
+        }
       }
       l_run = l_run * corr + (lsum0 + lsum1);
       m_run = m_new;
@@ -396,25 +421,56 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   p.scale_log2 = scale * 1.4426950408889634f;
   p.trace = g_attn_trace;
   const int q_bytes = p.nchunk_qk * AT_CHUNK_BYTES;
-  const int kv_bytes = q_bytes + p.nchunk_v * AT_CHUNK_BYTES;
   const int overhead = 1024 + 256 + 2048;          // alignment slack, barriers, static xch
   const int half_budget = (227 * 1024) / 2 - 1024;      // two CTAs per SM
   const int full_budget = 227 * 1024 - 3072;
   static int force_mode = -1;
   if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
-  if (force_mode != 1 && p.dv <= 128 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
-    // small heads: 2 CTAs/SM interleave (one softmaxes while the other's MMAs run)
-    p.sbuf = 1;
-    p.tmem_cols = 256;
-    p.stages = (half_budget - overhead - q_bytes) / kv_bytes;
-  } else {
-    p.sbuf = (2 * AT_TILE + p.dv <= 512) ? 2 : 1;
-    p.tmem_cols = 512;
+  // Configuration search (best first):
+  //  1. two CTAs per SM (256 TMEM columns each) with a DOUBLE-buffered S: the key tile shrinks to
+  //     96 or 64 so that 2*kt + dv <= 256 — QK^T of tile j+1 runs under the softmax of tile j and
+  //     the other CTA fills the remaining bubbles;
+  //  2. two CTAs per SM, 128-key tile, single S buffer;
+  //  3. one CTA per SM (512 columns), double-buffered S, largest key tile with >= 2 smem stages;
+  //  4. one CTA per SM, single S buffer.
+  static const int kts[3] = {128, 96, 64};
+  int kv_bytes = 0;
+  bool done = false;
+  for (int ki = 0; ki < 3 && !done && force_mode == 0; ++ki) {
+    const int kt = kts[ki];
+    kv_bytes = (p.nchunk_qk + p.nchunk_v) * kt * 128;
+    if (2 * kt + p.dv <= 256 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
+      p.kt = kt; p.sbuf = 2; p.tmem_cols = 256;
+      p.stages = (half_budget - overhead - q_bytes) / kv_bytes;
+      done = true;
+    }
+  }
+  if (!done && force_mode != 1 && p.dv <= 128) {
+    kv_bytes = (p.nchunk_qk + p.nchunk_v) * 128 * 128;
+    if (q_bytes + kv_bytes + overhead <= half_budget) {
+      p.kt = 128; p.sbuf = 1; p.tmem_cols = 256;
+      p.stages = (half_budget - overhead - q_bytes) / kv_bytes;
+      done = true;
+    }
+  }
+  for (int ki = 0; ki < 3 && !done; ++ki) {
+    const int kt = kts[ki];
+    kv_bytes = (p.nchunk_qk + p.nchunk_v) * kt * 128;
+    if (2 * kt + p.dv <= 512 && q_bytes + 2 * kv_bytes + overhead <= full_budget) {
+      p.kt = kt; p.sbuf = 2; p.tmem_cols = 512;
+      p.stages = (full_budget - overhead - q_bytes) / kv_bytes;
+      done = true;
+    }
+  }
+  if (!done) {
+    p.kt = 64; p.sbuf = 1; p.tmem_cols = 512;
+    kv_bytes = (p.nchunk_qk + p.nchunk_v) * p.kt * 128;
     p.stages = (full_budget - overhead - q_bytes) / kv_bytes;
   }
   if (p.stages > 4) p.stages = 4;
-  DL_CHECK_ARG(p.stages >= 1, "attention(tc): head dim %d does not fit shared memory", d);
+  DL_CHECK_ARG(p.stages >= 1 && p.kt + p.dv <= 512, "attention(tc): head dim %d does not fit shared memory", d);
   const uint32_t box[2] = {64, AT_TILE};
+  const uint32_t kbox[2] = {64, (uint32_t)p.kt};
   {
     const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * sq};
     const uint64_t str[1] = {(uint64_t)ldq * 2};
@@ -423,12 +479,12 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   {
     const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * skv};
     const uint64_t str[1] = {(uint64_t)ldk * 2};
-    if (make_tmap_bf16(&p.tmK, k, 2, dims, str, box)) return 1;
+    if (make_tmap_bf16(&p.tmK, k, 2, dims, str, kbox)) return 1;
   }
   {
     const uint64_t dims[2] = {(uint64_t)heads * dh_stride, (uint64_t)batch * skv};
     const uint64_t str[1] = {(uint64_t)ldv * 2};
-    if (make_tmap_bf16(&p.tmV, v, 2, dims, str, box)) return 1;
+    if (make_tmap_bf16(&p.tmV, v, 2, dims, str, kbox)) return 1;
   }
   const int smem_bytes = q_bytes + p.stages * kv_bytes + overhead;
   static bool attr_set[64] = {false};
