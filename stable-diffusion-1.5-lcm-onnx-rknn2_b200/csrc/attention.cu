@@ -426,17 +426,17 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   const int full_budget = 227 * 1024 - 3072;
   static int force_mode = -1;
   if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
-  // Configuration search (best first):
-  //  1. two CTAs per SM (256 TMEM columns each) with a DOUBLE-buffered S: the key tile shrinks to
-  //     96 or 64 so that 2*kt + dv <= 256 — QK^T of tile j+1 runs under the softmax of tile j and
-  //     the other CTA fills the remaining bubbles;
-  //  2. two CTAs per SM, 128-key tile, single S buffer;
+  // Configuration search:
+  //  1. (DL_ATTN_MODE=3 only; measured 13 % slower on B200) two CTAs per SM with a double-buffered
+  //     S: the key tile shrinks to 96 or 64 so that 2*kt + dv <= 256;
+  //  2. two CTAs per SM (256 TMEM columns each), 128-key tile, single S buffer: one CTA's softmax
+  //     runs under the other's MMAs;
   //  3. one CTA per SM (512 columns), double-buffered S, largest key tile with >= 2 smem stages;
   //  4. one CTA per SM, single S buffer.
   static const int kts[3] = {128, 96, 64};
   int kv_bytes = 0;
   bool done = false;
-  for (int ki = 0; ki < 3 && !done && force_mode == 0; ++ki) {
+  for (int ki = 0; ki < 3 && !done && force_mode == 3; ++ki) {   // measured slower: opt-in only
     const int kt = kts[ki];
     kv_bytes = (p.nchunk_qk + p.nchunk_v) * kt * 128;
     if (2 * kt + p.dv <= 256 && q_bytes + 2 * kv_bytes + overhead <= half_budget) {
