@@ -61,12 +61,12 @@ def unet_cfg_from_json(c: dict):
     from types import SimpleNamespace
     down = c.get("down_block_types", ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"])
     heads = c.get("attention_head_dim", 8)
-    if isinstance(heads, (list, tuple)):
-        if len(set(heads)) != 1:
-            raise RuntimeError("b200 worker: per-level attention_head_dim (SDXL) is not supported yet")
-        heads = heads[0]
-    if c.get("use_linear_projection", False) or c.get("addition_embed_type"):
-        raise RuntimeError("b200 worker: SDXL-class UNet configs are not supported yet")
+    heads = tuple(heads) if isinstance(heads, (list, tuple)) else heads
+    tl = c.get("transformer_layers_per_block", 1)
+    tl = tuple(tl) if isinstance(tl, (list, tuple)) else ((tl,) * len(down) if tl != 1 else ())
+    aet = c.get("addition_embed_type")
+    if aet not in (None, "text_time"):
+        raise RuntimeError(f"b200 worker: addition_embed_type={aet!r} is not supported")
     return SimpleNamespace(
         in_channels=c.get("in_channels", 4), out_channels=c.get("out_channels", 4),
         block_out_channels=tuple(c.get("block_out_channels", (320, 640, 1280, 1280))),
@@ -74,7 +74,10 @@ def unet_cfg_from_json(c: dict):
         layers_per_block=c.get("layers_per_block", 2),
         cross_attention_dim=c.get("cross_attention_dim", 768),
         attention_head_dim=heads, norm_num_groups=c.get("norm_num_groups", 32),
-        norm_eps=c.get("norm_eps", 1e-5), time_cond_proj_dim=c.get("time_cond_proj_dim"))
+        norm_eps=c.get("norm_eps", 1e-5), time_cond_proj_dim=c.get("time_cond_proj_dim"),
+        transformer_layers_per_block=tl, use_linear_projection=bool(c.get("use_linear_projection", False)),
+        addition_embed_type=aet, addition_time_embed_dim=c.get("addition_time_embed_dim", 256),
+        projection_class_embeddings_input_dim=c.get("projection_class_embeddings_input_dim", 2816))
 
 
 def vae_cfg_from_json(c: dict):
@@ -87,14 +90,17 @@ def vae_cfg_from_json(c: dict):
 
 
 class B200Worker(PipelineWorker):
+    _tag = "b200"
+    _env_what = "BACKEND=cuda"
+
     def __init__(self, worker_id: int):
         self.worker_id = worker_id
         model_root = (os.environ.get("MODEL_ROOT") or "").strip()
         model_name = (os.environ.get("MODEL") or "").strip()
         if not model_root:
-            raise RuntimeError("MODEL_ROOT is required for BACKEND=cuda")
+            raise RuntimeError(f"MODEL_ROOT is required for {self._env_what}")
         if not model_name:
-            raise RuntimeError("MODEL is required for BACKEND=cuda")
+            raise RuntimeError(f"MODEL is required for {self._env_what}")
         path = os.path.join(model_root, model_name)
         if not (os.path.isdir(path) and os.path.exists(os.path.join(path, "model_index.json"))):
             raise RuntimeError(f"b200 worker needs a diffusers-layout model directory, got: {path}")
@@ -117,9 +123,16 @@ class B200Worker(PipelineWorker):
         vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
         self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
                                     vae_cfg_from_json(vcfg_json), self.device)
-        self._text = _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
-        print(f"[b200] worker {worker_id} loaded: {model_name} on {self.device} "
+        self._text = self._make_text_encoder(path)
+        print(f"[{self._tag}] worker {worker_id} loaded: {model_name} on {self.device} "
               f"(noise dtype={dtype_str}, compute bf16)")
+
+    def _make_text_encoder(self, path):
+        return _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
+
+    def _generate(self, prompts, lat, noise, steps, gs, height, width):
+        pe = self._text.encode(prompts)
+        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True)
 
     # ------------------------------------------------------------------ jobs
     def _parse(self, req):
@@ -157,9 +170,9 @@ class B200Worker(PipelineWorker):
             lat = torch.cat([d[0] for d in draws], 0)
             noise = (torch.stack([torch.cat([d[1][i] for d in draws], 0) for i in range(steps - 1)])
                      if steps > 1 else None)
-            pe = self._text.encode([str(j.req.prompt) for j in jobs])
             gs = torch.tensor([float(j.req.guidance_scale) for j in jobs])
-            img, final = self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True)
+            img, final = self._generate([str(j.req.prompt) for j in jobs], lat, noise, steps, gs,
+                                        height, width)
             pooled = None
             if with_latents:
                 from dreamlab_b200 import lib
@@ -178,6 +191,26 @@ class B200Worker(PipelineWorker):
 
     def run_job_with_latents(self, job) -> Tuple[bytes, int, bytes]:
         return self.run_batch([job], with_latents=True)[0]
+
+
+class B200SDXLWorker(B200Worker):
+    """Drop-in for `DiffusersSDXLCudaWorker` (reference `backends/cuda_worker.py:307-614`): same
+    constructor / env / attributes / results / errors; SDXL-class UNet (text_time conditioning,
+    two text encoders -> [B,77,2048] + pooled [B,1280]), LCMScheduler, classifier-free guidance
+    when guidance_scale > 1 (all jobs of one batch must then share the scale), SDXL VAE."""
+    _tag = "b200-sdxl"
+    _env_what = "SDXL CUDA worker"
+
+    def _make_text_encoder(self, path):
+        ucfg = self.pipe.unet.cfg
+        if not self.pipe.is_sdxl:
+            raise RuntimeError("B200SDXLWorker needs an SDXL-class UNet (addition_embed_type=text_time)")
+        pooled = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+        return _SDXLTextEncoder(path, self.device, ucfg.cross_attention_dim, pooled)
+
+    def _generate(self, prompts, lat, noise, steps, gs, height, width):
+        pe, pooled = self._text.encode(prompts)
+        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, pooled_embeds=pooled)
 
 
 def _encode_png(arr) -> bytes:
@@ -229,3 +262,40 @@ class _TextEncoder:
         else:
             ids = self._hash_tokens(prompts)
         return self.model(ids.to(self.device))[0].float()
+
+
+class _SDXLTextEncoder:
+    """Prompt -> ([B,77,D] embeddings, [B,P] pooled) for SDXL: penultimate hidden states of
+    `text_encoder` (CLIP-L, 768) and `text_encoder_2` (OpenCLIP-bigG, 1280) concatenated, pooled =
+    `text_encoder_2`'s projected embedding.  Stock `transformers` towers are
+    used as a library *before* the hot path; without them in the model dir (offline fixtures),
+    seeded N(0,1) embeddings keyed by the prompt."""
+
+    def __init__(self, model_dir: str, device: str, dim: int, pooled_dim: int):
+        self.device, self.dim, self.pooled_dim = device, dim, pooled_dim
+        self.models = None
+        te1, te2 = os.path.join(model_dir, "text_encoder"), os.path.join(model_dir, "text_encoder_2")
+        if os.path.exists(os.path.join(te1, "config.json")) and os.path.exists(os.path.join(te2, "config.json")):
+            from transformers import CLIPTextModel, CLIPTextModelWithProjection, CLIPTokenizer
+            self.models = (CLIPTextModel.from_pretrained(te1, torch_dtype=torch.float16).to(device).eval(),
+                           CLIPTextModelWithProjection.from_pretrained(te2, torch_dtype=torch.float16).to(device).eval())
+            self.tokenizers = tuple(CLIPTokenizer.from_pretrained(os.path.join(model_dir, t))
+                                    for t in ("tokenizer", "tokenizer_2"))
+
+    @torch.no_grad()
+    def encode(self, prompts: List[str]):
+        if self.models is None:
+            pe, pooled = [], []
+            for p in prompts:
+                g = torch.Generator().manual_seed(int.from_bytes(p.encode("utf-8")[:7] or b"\0", "little"))
+                pe.append(torch.randn(1, 77, self.dim, generator=g))
+                pooled.append(torch.randn(1, self.pooled_dim, generator=g))
+            return torch.cat(pe, 0).to(self.device), torch.cat(pooled, 0).to(self.device)
+        hs, pooled = [], None
+        for tok, m in zip(self.tokenizers, self.models):
+            ids = tok(prompts, padding="max_length", max_length=77, truncation=True,
+                      return_tensors="pt").input_ids.to(self.device)
+            out = m(ids, output_hidden_states=True)
+            hs.append(out.hidden_states[-2].float())
+            pooled = out[0].float()          # the last tower's projected pooled embedding
+        return torch.cat(hs, -1), pooled

@@ -4,7 +4,8 @@ Keeps the reference's entry points (`backends/worker_factory.py:17-100`):
 `detect_worker_type() -> "sd15" | "sdxl"` from the `cross_attention_dim` of the model named by
 `MODEL_ROOT`/`MODEL` (768/1024 -> sd15, 1280/2048 -> sdxl, anything else raises) and
 `create_cuda_worker(worker_id)`.  The only behavioural change: SD1.5-class models now get the
-B200-native `B200Worker` instead of `DiffusersCudaWorker`.  Set `B200_WORKER=0` to get the
+B200-native `B200Worker` instead of `DiffusersCudaWorker`, SDXL-class models `B200SDXLWorker`
+instead of `DiffusersSDXLCudaWorker`.  Set `B200_WORKER=0` to get the
 reference's diffusers worker back when running inside the reference tree.
 """
 from __future__ import annotations
@@ -78,12 +79,12 @@ def _use_b200() -> bool:
 def create_cuda_worker(worker_id: int) -> "PipelineWorker":
     worker_type = detect_worker_type()
     if worker_type == "sdxl":
-        # SDXL-1024 (BASELINE config 5) is not built yet: defer to the reference's worker when
-        # this package is dropped into the reference tree, otherwise say so.
-        try:
-            from backends.cuda_worker import DiffusersSDXLCudaWorker
-        except ImportError:
-            raise RuntimeError("SDXL models are not supported by the b200 backend yet")
+        if _use_b200():
+            from backends.b200_worker import B200SDXLWorker
+            worker = B200SDXLWorker(worker_id=worker_id)
+            logger.info("[WorkerFactory] Created B200SDXLWorker (worker %d)", worker_id)
+            return worker
+        from backends.cuda_worker import DiffusersSDXLCudaWorker
         return DiffusersSDXLCudaWorker(worker_id=worker_id)
     if _use_b200():
         from backends.b200_worker import B200Worker

@@ -143,6 +143,12 @@ typedef struct dl_lcm_coeffs {
 int dl_lcm_step(const float* eps, const float* x, const float* noise, float* x_next,
                 float* denoised, long long n, const dl_lcm_coeffs* coeffs /* host */, void* stream);
 
+/* ---- classifier-free guidance combine of the doubled-batch UNet output (SDXL path:
+ * `StableDiffusionXLPipeline.__call__` behind reference `backends/cuda_worker.py:532`) --------
+ * out = eps_uncond + guidance_scale * (eps_text - eps_uncond), fp32, un-contracted            */
+int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidance_scale,
+                   float* out, long long n, void* stream);
+
 /* ---- run_job_with_latents tail: fp32 adaptive_avg_pool2d -> (8,8) -> fp16 NCHW ------------- *
  * (reference `backends/cuda_worker.py:297-304`).  lat: fp32 NHWC [nimg,h,w,c]; out: fp16
  * [nimg,c,8,8].  h, w multiples of 8.                                                         */

@@ -103,3 +103,60 @@ def pooled_latent_bytes(latents: torch.Tensor) -> bytes:
     fp32 adaptive_avg_pool2d → (8,8) → fp16 → C-order bytes (512 B for [1,4,8,8])."""
     lat8 = torch.nn.functional.adaptive_avg_pool2d(latents.to(torch.float32), (8, 8))
     return lat8.to(torch.float16).contiguous().numpy().tobytes(order="C")
+
+
+def sdxl_time_ids(height: int, width: int, batch: int) -> torch.Tensor:
+    """`_get_add_time_ids(original_size, crops_coords_top_left, target_size)` with the
+    pipeline defaults original_size = target_size = (height, width), crop (0, 0)."""
+    return torch.tensor([[height, width, 0, 0, height, width]], dtype=torch.float32).repeat(batch, 1)
+
+
+@torch.no_grad()
+def run_pipeline_sdxl(unet: OracleUNet, vae: OracleVAEDecoder, prompt_embeds: torch.Tensor,
+                      pooled_embeds: torch.Tensor, latents: torch.Tensor, step_noise: torch.Tensor,
+                      num_inference_steps: int, guidance_scale: float, height: int, width: int,
+                      negative_prompt_embeds: Optional[torch.Tensor] = None,
+                      negative_pooled_embeds: Optional[torch.Tensor] = None,
+                      output_type: str = "u8", record: Optional[dict] = None):
+    """What `self.pipe(prompt, width, height, num_inference_steps, guidance_scale, generator)`
+    does at `backends/cuda_worker.py:532-539` (`StableDiffusionXLPipeline.__call__` with the
+    LCMScheduler swapped in at `:387`): classifier-free guidance on a doubled batch
+    [uncond, cond] when guidance_scale > 1 (SDXL-base has no time_cond_proj), text_time
+    micro-conditioning, `noise_pred = uncond + gs * (text - uncond)`, `LCMScheduler.step`.
+    With no negative prompt and `force_zeros_for_empty_prompt` (SDXL-base config) the
+    unconditional embeddings are zeros."""
+    sched = OracleLCMScheduler()
+    timesteps = sched.set_timesteps(num_inference_steps)
+    B = latents.shape[0]
+    do_cfg = guidance_scale > 1.0 and not unet.cfg.time_cond_proj_dim
+    tid = sdxl_time_ids(height, width, B)
+    ctx, pooled, tids = prompt_embeds, pooled_embeds, tid
+    if do_cfg:
+        neg = torch.zeros_like(prompt_embeds) if negative_prompt_embeds is None else negative_prompt_embeds
+        negp = torch.zeros_like(pooled_embeds) if negative_pooled_embeds is None else negative_pooled_embeds
+        ctx = torch.cat([neg, prompt_embeds], 0)
+        pooled = torch.cat([negp, pooled_embeds], 0)
+        tids = torch.cat([tid, tid], 0)
+    w_emb = None
+    if unet.cfg.time_cond_proj_dim:
+        w_emb = guidance_scale_embedding(torch.full((B,), guidance_scale - 1.0), unet.cfg.time_cond_proj_dim)
+    latents = latents * sched.init_noise_sigma
+    if record is not None:
+        record.update(timesteps=timesteps.clone(), noise_pred=[], latents=[])
+    for i, t in enumerate(timesteps):
+        x = torch.cat([latents] * 2, 0) if do_cfg else latents
+        eps = unet(x, t, ctx, w_emb, text_embeds=pooled, time_ids=tids)
+        if do_cfg:
+            e_u, e_t = eps.chunk(2)
+            eps = e_u + guidance_scale * (e_t - e_u)
+        z = step_noise[i] if i < num_inference_steps - 1 else None
+        latents, _ = sched.step(eps, int(t), latents, noise=z)
+        if record is not None:
+            record["noise_pred"].append(eps.clone())
+            record["latents"].append(latents.clone())
+    if output_type == "latent":
+        return latents
+    image = vae(latents / vae.cfg.scaling_factor, tiling=False)
+    if record is not None:
+        record["image_f32"] = image.clone()
+    return denormalize_to_u8(image)

@@ -1,9 +1,10 @@
-"""Oracle UNet2DConditionModel — SD1.5 (+LCM time_cond_proj_dim) (test infrastructure).
+"""Oracle UNet2DConditionModel — SD1.5 (+LCM time_cond_proj_dim) and SDXL-base (test infrastructure).
 
 fp32 PyTorch restatement of the module the reference runs through diffusers at
 `backends/cuda_worker.py:222` (UNet call mirrored at `backends/rknnlcm.py:588-593`).
 Architecture per SURVEY.md Appendix A.2; parameter names are the diffusers
-state-dict keys so a real checkpoint loads 1:1.  NCHW like diffusers.
+state-dict keys so a real checkpoint loads 1:1.  NCHW like diffusers.  The SDXL variant is the
+UNet `StableDiffusionXLPipeline` runs at `backends/cuda_worker.py:532` (config C5).
 """
 from __future__ import annotations
 
@@ -28,10 +29,41 @@ class UNetConfig:
     norm_num_groups: int = 32
     norm_eps: float = 1e-5
     time_cond_proj_dim: Optional[int] = 256   # LCM_Dreamshaper_v7; None for vanilla SD1.5
+    # --- SDXL additions (App. A.2 "SDXL-base"); defaults reproduce SD1.5
+    transformer_layers_per_block: Tuple[int, ...] = ()     # () == 1 everywhere
+    use_linear_projection: bool = False
+    addition_embed_type: Optional[str] = None              # "text_time" for SDXL
+    addition_time_embed_dim: int = 256
+    projection_class_embeddings_input_dim: int = 2816
+
+    def heads_at(self, i: int) -> int:
+        a = self.attention_head_dim
+        return a if isinstance(a, int) else a[i]
+
+    def depth_at(self, i: int) -> int:
+        t = self.transformer_layers_per_block
+        return t[i] if t else 1
 
     @staticmethod
     def sd15_lcm() -> "UNetConfig":
         return UNetConfig()
+
+    @staticmethod
+    def sdxl_base() -> "UNetConfig":
+        return UNetConfig(block_out_channels=(320, 640, 1280), down_attn=(False, True, True),
+                          cross_attention_dim=2048, attention_head_dim=(5, 10, 20),
+                          time_cond_proj_dim=None, transformer_layers_per_block=(1, 2, 10),
+                          use_linear_projection=True, addition_embed_type="text_time")
+
+    @staticmethod
+    def tiny_sdxl() -> "UNetConfig":
+        """SDXL topology (3 levels, no attention at level 0, deep transformers, linear
+        projections, text_time embedding), small widths."""
+        return UNetConfig(block_out_channels=(64, 128, 256), down_attn=(False, True, True),
+                          cross_attention_dim=128, attention_head_dim=(2, 2, 4),
+                          time_cond_proj_dim=None, transformer_layers_per_block=(1, 2, 3),
+                          use_linear_projection=True, addition_embed_type="text_time",
+                          addition_time_embed_dim=32, projection_class_embeddings_input_dim=6 * 32 + 80)
 
     @staticmethod
     def tiny() -> "UNetConfig":
@@ -139,22 +171,31 @@ class BasicTransformerBlock(nn.Module):
 
 
 class Transformer2DModel(nn.Module):
-    def __init__(self, dim, heads, ctx_dim, groups):
+    def __init__(self, dim, heads, ctx_dim, groups, depth=1, linear_proj=False):
         super().__init__()
+        self.linear_proj = linear_proj
         self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
-        self.proj_in = nn.Conv2d(dim, dim, 1)      # use_linear_projection=False
-        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, ctx_dim)])
-        self.proj_out = nn.Conv2d(dim, dim, 1)
+        # use_linear_projection: SD1.5 False (1x1 conv before the reshape), SDXL True (Linear after)
+        self.proj_in = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(dim, heads, ctx_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(dim, dim) if linear_proj else nn.Conv2d(dim, dim, 1)
 
     def forward(self, x, ctx):
         B, C, H, W = x.shape
         res = x
-        h = self.proj_in(self.norm(x))
-        h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        h = self.norm(x)
+        if self.linear_proj:
+            h = self.proj_in(h.permute(0, 2, 3, 1).reshape(B, H * W, C))
+        else:
+            h = self.proj_in(h).permute(0, 2, 3, 1).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             h = blk(h, ctx)
-        h = h.reshape(B, H, W, C).permute(0, 3, 1, 2)
-        return self.proj_out(h) + res
+        if self.linear_proj:
+            h = self.proj_out(h).reshape(B, H, W, C).permute(0, 3, 1, 2)
+        else:
+            h = self.proj_out(h.reshape(B, H, W, C).permute(0, 3, 1, 2))
+        return h + res
 
 
 class Downsample2D(nn.Module):
@@ -176,15 +217,15 @@ class Upsample2D(nn.Module):
 
 
 class DownBlock(nn.Module):
-    def __init__(self, cfg: UNetConfig, cin, cout, temb, attn, down):
+    def __init__(self, cfg: UNetConfig, cin, cout, temb, attn, down, heads=None, depth=1):
         super().__init__()
         self.resnets = nn.ModuleList(
             [ResnetBlock2D(cin if i == 0 else cout, cout, temb, cfg.norm_num_groups, cfg.norm_eps)
              for i in range(cfg.layers_per_block)])
         if attn:
             self.attentions = nn.ModuleList(
-                [Transformer2DModel(cout, cfg.attention_head_dim, cfg.cross_attention_dim,
-                                    cfg.norm_num_groups) for _ in range(cfg.layers_per_block)])
+                [Transformer2DModel(cout, heads, cfg.cross_attention_dim, cfg.norm_num_groups, depth,
+                                    cfg.use_linear_projection) for _ in range(cfg.layers_per_block)])
         else:
             self.attentions = None
         self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if down else None
@@ -203,13 +244,13 @@ class DownBlock(nn.Module):
 
 
 class MidBlock(nn.Module):
-    def __init__(self, cfg: UNetConfig, c, temb):
+    def __init__(self, cfg: UNetConfig, c, temb, heads, depth):
         super().__init__()
         self.resnets = nn.ModuleList(
             [ResnetBlock2D(c, c, temb, cfg.norm_num_groups, cfg.norm_eps) for _ in range(2)])
         self.attentions = nn.ModuleList(
-            [Transformer2DModel(c, cfg.attention_head_dim, cfg.cross_attention_dim,
-                                cfg.norm_num_groups)])
+            [Transformer2DModel(c, heads, cfg.cross_attention_dim, cfg.norm_num_groups, depth,
+                                cfg.use_linear_projection)])
 
     def forward(self, x, temb, ctx):
         x = self.resnets[0](x, temb)
@@ -218,7 +259,7 @@ class MidBlock(nn.Module):
 
 
 class UpBlock(nn.Module):
-    def __init__(self, cfg: UNetConfig, prev_out, cout, skip_chs, temb, attn, up):
+    def __init__(self, cfg: UNetConfig, prev_out, cout, skip_chs, temb, attn, up, heads=None, depth=1):
         super().__init__()
         n = cfg.layers_per_block + 1
         self.resnets = nn.ModuleList(
@@ -226,8 +267,8 @@ class UpBlock(nn.Module):
                            cfg.norm_num_groups, cfg.norm_eps) for i in range(n)])
         if attn:
             self.attentions = nn.ModuleList(
-                [Transformer2DModel(cout, cfg.attention_head_dim, cfg.cross_attention_dim,
-                                    cfg.norm_num_groups) for _ in range(n)])
+                [Transformer2DModel(cout, heads, cfg.cross_attention_dim, cfg.norm_num_groups, depth,
+                                    cfg.use_linear_projection) for _ in range(n)])
         else:
             self.attentions = None
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if up else None
@@ -251,15 +292,22 @@ class OracleUNet(nn.Module):
         temb = ch[0] * 4
         self.conv_in = nn.Conv2d(cfg.in_channels, ch[0], 3, padding=1)
         self.time_embedding = TimestepEmbedding(ch[0], temb, cfg.time_cond_proj_dim)
+        if cfg.addition_embed_type == "text_time":
+            # add_time_proj = Timesteps(addition_time_embed_dim) has no parameters
+            self.add_embedding = TimestepEmbedding(cfg.projection_class_embeddings_input_dim, temb, None)
+        else:
+            self.add_embedding = None
         self.down_blocks = nn.ModuleList()
         skip_chs = [ch[0]]
         cout = ch[0]
         for i, c in enumerate(ch):
             cin, cout = cout, c
             last = i == len(ch) - 1
-            self.down_blocks.append(DownBlock(cfg, cin, cout, temb, cfg.down_attn[i], not last))
+            self.down_blocks.append(DownBlock(cfg, cin, cout, temb, cfg.down_attn[i], not last,
+                                              cfg.heads_at(i), cfg.depth_at(i)))
             skip_chs += [cout] * cfg.layers_per_block + ([cout] if not last else [])
-        self.mid_block = MidBlock(cfg, ch[-1], temb)
+        n_lv = len(ch)
+        self.mid_block = MidBlock(cfg, ch[-1], temb, cfg.heads_at(n_lv - 1), cfg.depth_at(n_lv - 1))
         self.up_blocks = nn.ModuleList()
         rev = list(reversed(ch))
         rev_attn = list(reversed(cfg.down_attn))
@@ -268,16 +316,25 @@ class OracleUNet(nn.Module):
             n = cfg.layers_per_block + 1
             sk = [skip_chs.pop() for _ in range(n)]
             last = i == len(ch) - 1
-            self.up_blocks.append(UpBlock(cfg, prev, c, sk, temb, rev_attn[i], not last))
+            lv = n_lv - 1 - i
+            self.up_blocks.append(UpBlock(cfg, prev, c, sk, temb, rev_attn[i], not last,
+                                          cfg.heads_at(lv), cfg.depth_at(lv)))
             prev = c
         self.conv_norm_out = nn.GroupNorm(cfg.norm_num_groups, ch[0], eps=cfg.norm_eps)
         self.conv_out = nn.Conv2d(ch[0], cfg.out_channels, 3, padding=1)
 
-    def forward(self, sample, timestep, encoder_hidden_states, timestep_cond=None):
+    def forward(self, sample, timestep, encoder_hidden_states, timestep_cond=None,
+                text_embeds=None, time_ids=None):
         B = sample.shape[0]
         t = torch.as_tensor(timestep).reshape(-1).expand(B)
         t_emb = timestep_embedding(t, self.cfg.block_out_channels[0])
         emb = self.time_embedding(t_emb, timestep_cond)
+        if self.add_embedding is not None:
+            # SDXL "text_time": sinusoid of each of the 6 micro-conditioning ids, concatenated
+            # after the pooled text embedding (text first), through its own 2-layer MLP
+            te = timestep_embedding(time_ids.reshape(-1), self.cfg.addition_time_embed_dim)
+            add = torch.cat([text_embeds.to(torch.float32), te.reshape(B, -1)], dim=-1)
+            emb = emb + self.add_embedding(add)
         x = self.conv_in(sample)
         skips = [x]
         for blk in self.down_blocks:

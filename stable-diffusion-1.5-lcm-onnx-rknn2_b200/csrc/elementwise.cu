@@ -227,6 +227,21 @@ __global__ void lcm_step_kernel(const float4* __restrict__ eps, const float4* __
   }
 }
 
+// ---- classifier-free guidance: out = u + gs * (t - u), un-contracted like the reference ------
+__global__ void cfg_combine_kernel(const float4* __restrict__ u, const float4* __restrict__ t, float gs,
+                                   float4* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = u[i], b = t[i];
+    float4 o;
+    o.x = __fadd_rn(a.x, __fmul_rn(gs, __fsub_rn(b.x, a.x)));
+    o.y = __fadd_rn(a.y, __fmul_rn(gs, __fsub_rn(b.y, a.y)));
+    o.z = __fadd_rn(a.z, __fmul_rn(gs, __fsub_rn(b.z, a.z)));
+    o.w = __fadd_rn(a.w, __fmul_rn(gs, __fsub_rn(b.w, a.w)));
+    out[i] = o;
+  }
+}
+
 // ---- fp32 adaptive_avg_pool2d -> (8,8) -> fp16, NHWC in, NCHW out -----------------------------
 __global__ void latent_pool8_kernel(const float* __restrict__ lat, int nimg, int h, int w, int c,
                                     __half* __restrict__ out) {
@@ -331,6 +346,16 @@ extern "C" int dl_lcm_step(const float* eps, const float* x, const float* noise,
       reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(x_next),
       reinterpret_cast<float4*>(denoised), n / 4, *k);
   return check_launch("lcm_step");
+}
+
+extern "C" int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidance_scale,
+                              float* out, long long n, void* stream_) {
+  DL_CHECK_ARG(eps_uncond && eps_text && out, "cfg_combine: null pointer");
+  DL_CHECK_ARG(n % 4 == 0, "cfg_combine: n must be a multiple of 4");
+  cfg_combine_kernel<<<grid_for(n / 4, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(eps_uncond), reinterpret_cast<const float4*>(eps_text),
+      guidance_scale, reinterpret_cast<float4*>(out), n / 4);
+  return check_launch("cfg_combine");
 }
 
 extern "C" int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16,

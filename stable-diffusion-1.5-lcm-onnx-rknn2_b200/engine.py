@@ -91,37 +91,43 @@ def resnet(ctx, x, p: Packed, *, temb=None, x1=None, eps=1e-5, groups=32):
     return conv3x3(ctx, h, p["conv2_w"], p["conv2_b"], cout, residual=sc)
 
 
-def transformer(ctx, x, p: Packed, kv, *, groups=32):
-    """Transformer2DModel (1 BasicTransformerBlock).  kv: hoisted cross-attn [B*77, 2*heads*hstride]."""
-    B, H, W, C = x.shape
-    S = H * W
-    heads, d, hstride = p["heads"], p["d"], p["hstride"]
+def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
+    """One BasicTransformerBlock on token rows h [B*S, C]; kv = hoisted cross-attn K/V."""
     hs = heads * hstride
     scale = 1.0 / math.sqrt(d)
-    hn = groupnorm(ctx, x, p["norm_w"], p["norm_b"], eps=1e-6, silu=False, groups=groups)
-    h = linear(ctx, hn.view(B * S, C), p["proj_in_w"], p["proj_in_b"], C)
     # --- self attention
     n1 = ctx.empty(B * S, C)
-    lib.layernorm(h, n1, p["ln1_w"], p["ln1_b"])
-    qkv = linear(ctx, n1, p["qkv_w"], p["qkv_b"], 3 * hs)
+    lib.layernorm(h, n1, q["ln1_w"], q["ln1_b"])
+    qkv = linear(ctx, n1, q["qkv_w"], q["qkv_b"], 3 * hs)
     a = ctx.empty(B * S, C)
     lib.attention(qkv, qkv[:, hs:], qkv[:, 2 * hs:], a, batch=B, sq=S, skv=S, heads=heads, d=d,
                   dh_stride=hstride, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale, v_ones=True)
-    h = linear(ctx, a, p["o1_w"], p["o1_b"], C, residual=h)
+    h = linear(ctx, a, q["o1_w"], q["o1_b"], C, residual=h)
     # --- cross attention (K/V precomputed once per request)
     n2 = ctx.empty(B * S, C)
-    lib.layernorm(h, n2, p["ln2_w"], p["ln2_b"])
-    q = linear(ctx, n2, p["q2_w"], None, hs)
+    lib.layernorm(h, n2, q["ln2_w"], q["ln2_b"])
+    qq = linear(ctx, n2, q["q2_w"], None, hs)
     skv = kv.shape[0] // B
     a2 = ctx.empty(B * S, C)
-    lib.attention(q, kv, kv[:, hs:], a2, batch=B, sq=S, skv=skv, heads=heads, d=d, dh_stride=hstride,
+    lib.attention(qq, kv, kv[:, hs:], a2, batch=B, sq=S, skv=skv, heads=heads, d=d, dh_stride=hstride,
                   ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale, v_ones=True)
-    h = linear(ctx, a2, p["o2_w"], p["o2_b"], C, residual=h)
+    h = linear(ctx, a2, q["o2_w"], q["o2_b"], C, residual=h)
     # --- GEGLU feed-forward
     n3 = ctx.empty(B * S, C)
-    lib.layernorm(h, n3, p["ln3_w"], p["ln3_b"])
-    g = linear(ctx, n3, p["ff1_w"], p["ff1_b"], 8 * C, mode=lib.EPI_GEGLU)
-    h = linear(ctx, g, p["ff2_w"], p["ff2_b"], C, residual=h)
+    lib.layernorm(h, n3, q["ln3_w"], q["ln3_b"])
+    g = linear(ctx, n3, q["ff1_w"], q["ff1_b"], 8 * C, mode=lib.EPI_GEGLU)
+    return linear(ctx, g, q["ff2_w"], q["ff2_b"], C, residual=h)
+
+
+def transformer(ctx, x, p: Packed, kvs, *, groups=32):
+    """Transformer2DModel.  kvs: one hoisted cross-attn K/V [B*77, 2*heads*hstride] per block."""
+    B, H, W, C = x.shape
+    S = H * W
+    hn = groupnorm(ctx, x, p["norm_w"], p["norm_b"], eps=1e-6, silu=False, groups=groups)
+    h = linear(ctx, hn.view(B * S, C), p["proj_in_w"], p["proj_in_b"], C)
+    for q, kv in zip(p["blocks"], kvs):
+        h = transformer_block(ctx, h, q, kv, B=B, S=S, C=C, heads=p["heads"], d=p["d"],
+                              hstride=p["hstride"])
     out = linear(ctx, h, p["proj_out_w"], p["proj_out_b"], C, residual=x.view(B * S, C))
     return out.view(B, H, W, C)
 
@@ -161,17 +167,37 @@ class UNetB200:
         self.groups = getattr(cfg, "norm_num_groups", 32)
 
     @torch.no_grad()
-    def encode_context(self, prompt_embeds: torch.Tensor) -> List[torch.Tensor]:
-        """Hoisted cross-attention K/V for every transformer layer.  prompt_embeds [B,77,D]."""
+    def encode_context(self, prompt_embeds: torch.Tensor) -> List[List[torch.Tensor]]:
+        """Hoisted cross-attention K/V: per Transformer2DModel, one tensor per block.
+        prompt_embeds [B,77,D]."""
         B, T, D = prompt_embeds.shape
         ctx = _Ctx(self.device, B)
         pe = prompt_embeds.to(self.device, BF16).contiguous().view(B * T, D)
-        return [linear(ctx, pe, t["kv2_w"], t["kv2_b"], 2 * t["heads"] * t["hstride"])
-                for t in self.P["transformers"]]
+        return [[linear(ctx, pe, q["kv2_w"], q["kv2_b"], 2 * t["heads"] * t["hstride"])
+                 for q in t["blocks"]] for t in self.P["transformers"]]
 
     @torch.no_grad()
-    def time_embeddings(self, timesteps: List[int], batch: int, w_emb: Optional[torch.Tensor]):
-        """Per step: all ResnetBlock2D time projections, fp32 [B, temb_total]."""
+    def addition_embedding(self, text_embeds: torch.Tensor, time_ids: torch.Tensor) -> torch.Tensor:
+        """SDXL `text_time` embedding (constant over the steps): fp32 [B, 4*ch0].
+        text_embeds [B, P] pooled text, time_ids [B, 6]."""
+        P = self.P
+        B = text_embeds.shape[0]
+        td = self.cfg.addition_time_embed_dim
+        ids = time_ids.to(self.device, torch.float32).reshape(-1).contiguous()
+        sin = torch.empty(ids.numel(), td, device=self.device, dtype=torch.float32)
+        lib.timestep_sinusoid(ids, sin)
+        add = torch.cat([text_embeds.to(self.device, torch.float32), sin.view(B, -1)], dim=1).contiguous()
+        e1 = torch.empty(B, P["add1_w"].shape[0], device=self.device, dtype=torch.float32)
+        lib.small_linear(add, P["add1_w"], e1, bias=P["add1_b"], silu_out=True)
+        out = torch.empty_like(e1)
+        lib.small_linear(e1, P["add2_w"], out, bias=P["add2_b"])
+        return out
+
+    @torch.no_grad()
+    def time_embeddings(self, timesteps: List[int], batch: int, w_emb: Optional[torch.Tensor],
+                        aug_emb: Optional[torch.Tensor] = None):
+        """Per step: all ResnetBlock2D time projections, fp32 [B, temb_total].
+        aug_emb: SDXL addition embedding, added to the time embedding (`emb = emb + aug_emb`)."""
         P = self.P
         ch0 = self.cfg.block_out_channels[0]
         out = []
@@ -187,24 +213,28 @@ class UNetB200:
             e1 = torch.empty(batch, ch0 * 4, device=self.device, dtype=torch.float32)
             lib.small_linear(x, P["t1_w"], e1, bias=P["t1_b"], silu_out=True)
             emb = torch.empty_like(e1)
-            lib.small_linear(e1, P["t2_w"], emb, bias=P["t2_b"])
+            lib.small_linear(e1, P["t2_w"], emb, bias=P["t2_b"], add=aug_emb)
             temb = torch.empty(batch, P["temb_total"], device=self.device, dtype=torch.float32)
             lib.small_linear(emb, P["temb_w"], temb, bias=P["temb_b"], silu_in=True)
             out.append(temb)
         return out
 
     @torch.no_grad()
-    def forward(self, latents_nhwc: torch.Tensor, temb: torch.Tensor, kvs: List[torch.Tensor],
-                eps_out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """latents_nhwc fp32 [B,h,w,4] -> noise_pred fp32 [B,h,w,4]."""
+    def forward(self, latents_nhwc: torch.Tensor, temb: torch.Tensor, kvs: List[List[torch.Tensor]],
+                eps_out: Optional[torch.Tensor] = None, repeat: int = 1) -> torch.Tensor:
+        """latents_nhwc fp32 [b,h,w,4] -> noise_pred fp32 [b*repeat,h,w,4].  repeat=2 is the
+        classifier-free-guidance doubled batch `cat([latents]*2)`: the same latents are packed
+        twice, temb / kvs carry the [uncond, cond] halves."""
         P = self.P
-        B, H, W, Cin = latents_nhwc.shape
+        b0, H, W, Cin = latents_nhwc.shape
+        B = b0 * repeat
         ctx = _Ctx(self.device, B)
         g = self.groups
         ch = self.cfg.block_out_channels
         kv_it = iter(kvs)
         xin = ctx.empty(B, H, W, 64)
-        lib.pack_latent(latents_nhwc, xin, cin=Cin)
+        for r in range(repeat):
+            lib.pack_latent(latents_nhwc, xin[r * b0:(r + 1) * b0], cin=Cin)
         h = conv3x3(ctx, xin, P["conv_in_w"], P["conv_in_b"], ch[0])
         skips = [h]
         for blk in P["down"]:
@@ -302,39 +332,57 @@ class VAEDecoderB200:
 # pipeline: denoise loop + decode
 # ------------------------------------------------------------------------------------------------
 class _StaticGraph:
-    """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps)."""
+    """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps[, gs])."""
 
-    def __init__(self, pipe: "LCMPipelineB200", B, h, w, steps):
+    def __init__(self, pipe: "LCMPipelineB200", B, h, w, steps, cfg_scale=None):
         dev = pipe.device
-        D = pipe.unet.cfg.cross_attention_dim
-        self.pe = torch.zeros(B, 77, D, device=dev, dtype=BF16)
-        cd = pipe.unet.cfg.time_cond_proj_dim
+        ucfg = pipe.unet.cfg
+        D = ucfg.cross_attention_dim
+        Bc = 2 * B if cfg_scale is not None else B          # CFG: [uncond, cond] context rows
+        self.pe = torch.zeros(Bc, 77, D, device=dev, dtype=BF16)
+        cd = ucfg.time_cond_proj_dim
         self.w_emb = torch.zeros(B, cd, device=dev, dtype=torch.float32) if cd else None
+        self.add = None
+        if pipe.unet.P["add1_w"] is not None:
+            pdim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+            self.add = (torch.zeros(Bc, pdim, device=dev, dtype=torch.float32),
+                        torch.zeros(Bc, 6, device=dev, dtype=torch.float32))
         self.lat = torch.zeros(B, 4, h, w, device=dev, dtype=torch.float32)
         self.noise = torch.zeros(max(steps - 1, 1), B, 4, h, w, device=dev, dtype=torch.float32)
         self.steps = steps
+        args = (self.pe, self.w_emb, self.lat, self.noise, steps)
+        kw = dict(add=self.add, cfg_scale=cfg_scale)
         # warm-up on a side stream (lazy per-device init: smem attributes, module load)
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            pipe.run_static(self.pe, self.w_emb, self.lat, self.noise, steps)
+            pipe.run_static(*args, **kw)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.launch_count
         with torch.cuda.graph(self.graph):
-            self.img, self.final = pipe.run_static(self.pe, self.w_emb, self.lat, self.noise, steps)
+            self.img, self.final = pipe.run_static(*args, **kw)
         self.launches = lib.launch_count - n0        # native kernel launches per replay
 
 
 class LCMPipelineB200:
-    """The hot path as one object: `generate()` = 4..8 x (UNet + scheduler step) + VAE decode."""
+    """The hot path as one object: `generate()` = n x (UNet + scheduler step) + VAE decode.
+
+    SD1.5-LCM (guidance through the w-embedding, no CFG) and SDXL-class UNets (text_time
+    micro-conditioning; classifier-free guidance on a doubled batch when guidance_scale > 1 and
+    the UNet has no time_cond_proj — `StableDiffusionXLPipeline.__call__` behind reference
+    `backends/cuda_worker.py:532`) share this loop."""
 
     def __init__(self, unet_sd, unet_cfg, vae_sd, vae_cfg, device="cuda:0"):
         self.device = torch.device(device)
         self.unet = UNetB200(unet_sd, unet_cfg, device)
         self.vae = VAEDecoderB200(vae_sd, vae_cfg, device)
         self._graphs = {}
+
+    @property
+    def is_sdxl(self) -> bool:
+        return self.unet.P["add1_w"] is not None
 
     def _w_emb(self, B, guidance_scale):
         cd = self.unet.cfg.time_cond_proj_dim
@@ -343,26 +391,42 @@ class LCMPipelineB200:
         gs = torch.as_tensor(guidance_scale, dtype=torch.float32).reshape(-1).expand(B)
         return guidance_scale_embedding(gs - 1.0, cd)           # host, fp32 [B, cd]
 
+    def cfg_scale_for(self, guidance_scale) -> Optional[float]:
+        """The CFG weight, or None when the pass is not classifier-free guided
+        (`do_classifier_free_guidance = guidance_scale > 1 and time_cond_proj_dim is None`)."""
+        if self.unet.cfg.time_cond_proj_dim:
+            return None
+        gs = torch.as_tensor(guidance_scale, dtype=torch.float32).reshape(-1)
+        if gs.numel() > 1 and not bool((gs == gs[0]).all()):
+            raise RuntimeError("classifier-free guidance needs one guidance_scale per batch")
+        g = float(gs[0])
+        return g if g > 1.0 else None
+
     @torch.no_grad()
-    def run_static(self, pe_bf16, w_emb, lat_nchw, noise_nchw, steps: int, record: dict = None):
-        """Everything on device, no host sync, graph-capturable.  Returns (u8 images, latents)."""
+    def run_static(self, pe_bf16, w_emb, lat_nchw, noise_nchw, steps: int, record: dict = None,
+                   add=None, cfg_scale: Optional[float] = None):
+        """Everything on device, no host sync, graph-capturable.  Returns (u8 images, latents).
+        pe_bf16 / add carry 2B rows ([uncond, cond]) when cfg_scale is set."""
         B = lat_nchw.shape[0]
+        Bu = 2 * B if cfg_scale is not None else B
         sched = LCMSchedule(steps)
         kvs = self.unet.encode_context(pe_bf16)
-        tembs = self.unet.time_embeddings(sched.timesteps, B, w_emb)
-        lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record)
+        aug = self.unet.addition_embedding(*add) if add is not None else None
+        tembs = self.unet.time_embeddings(sched.timesteps, Bu, w_emb, aug)
+        lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale)
         return self.vae.decode(lat), lat
 
-    def graph_for(self, B, h, w, steps) -> _StaticGraph:
-        key = (B, h, w, steps)
+    def graph_for(self, B, h, w, steps, cfg_scale=None) -> _StaticGraph:
+        key = (B, h, w, steps, cfg_scale)
         g = self._graphs.get(key)
         if g is None:
             with torch.cuda.device(self.device):
-                g = self._graphs[key] = _StaticGraph(self, B, h, w, steps)
+                g = self._graphs[key] = _StaticGraph(self, B, h, w, steps, cfg_scale)
         return g
 
     @torch.no_grad()
-    def denoise(self, latents_nchw, step_noise_nchw, sched, kvs, tembs, record: dict = None):
+    def denoise(self, latents_nchw, step_noise_nchw, sched, kvs, tembs, record: dict = None,
+                cfg_scale: Optional[float] = None):
         """latents fp32 NCHW [B,4,h,w]; step_noise [steps-1,B,4,h,w].  Returns final latents NHWC."""
         B, C, H, W = latents_nchw.shape
         x = torch.empty(B, H, W, C, device=self.device, dtype=torch.float32)
@@ -375,7 +439,12 @@ class LCMPipelineB200:
                                  noise.view((n - 1) * B, H, W, C))
         den = torch.empty_like(x)
         for i in range(n):
-            eps = self.unet.forward(x, tembs[i], kvs)
+            if cfg_scale is None:
+                eps = self.unet.forward(x, tembs[i], kvs)
+            else:
+                eps2 = self.unet.forward(x, tembs[i], kvs, repeat=2)
+                eps = torch.empty_like(x)
+                lib.cfg_combine(eps2[:B], eps2[B:], cfg_scale, eps)
             x_next = torch.empty_like(x)
             lib.lcm_step(eps, x, noise[i] if sched.has_noise(i) else None, x_next, den, sched.coeffs(i))
             if record is not None:
@@ -384,32 +453,65 @@ class LCMPipelineB200:
             x = x_next
         return x
 
+    def _conditioning(self, prompt_embeds, pooled_embeds, time_ids, negative_prompt_embeds,
+                      negative_pooled_embeds, cfg_scale, height, width):
+        """-> (context rows, (pooled, time_ids) or None), doubled [uncond, cond] under CFG.
+        With no negative prompt the unconditional half is zeros (`force_zeros_for_empty_prompt`,
+        SDXL-base pipeline config)."""
+        B = prompt_embeds.shape[0]
+        pe = prompt_embeds
+        add = None
+        if self.is_sdxl:
+            if pooled_embeds is None:
+                raise RuntimeError("SDXL-class UNet needs pooled_embeds (text_time conditioning)")
+            if time_ids is None:
+                time_ids = torch.tensor([[height, width, 0, 0, height, width]],
+                                        dtype=torch.float32).repeat(B, 1)
+            add = (pooled_embeds.float(), time_ids.float())
+        if cfg_scale is not None:
+            neg = torch.zeros_like(pe) if negative_prompt_embeds is None else negative_prompt_embeds
+            pe = torch.cat([neg.to(pe.device, pe.dtype), pe], 0)
+            if add is not None:
+                negp = (torch.zeros_like(add[0]) if negative_pooled_embeds is None
+                        else negative_pooled_embeds.to(add[0].device).float())
+                add = (torch.cat([negp, add[0]], 0), torch.cat([add[1], add[1]], 0))
+        return pe, add
+
     @torch.no_grad()
     def generate(self, prompt_embeds, latents_nchw, step_noise_nchw, num_inference_steps: int,
                  guidance_scale=1.0, record: dict = None, return_latents: bool = False,
-                 use_graph: bool = False):
+                 use_graph: bool = False, pooled_embeds=None, time_ids=None,
+                 negative_prompt_embeds=None, negative_pooled_embeds=None):
         """Public entry: host or device tensors in -> u8 images [B,H,W,3] on device (and the
         final latents NHWC fp32 if asked).  With use_graph the whole pass is one CUDA-graph
         replay; the returned tensors are the graph's static outputs (consume before next call)."""
         B, _, h, w = latents_nchw.shape
         steps = int(num_inference_steps)
         w_emb = self._w_emb(B, guidance_scale)
+        cfg_scale = self.cfg_scale_for(guidance_scale)
+        pe_all, add = self._conditioning(prompt_embeds, pooled_embeds, time_ids, negative_prompt_embeds,
+                                         negative_pooled_embeds, cfg_scale, 8 * h, 8 * w)
         with torch.cuda.device(self.device):
             if use_graph and record is None:
-                g = self.graph_for(B, h, w, steps)
-                g.pe.copy_(prompt_embeds, non_blocking=True)
+                g = self.graph_for(B, h, w, steps, cfg_scale)
+                g.pe.copy_(pe_all, non_blocking=True)
                 if w_emb is not None:
                     g.w_emb.copy_(w_emb, non_blocking=True)
+                if add is not None:
+                    g.add[0].copy_(add[0], non_blocking=True)
+                    g.add[1].copy_(add[1], non_blocking=True)
                 g.lat.copy_(latents_nchw, non_blocking=True)
                 if steps > 1:
                     g.noise.copy_(step_noise_nchw, non_blocking=True)
                 g.graph.replay()
                 img, lat = g.img, g.final
             else:
-                pe = prompt_embeds.to(self.device, BF16).contiguous()
+                pe = pe_all.to(self.device, BF16).contiguous()
                 we = w_emb.to(self.device) if w_emb is not None else None
+                if add is not None:
+                    add = (add[0].to(self.device), add[1].to(self.device))
                 lat0 = latents_nchw.to(self.device, torch.float32).contiguous()
                 nz = (step_noise_nchw.to(self.device, torch.float32).contiguous()
                       if steps > 1 else None)
-                img, lat = self.run_static(pe, we, lat0, nz, steps, record)
+                img, lat = self.run_static(pe, we, lat0, nz, steps, record, add=add, cfg_scale=cfg_scale)
         return (img, lat) if return_latents else img

@@ -23,6 +23,7 @@ EXPORTS = [
     "dl_debug_attention_trace",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
+    "dl_cfg_combine",
 ]
 
 
@@ -94,6 +95,8 @@ def load() -> C.CDLL:
                                                 C.c_void_p]
             lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_cfg_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong,
+                                           C.c_void_p]
             lib.dl_latent_pool8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_void_p]
             _lib = lib
@@ -328,6 +331,12 @@ def lcm_step(eps, x, noise, x_next, denoised, coeffs):
     k = LcmCoeffs(*[float(v) for v in coeffs])
     _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
                               denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def cfg_combine(eps_uncond, eps_text, guidance_scale, out):
+    _check(load().dl_cfg_combine(eps_uncond.data_ptr(), eps_text.data_ptr(), float(guidance_scale),
+                                 out.data_ptr(), out.numel(), _stream()), "cfg_combine")
     _count()
 
 

@@ -23,6 +23,33 @@ def sd15_lcm_unet_cfg():
                            norm_eps=1e-5, time_cond_proj_dim=256)
 
 
+def sdxl_unet_cfg():
+    """SDXL-base UNet (SURVEY.md App. A.2 "SDXL-base"; BASELINE config C5)."""
+    return SimpleNamespace(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280),
+                           down_attn=(False, True, True), layers_per_block=2,
+                           cross_attention_dim=2048, attention_head_dim=(5, 10, 20),
+                           norm_num_groups=32, norm_eps=1e-5, time_cond_proj_dim=None,
+                           transformer_layers_per_block=(1, 2, 10), use_linear_projection=True,
+                           addition_embed_type="text_time", addition_time_embed_dim=256,
+                           projection_class_embeddings_input_dim=2816)
+
+
+def sdxl_vae_cfg():
+    return SimpleNamespace(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512),
+                           layers_per_block=2, norm_num_groups=32, scaling_factor=0.13025,
+                           sample_size=1024)
+
+
+def heads_at(cfg, i: int) -> int:
+    a = cfg.attention_head_dim
+    return a if isinstance(a, int) else a[i]
+
+
+def depth_at(cfg, i: int) -> int:
+    t = getattr(cfg, "transformer_layers_per_block", None)
+    return t[i] if t else 1
+
+
 def sd_vae_cfg():
     return SimpleNamespace(latent_channels=4, out_channels=3, block_out_channels=(128, 256, 512, 512),
                            layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215,
@@ -40,20 +67,22 @@ def _resnet(s, p, cin, cout, temb):
         s[p + "conv_shortcut.weight"] = (cout, cin, 1, 1); s[p + "conv_shortcut.bias"] = (cout,)
 
 
-def _transformer(s, p, c, ctx):
+def _transformer(s, p, c, ctx, depth=1, linear_proj=False):
+    proj = (c, c) if linear_proj else (c, c, 1, 1)
     s[p + "norm.weight"] = (c,); s[p + "norm.bias"] = (c,)
-    s[p + "proj_in.weight"] = (c, c, 1, 1); s[p + "proj_in.bias"] = (c,)
-    b = p + "transformer_blocks.0."
-    for i in (1, 2, 3):
-        s[b + f"norm{i}.weight"] = (c,); s[b + f"norm{i}.bias"] = (c,)
-    for a, kd in (("attn1", c), ("attn2", ctx)):
-        s[b + f"{a}.to_q.weight"] = (c, c)
-        s[b + f"{a}.to_k.weight"] = (c, kd)
-        s[b + f"{a}.to_v.weight"] = (c, kd)
-        s[b + f"{a}.to_out.0.weight"] = (c, c); s[b + f"{a}.to_out.0.bias"] = (c,)
-    s[b + "ff.net.0.proj.weight"] = (8 * c, c); s[b + "ff.net.0.proj.bias"] = (8 * c,)
-    s[b + "ff.net.2.weight"] = (c, 4 * c); s[b + "ff.net.2.bias"] = (c,)
-    s[p + "proj_out.weight"] = (c, c, 1, 1); s[p + "proj_out.bias"] = (c,)
+    s[p + "proj_in.weight"] = proj; s[p + "proj_in.bias"] = (c,)
+    for l in range(depth):
+        b = p + f"transformer_blocks.{l}."
+        for i in (1, 2, 3):
+            s[b + f"norm{i}.weight"] = (c,); s[b + f"norm{i}.bias"] = (c,)
+        for a, kd in (("attn1", c), ("attn2", ctx)):
+            s[b + f"{a}.to_q.weight"] = (c, c)
+            s[b + f"{a}.to_k.weight"] = (c, kd)
+            s[b + f"{a}.to_v.weight"] = (c, kd)
+            s[b + f"{a}.to_out.0.weight"] = (c, c); s[b + f"{a}.to_out.0.bias"] = (c,)
+        s[b + "ff.net.0.proj.weight"] = (8 * c, c); s[b + "ff.net.0.proj.bias"] = (8 * c,)
+        s[b + "ff.net.2.weight"] = (c, 4 * c); s[b + "ff.net.2.bias"] = (c,)
+    s[p + "proj_out.weight"] = proj; s[p + "proj_out.bias"] = (c,)
 
 
 def unet_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
@@ -65,6 +94,12 @@ def unet_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
     s["time_embedding.linear_2.weight"] = (temb, temb); s["time_embedding.linear_2.bias"] = (temb,)
     if cfg.time_cond_proj_dim:
         s["time_embedding.cond_proj.weight"] = (ch[0], cfg.time_cond_proj_dim)
+    if getattr(cfg, "addition_embed_type", None) == "text_time":
+        pin = cfg.projection_class_embeddings_input_dim
+        s["add_embedding.linear_1.weight"] = (temb, pin); s["add_embedding.linear_1.bias"] = (temb,)
+        s["add_embedding.linear_2.weight"] = (temb, temb); s["add_embedding.linear_2.bias"] = (temb,)
+    lin = bool(getattr(cfg, "use_linear_projection", False))
+    n_lv = len(ch)
     skips = [ch[0]]
     cout = ch[0]
     for i, c in enumerate(ch):
@@ -72,14 +107,15 @@ def unet_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
         for j in range(cfg.layers_per_block):
             _resnet(s, f"down_blocks.{i}.resnets.{j}.", cin if j == 0 else cout, cout, temb)
             if cfg.down_attn[i]:
-                _transformer(s, f"down_blocks.{i}.attentions.{j}.", cout, cfg.cross_attention_dim)
+                _transformer(s, f"down_blocks.{i}.attentions.{j}.", cout, cfg.cross_attention_dim,
+                             depth_at(cfg, i), lin)
             skips.append(cout)
         if i != len(ch) - 1:
             s[f"down_blocks.{i}.downsamplers.0.conv.weight"] = (cout, cout, 3, 3)
             s[f"down_blocks.{i}.downsamplers.0.conv.bias"] = (cout,)
             skips.append(cout)
     _resnet(s, "mid_block.resnets.0.", ch[-1], ch[-1], temb)
-    _transformer(s, "mid_block.attentions.0.", ch[-1], cfg.cross_attention_dim)
+    _transformer(s, "mid_block.attentions.0.", ch[-1], cfg.cross_attention_dim, depth_at(cfg, n_lv - 1), lin)
     _resnet(s, "mid_block.resnets.1.", ch[-1], ch[-1], temb)
     rev, rattn = list(reversed(ch)), list(reversed(cfg.down_attn))
     prev = rev[0]
@@ -87,7 +123,8 @@ def unet_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
         for j in range(cfg.layers_per_block + 1):
             _resnet(s, f"up_blocks.{i}.resnets.{j}.", (prev if j == 0 else c) + skips.pop(), c, temb)
             if rattn[i]:
-                _transformer(s, f"up_blocks.{i}.attentions.{j}.", c, cfg.cross_attention_dim)
+                _transformer(s, f"up_blocks.{i}.attentions.{j}.", c, cfg.cross_attention_dim,
+                             depth_at(cfg, n_lv - 1 - i), lin)
         if i != len(ch) - 1:
             s[f"up_blocks.{i}.upsamplers.0.conv.weight"] = (c, c, 3, 3)
             s[f"up_blocks.{i}.upsamplers.0.conv.bias"] = (c,)

@@ -118,37 +118,53 @@ def pack_resnet(sd: Dict[str, torch.Tensor], prefix: str, device) -> Packed:
     return p
 
 
-def pack_transformer(sd, prefix: str, heads: int, device) -> Packed:
+def pack_transformer(sd, prefix: str, heads: int, device, depth: int = 1) -> Packed:
+    """Transformer2DModel with `depth` BasicTransformerBlocks.  proj_in/proj_out are 1x1 convs
+    (SD1.5) or Linears (SDXL, use_linear_projection): the same [C, C] matrix on NHWC rows."""
     p = Packed()
     p["norm_w"], p["norm_b"] = _f32(sd[prefix + "norm.weight"], device), _f32(sd[prefix + "norm.bias"], device)
     p["proj_in_w"], p["proj_in_b"] = pack_conv1x1(sd[prefix + "proj_in.weight"], device), _f32(sd[prefix + "proj_in.bias"], device)
     p["proj_out_w"], p["proj_out_b"] = pack_conv1x1(sd[prefix + "proj_out.weight"], device), _f32(sd[prefix + "proj_out.bias"], device)
-    b = prefix + "transformer_blocks.0."
-    c = sd[b + "attn1.to_q.weight"].shape[0]
+    c = sd[prefix + "transformer_blocks.0.attn1.to_q.weight"].shape[0]
     p["c"], p["heads"], p["d"] = c, heads, c // heads
     p["hstride"] = head_stride(c // heads)
-    for i in (1, 2, 3):
-        p[f"ln{i}_w"], p[f"ln{i}_b"] = _f32(sd[b + f"norm{i}.weight"], device), _f32(sd[b + f"norm{i}.bias"], device)
-    qkv = torch.cat([pad_heads(sd[b + f"attn1.to_{n}.weight"].float(), heads) for n in "qkv"], 0)
-    p["qkv_w"] = _bf(qkv, device)
-    p["qkv_b"] = _f32(ones_bias(heads, c // heads, 3, 2), device)
-    p["o1_w"], p["o1_b"] = _bf(sd[b + "attn1.to_out.0.weight"], device), _f32(sd[b + "attn1.to_out.0.bias"], device)
-    p["q2_w"] = _bf(pad_heads(sd[b + "attn2.to_q.weight"].float(), heads), device)
-    kv = torch.cat([pad_heads(sd[b + f"attn2.to_{n}.weight"].float(), heads) for n in "kv"], 0)
-    p["kv2_w"] = _bf(kv, device)
-    p["kv2_b"] = _f32(ones_bias(heads, c // heads, 2, 1), device)
-    p["o2_w"], p["o2_b"] = _bf(sd[b + "attn2.to_out.0.weight"], device), _f32(sd[b + "attn2.to_out.0.bias"], device)
-    p["ff1_w"] = _bf(interleave_geglu(sd[b + "ff.net.0.proj.weight"].float()), device)
-    p["ff1_b"] = _f32(interleave_geglu(sd[b + "ff.net.0.proj.bias"].float()), device)
-    p["ff2_w"], p["ff2_b"] = _bf(sd[b + "ff.net.2.weight"], device), _f32(sd[b + "ff.net.2.bias"], device)
+    p["blocks"] = []
+    for l in range(depth):
+        b = prefix + f"transformer_blocks.{l}."
+        q = Packed()
+        for i in (1, 2, 3):
+            q[f"ln{i}_w"], q[f"ln{i}_b"] = _f32(sd[b + f"norm{i}.weight"], device), _f32(sd[b + f"norm{i}.bias"], device)
+        qkv = torch.cat([pad_heads(sd[b + f"attn1.to_{n}.weight"].float(), heads) for n in "qkv"], 0)
+        q["qkv_w"] = _bf(qkv, device)
+        q["qkv_b"] = _f32(ones_bias(heads, c // heads, 3, 2), device)
+        q["o1_w"], q["o1_b"] = _bf(sd[b + "attn1.to_out.0.weight"], device), _f32(sd[b + "attn1.to_out.0.bias"], device)
+        q["q2_w"] = _bf(pad_heads(sd[b + "attn2.to_q.weight"].float(), heads), device)
+        kv = torch.cat([pad_heads(sd[b + f"attn2.to_{n}.weight"].float(), heads) for n in "kv"], 0)
+        q["kv2_w"] = _bf(kv, device)
+        q["kv2_b"] = _f32(ones_bias(heads, c // heads, 2, 1), device)
+        q["o2_w"], q["o2_b"] = _bf(sd[b + "attn2.to_out.0.weight"], device), _f32(sd[b + "attn2.to_out.0.bias"], device)
+        q["ff1_w"] = _bf(interleave_geglu(sd[b + "ff.net.0.proj.weight"].float()), device)
+        q["ff1_b"] = _f32(interleave_geglu(sd[b + "ff.net.0.proj.bias"].float()), device)
+        q["ff2_w"], q["ff2_b"] = _bf(sd[b + "ff.net.2.weight"], device), _f32(sd[b + "ff.net.2.bias"], device)
+        p["blocks"].append(q)
     return p
+
+
+def _heads_at(cfg, i):
+    a = cfg.attention_head_dim
+    return a if isinstance(a, int) else a[i]
+
+
+def _depth_at(cfg, i):
+    t = getattr(cfg, "transformer_layers_per_block", None)
+    return t[i] if t else 1
 
 
 def pack_unet(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
     """cfg: anything with block_out_channels, down_attn, layers_per_block, attention_head_dim,
     time_cond_proj_dim (oracle.unet.UNetConfig or a dict-like parsed from unet/config.json)."""
-    heads = cfg.attention_head_dim
     ch = cfg.block_out_channels
+    n_lv = len(ch)
     P = Packed()
     P["cfg"] = cfg
     P["conv_in_w"] = pack_conv3x3(sd["conv_in.weight"], device, pad_in_to=64)
@@ -157,6 +173,11 @@ def pack_unet(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
     P["t2_w"], P["t2_b"] = _bf(sd["time_embedding.linear_2.weight"], device), _f32(sd["time_embedding.linear_2.bias"], device)
     P["cond_w"] = (_bf(sd["time_embedding.cond_proj.weight"], device)
                    if "time_embedding.cond_proj.weight" in sd else None)
+    if "add_embedding.linear_1.weight" in sd:        # SDXL text_time micro-conditioning MLP
+        P["add1_w"], P["add1_b"] = _bf(sd["add_embedding.linear_1.weight"], device), _f32(sd["add_embedding.linear_1.bias"], device)
+        P["add2_w"], P["add2_b"] = _bf(sd["add_embedding.linear_2.weight"], device), _f32(sd["add_embedding.linear_2.bias"], device)
+    else:
+        P["add1_w"] = None
     resnets = []          # in execution order, for the fused time_emb_proj matrix
 
     def res(prefix):
@@ -172,13 +193,15 @@ def pack_unet(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
         for j in range(cfg.layers_per_block):
             blk["resnets"].append(res(f"down_blocks.{i}.resnets.{j}."))
             if cfg.down_attn[i]:
-                blk["attns"].append(pack_transformer(sd, f"down_blocks.{i}.attentions.{j}.", heads, device))
+                blk["attns"].append(pack_transformer(sd, f"down_blocks.{i}.attentions.{j}.",
+                                                     _heads_at(cfg, i), device, _depth_at(cfg, i)))
         if i != len(ch) - 1:
             k = f"down_blocks.{i}.downsamplers.0.conv."
             blk["down"] = Packed(w=pack_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))
         P["down"].append(blk)
     P["mid"] = Packed(resnets=[res("mid_block.resnets.0.")],
-                      attns=[pack_transformer(sd, "mid_block.attentions.0.", heads, device)])
+                      attns=[pack_transformer(sd, "mid_block.attentions.0.", _heads_at(cfg, n_lv - 1),
+                                              device, _depth_at(cfg, n_lv - 1))])
     P["mid"]["resnets"].append(res("mid_block.resnets.1."))
     P["up"] = []
     rev_attn = list(reversed(cfg.down_attn))
@@ -187,7 +210,9 @@ def pack_unet(sd: Dict[str, torch.Tensor], cfg, device) -> Packed:
         for j in range(cfg.layers_per_block + 1):
             blk["resnets"].append(res(f"up_blocks.{i}.resnets.{j}."))
             if rev_attn[i]:
-                blk["attns"].append(pack_transformer(sd, f"up_blocks.{i}.attentions.{j}.", heads, device))
+                blk["attns"].append(pack_transformer(sd, f"up_blocks.{i}.attentions.{j}.",
+                                                     _heads_at(cfg, n_lv - 1 - i), device,
+                                                     _depth_at(cfg, n_lv - 1 - i)))
         if i != len(ch) - 1:
             k = f"up_blocks.{i}.upsamplers.0.conv."
             blk["up"] = Packed(w=pack_upsample_conv3x3(sd[k + "weight"], device), b=_f32(sd[k + "bias"], device))

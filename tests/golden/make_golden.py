@@ -39,9 +39,32 @@ def full(size=512, steps=4, tiling=False):
                         image=img)
 
 
+def sdxl_inputs(batch, size, steps, ctx_dim=2048, pooled_dim=1280):
+    pe, lat, noise = synthetic_inputs(batch, size, size, steps, ctx_dim=ctx_dim)
+    pooled = torch.randn(batch, pooled_dim, generator=torch.Generator().manual_seed(2))
+    return pe, pooled, lat, noise
+
+
+def sdxl(size=512, steps=3, gs=7.5):
+    """BASELINE config C5 architecture (SDXL-base UNet, random-init seed 0; SDXL VAE scaling),
+    classifier-free guidance 7.5 with the zero unconditional embedding, at a size and step
+    count the fp32 CPU oracle finishes in minutes."""
+    from oracle.pipeline import run_pipeline_sdxl
+    torch.set_num_threads(os.cpu_count())
+    unet, vae = build_random_init(UNetConfig.sdxl_base(), VAEConfig(scaling_factor=0.13025, sample_size=1024), seed=0)
+    pe, pooled, lat, noise = sdxl_inputs(1, size, steps)
+    rec = {}
+    img = run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, steps, gs, size, size, record=rec)
+    np.savez_compressed(os.path.join(HERE, f"sdxl_{size}_{steps}step_cfg.npz"),
+                        noise_pred=torch.stack(rec["noise_pred"]).numpy().astype(np.float32),
+                        latents=torch.stack(rec["latents"]).numpy().astype(np.float32), image=img)
+
+
 if __name__ == "__main__":
     tiny()
     if "--full" in sys.argv:
         full()
+    if "--sdxl" in sys.argv:
+        sdxl()
     if "--c3" in sys.argv:
         full(768, 8)          # BASELINE config C3 geometry (B=1), untiled VAE decode

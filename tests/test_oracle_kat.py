@@ -40,6 +40,29 @@ def test_param_counts_match_published_architectures():
     assert n_vanilla == 859_520_964                   # the published SD1.5 UNet size
     n_vae, v = _meta_count(OracleVAEDecoder, VAEConfig())
     assert n_vae == 49_490_199                        # decoder 49 490 179 + post_quant_conv 20
+    n_xl, x = _meta_count(OracleUNet, UNetConfig.sdxl_base())
+    assert n_xl == 2_567_463_684                      # the published SDXL-base UNet size (2.57 B)
+    assert x.add_embedding.linear_1.weight.shape == (1280, 2816)
+    assert len(x.mid_block.attentions[0].transformer_blocks) == 10
+    assert x.down_blocks[0].attentions is None        # DownBlock2D: no attention at 128^2
+
+
+def test_sdxl_oracle_cfg_pipeline_semantics():
+    """CFG algebra and text_time plumbing of `run_pipeline_sdxl` on the tiny SDXL topology:
+    gs <= 1 runs the single-batch branch; with identical cond/uncond inputs CFG is the identity."""
+    from oracle.pipeline import build_random_init, run_pipeline_sdxl, synthetic_inputs
+    cfg = UNetConfig.tiny_sdxl()
+    unet, vae = build_random_init(cfg, VAEConfig.tiny(), seed=0)
+    pe, lat, noise = synthetic_inputs(1, 64, 64, 2, ctx_dim=cfg.cross_attention_dim)
+    pooled = torch.randn(1, 80, generator=torch.Generator().manual_seed(2))
+    r1, r2 = {}, {}
+    run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, 2, 1.0, 64, 64, record=r1, output_type="latent")
+    run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, 2, 5.0, 64, 64, record=r2, output_type="latent",
+                      negative_prompt_embeds=pe, negative_pooled_embeds=pooled)
+    assert torch.allclose(r1["noise_pred"][0], r2["noise_pred"][0], atol=1e-5)
+    r3 = {}
+    run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, 2, 5.0, 64, 64, record=r3, output_type="latent")
+    assert not torch.allclose(r1["noise_pred"][0], r3["noise_pred"][0], atol=1e-3)
 
 
 def test_diffusers_state_dict_names():

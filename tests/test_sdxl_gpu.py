@@ -1,0 +1,73 @@
+"""SDXL-class path (BASELINE config C5 architecture) against the fp32 oracle:
+text_time micro-conditioning, per-level head counts (head dim 64), deep transformers with linear
+projections, classifier-free guidance on the doubled batch, LCMScheduler.  Same protocol and
+tolerances as tests/test_pipeline_gpu.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_pipeline_gpu import NOISE_PRED_TOL, PSNR_MIN_DB, max_rel_err, psnr_u8
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(batch, size, steps, ctx_dim, pooled_dim):
+    from oracle.pipeline import synthetic_inputs
+    pe, lat, noise = synthetic_inputs(batch, size, size, steps, ctx_dim=ctx_dim)
+    pooled = torch.randn(batch, pooled_dim, generator=torch.Generator().manual_seed(2))
+    return pe, pooled, lat, noise
+
+
+@pytest.mark.parametrize("gs", [7.5, 1.0])
+def test_tiny_sdxl_pipeline_parity(gs):
+    """SDXL topology at small widths, live against the oracle; gs=7.5 runs CFG (doubled batch),
+    gs=1.0 the un-guided branch of the same pipeline."""
+    from oracle.pipeline import build_random_init, run_pipeline_sdxl
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from dreamlab_b200.engine import LCMPipelineB200
+    ucfg = UNetConfig.tiny_sdxl()
+    unet, vae = build_random_init(ucfg, VAEConfig.tiny(), seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0")
+    assert pipe.is_sdxl
+    steps, size, B = 3, 128, 2
+    pdim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+    pe, pooled, lat, noise = _inputs(B, size, steps, ucfg.cross_attention_dim, pdim)
+    rec_o, rec_c = {}, {}
+    ref = run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, steps, gs, size, size, record=rec_o)
+    img = pipe.generate(pe, lat, noise, steps, gs, record=rec_c, pooled_embeds=pooled)
+    torch.cuda.synchronize()
+    errs = [max_rel_err(c.cpu(), o) for c, o in zip(rec_c["noise_pred"], rec_o["noise_pred"])]
+    p = psnr_u8(img.cpu().numpy(), ref)
+    print(f"tiny SDXL gs={gs}: noise_pred max-rel-err per step {['%.2e' % e for e in errs]}  PSNR {p:.1f} dB")
+    assert max(errs) <= NOISE_PRED_TOL, errs
+    assert p >= PSNR_MIN_DB, p
+    # graph replay == eager, byte for byte
+    img2 = pipe.generate(pe, lat, noise, steps, gs, use_graph=True, pooled_embeds=pooled).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(img2, img)
+
+
+def test_sdxl_base_512_3step_cfg_vs_committed_golden():
+    """Full SDXL-base UNet (2.57 B parameters, random-init seed 0) + SDXL VAE scaling, 512x512,
+    3 LCM steps, CFG 7.5, against oracle outputs committed in tests/golden/ (make_golden.py --sdxl)."""
+    from dreamlab_b200 import synthetic as syn
+    from dreamlab_b200.engine import LCMPipelineB200
+    from oracle.pipeline import build_random_init
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sdxl_512_3step_cfg.npz"))
+    unet, vae = build_random_init(UNetConfig.sdxl_base(), VAEConfig(scaling_factor=0.13025, sample_size=1024), seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0")
+    del unet
+    pe, pooled, lat, noise = _inputs(1, 512, 3, 2048, 1280)
+    rec = {}
+    img = pipe.generate(pe, lat, noise, 3, 7.5, record=rec, pooled_embeds=pooled)
+    torch.cuda.synchronize()
+    errs = [max_rel_err(rec["noise_pred"][i].cpu(), torch.from_numpy(g["noise_pred"][i])) for i in range(3)]
+    p = psnr_u8(img.cpu().numpy(), g["image"])
+    print(f"SDXL 512^2 CFG noise_pred max-rel-err per step: {['%.2e' % e for e in errs]}  image PSNR {p:.1f} dB")
+    assert max(errs) <= NOISE_PRED_TOL, errs
+    assert p >= PSNR_MIN_DB, p

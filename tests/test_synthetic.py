@@ -21,6 +21,11 @@ def test_unet_and_vae_shape_tables_match_oracle():
     assert S.vae_decoder_shapes(vt.cfg) == _shapes(vt)
     n = sum(torch.Size(s).numel() for s in S.unet_shapes(S.sd15_lcm_unet_cfg()).values())
     assert n == 859_602_884
+    with torch.device("meta"):
+        x, xt = OracleUNet(UNetConfig.sdxl_base()), OracleUNet(UNetConfig.tiny_sdxl())
+    assert S.unet_shapes(S.sdxl_unet_cfg()) == _shapes(x)
+    assert S.unet_shapes(xt.cfg) == _shapes(xt)
+    assert sum(torch.Size(s).numel() for s in S.unet_shapes(S.sdxl_unet_cfg()).values()) == 2_567_463_684
 
 
 def test_random_state_dict_is_deterministic_and_bounded():

@@ -63,11 +63,40 @@ def test_sd15_gets_b200_worker_with_worker_id_kwarg():
     assert w is fake.return_value
 
 
-def test_sdxl_is_reported_unsupported_outside_reference_tree():
+def test_sdxl_gets_b200_sdxl_worker_with_worker_id_kwarg():
+    """Reference `backends/worker_factory.py:91-94` (sdxl -> SDXL worker class, keyword ctor)."""
+    fake = Mock()
     with patch("backends.worker_factory.detect_worker_type", return_value="sdxl"), \
-            patch.dict(sys.modules, {"backends.cuda_worker": None}):
-        with pytest.raises(RuntimeError, match="SDXL"):
-            create_cuda_worker(worker_id=0)
+            patch("backends.b200_worker.B200SDXLWorker", fake):
+        w = create_cuda_worker(worker_id=5)
+    fake.assert_called_once_with(worker_id=5)
+    assert w is fake.return_value
+
+
+def test_sdxl_worker_contract_errors_without_loading():
+    """Same env errors as `DiffusersSDXLCudaWorker.__init__` (reference `cuda_worker.py:343-346`)."""
+    from backends.b200_worker import B200SDXLWorker
+    with patch.dict(os.environ, {}, clear=True):
+        with pytest.raises(RuntimeError, match="MODEL_ROOT is required for SDXL CUDA worker"):
+            B200SDXLWorker(worker_id=0)
+    with patch.dict(os.environ, {"MODEL_ROOT": "/models"}, clear=True):
+        with pytest.raises(RuntimeError, match="MODEL is required for SDXL CUDA worker"):
+            B200SDXLWorker(worker_id=0)
+
+
+def test_unet_cfg_from_json_sdxl():
+    from backends.b200_worker import unet_cfg_from_json
+    c = unet_cfg_from_json({"block_out_channels": [320, 640, 1280],
+                            "down_block_types": ["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+                            "attention_head_dim": [5, 10, 20], "transformer_layers_per_block": [1, 2, 10],
+                            "cross_attention_dim": 2048, "use_linear_projection": True,
+                            "addition_embed_type": "text_time", "addition_time_embed_dim": 256,
+                            "projection_class_embeddings_input_dim": 2816})
+    assert c.down_attn == (False, True, True) and c.attention_head_dim == (5, 10, 20)
+    assert c.transformer_layers_per_block == (1, 2, 10) and c.use_linear_projection
+    assert c.time_cond_proj_dim is None and c.addition_embed_type == "text_time"
+    d = unet_cfg_from_json({})
+    assert d.attention_head_dim == 8 and d.transformer_layers_per_block == () and not d.use_linear_projection
 
 
 def test_b200_worker_contract_errors_without_loading():
