@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DL_ABI_VERSION 1
+#define DL_ABI_VERSION 2
 
 /* ---- library ---------------------------------------------------------------------------- */
 int dl_abi_version(void);
@@ -75,6 +75,9 @@ typedef struct dl_igemm_desc {
   int mode;                  /* DL_EPI_*                                                      */
   float alpha;               /* accumulator scale (0 -> 1)                                    */
   int bn;                    /* N tile (multiple of 16, <=256); 0 = auto                      */
+  int in_rows;               /* halo-padded row strips (SDXL patch parallel): a0/a1 */
+  int in_row0;               /*   hold in_rows >= h rows per image and output row y reads input rows
+                                y + dy + in_row0; 0/0 = dense (in_rows = h)                    */
 } dl_igemm_desc;
 
 int dl_igemm(const dl_igemm_desc* desc, void* stream);
@@ -90,6 +93,20 @@ size_t dl_groupnorm_workspace_bytes(int nimg, int groups);
 int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
                  float eps, const float* gamma, const float* beta, int apply_silu, void* out,
                  void* workspace, void* stream);
+
+/* Split form for row-strip (patch-parallel) execution, SURVEY.md §8e exchange X3: `stats` gets
+ * the strip's per-(image, group) (mean, M2) as fp32 [nimg, groups, 2]; the caller all-gathers the
+ * records of all ranks into stats_all [nranks, nimg, groups, 2] (equal strips: hw pixels each);
+ * dl_groupnorm_apply merges them in rank order and normalises the strip.  out_img_stride
+ * (elements, 0 = dense) lets the result land inside a halo-padded buffer.  The workspace must
+ * be zero-initialised once (>= dl_groupnorm_split_workspace_bytes()).                          */
+size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups);
+int dl_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
+                       float* stats, void* workspace, void* stream);
+int dl_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
+                       float eps, const float* gamma, const float* beta, int apply_silu,
+                       const float* stats_all, int nranks, void* out, long long out_img_stride,
+                       void* stream);
 
 /* ---- LayerNorm over the channel dim, bf16 rows (BasicTransformerBlock.norm1/2/3, K8) ------ */
 int dl_layernorm(const void* x, long long rows, int c, float eps, const float* gamma,
@@ -122,6 +139,10 @@ int dl_small_linear(const float* x, int m, int k, const void* w, const float* bi
 int dl_upsample2x(const void* x, int nimg, int h, int w, int c, void* out, void* stream);
 /* cols[n*ho*wo, 9*c] for conv3x3 stride 2 pad 1 (Downsample2D); K index = tap*c + channel     */
 int dl_im2col_s2(const void* x, int nimg, int h, int w, int c, void* cols, void* stream);
+/* same over a halo-padded strip: x holds in_rows rows per image, logical row y is input row
+ * y + in_row0 (rows outside [0, in_rows) read as zero); h = logical rows of the strip           */
+int dl_im2col_s2_halo(const void* x, int nimg, int in_rows, int in_row0, int h, int w, int c,
+                      void* cols, void* stream);
 /* bf16 [npix, cpad] <- mat . (fp32 NHWC [npix, cin] * scale) + vec, zero-padded to cpad channels
  * (feeds conv_in).  mat/vec: optional fp32 [cin,cin] / [cin] = the VAE post_quant_conv 1x1 and the
  * `latents / scaling_factor` of reference `backends/rknnlcm.py:614` (K13); NULL = identity.     */

@@ -50,6 +50,7 @@ struct IgemmParams {
   int tiles_x, tiles_y, tiles_n;
   int W, H, NIMG;
   int taps, kc0, kc1;
+  int in_row0;           // input row of output row 0 (halo-padded strips: 1), else 0
   signed char tdy[9], tdx[9];   // per-tap input offsets (3x3: -1..1; folded upsample: 2x2 phase taps)
   int N, BN, n_tiles, m_tiles;
   int stages, tmem_cols, acc_bufs;
@@ -132,7 +133,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.tdy[tap];
+          const int dy = p.tdy[tap] + p.in_row0;
           const int dx = p.tdx[tap];
           for (int c = 0; c < kc; ++c, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -448,8 +449,12 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
     DL_CHECK_ARG(d->alpha == 0.0f || d->alpha == 1.0f, "igemm: residual needs alpha == 1");
   }
 
+  const int in_rows = d->in_rows > 0 ? d->in_rows : d->h;
+  DL_CHECK_ARG(d->in_row0 >= 0 && d->in_row0 + d->h <= in_rows + 1 && (d->in_rows == 0 || d->taps != 1),
+               "igemm: bad halo geometry (in_rows=%d in_row0=%d h=%d)", d->in_rows, d->in_row0, d->h);
   IgemmParams p;
   memset(&p, 0, sizeof(p));
+  p.in_row0 = d->in_row0;
   // ---- M tiling: tw x th x tn = 128 (powers of two; partial tiles are masked) ----
   const int tw = pick_extent(d->w, 128);
   const int th = pick_extent(d->h, 128 / tw);
@@ -504,16 +509,18 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
 
   // ---- tensor maps ----
   {
-    const uint64_t dims[4] = {(uint64_t)d->c0, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    // halo-padded strips (patch parallel): the input holds in_rows >= h rows per image and
+    // output row y reads input rows y + dy + in_row0; rows outside [0, in_rows) are zero fill
+    const uint64_t dims[4] = {(uint64_t)d->c0, (uint64_t)d->w, (uint64_t)in_rows, (uint64_t)d->nimg};
     const uint64_t ps = (uint64_t)d->a0_pix_stride * 2;
-    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * in_rows};
     const uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (make_tmap_bf16(&p.tmA0, d->a0, 4, dims, strides, box)) return 1;
   }
   if (d->c1 > 0) {
-    const uint64_t dims[4] = {(uint64_t)d->c1, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};
+    const uint64_t dims[4] = {(uint64_t)d->c1, (uint64_t)d->w, (uint64_t)in_rows, (uint64_t)d->nimg};
     const uint64_t ps = (uint64_t)d->a1_pix_stride * 2;
-    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * d->h};
+    const uint64_t strides[3] = {ps, ps * d->w, ps * d->w * in_rows};
     const uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (make_tmap_bf16(&p.tmA1, d->a1, 4, dims, strides, box)) return 1;
   }

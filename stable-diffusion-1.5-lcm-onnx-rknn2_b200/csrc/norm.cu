@@ -481,7 +481,227 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
   }
 }
 
+// ---- split GroupNorm (statistics | apply) for row-strip patch-parallel execution -------------
+// A rank holds a strip of rows of every image: gn_stats_kernel reduces the strip to per-(image,
+// group) (mean, M2); the host all-gathers those [nimg, groups, 2] fp32 records across the ranks
+// (SURVEY.md §8e exchange X3); gn_apply_kernel Chan-merges the R records in rank order (every
+// rank computes bit-identical statistics) and normalises its strip, optionally writing into a
+// halo-padded buffer (out_img_stride > hw*C).  Deterministic: fixed slab partition, fixed merge
+// order, the last-arriving CTA of an image does the slab merge (no float atomics).
+constexpr int GNX_THREADS = 512;
+constexpr int GNX_MAX_SLABS = 256;
+
+struct GnSplitParams {
+  const __nv_bfloat16* x0; int c0;
+  const __nv_bfloat16* x1; int c1;
+  int nimg, hw, groups, V, L, slabs, pps;
+  float* partial;            // [nimg][slabs][groups][2]
+  float* stats;              // [nimg][groups][2]  (mean, M2) of the local strip
+  unsigned int* counters;    // [nimg], zero on entry, zero on exit
+  // apply side
+  const float* stats_all;    // [R][nimg][groups][2]
+  int R;
+  float eps;
+  const float* gamma; const float* beta;
+  int apply_silu;
+  __nv_bfloat16* out;
+  long long out_img_stride;  // elements between images of `out`
+};
+
+__device__ __forceinline__ void chan_merge(float& n_a, float& mean_a, float& m2_a, float n_b,
+                                           float mean_b, float m2_b) {
+  const float n_ab = n_a + n_b;
+  const float delta = mean_b - mean_a;
+  mean_a += delta * (n_b / n_ab);
+  m2_a += m2_b + delta * delta * (n_a * n_b / n_ab);
+  n_a = n_ab;
+}
+
+__global__ void __launch_bounds__(GNX_THREADS) gn_stats_kernel(const GnSplitParams p) {
+  __shared__ float s_sum[GNX_THREADS * 8];
+  __shared__ float s_sq[GNX_THREADS * 8];
+  __shared__ int s_last;
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const int img = blockIdx.y, slab = blockIdx.x;
+  const int p_begin = slab * p.pps;
+  const int p_end = min(p.hw, p_begin + p.pps);
+  const int v = threadIdx.x % p.V, l = threadIdx.x / p.V;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (l < p.L) {
+    const long long base = (long long)img * p.hw;
+#pragma unroll 4
+    for (int px = p_begin + l; px < p_end; px += p.L) {
+      const uint4 u = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v);
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(ww[j]);
+        s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+        s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_sum[l * C + v * 8 + j] = s[j]; s_sq[l * C + v * 8 + j] = q[j]; }
+  }
+  __syncthreads();
+  float* part = p.partial + ((size_t)img * p.slabs + slab) * p.groups * 2;
+  const int nvals = p.L * cpg;
+  for (int g = warp; g < p.groups; g += GNX_THREADS / 32) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = lane; i < nvals; i += 32) {
+      const int ll = i / cpg, c = g * cpg + (i - ll * cpg);
+      ts += s_sum[ll * C + c];
+      tq += s_sq[ll * C + c];
+    }
+    ts = warp_sum(ts);
+    tq = warp_sum(tq);
+    if (lane == 0) {
+      const float cnt = (float)(p_end - p_begin) * (float)cpg;
+      const float mean = cnt > 0.f ? ts / cnt : 0.f;
+      part[g * 2 + 0] = mean;
+      part[g * 2 + 1] = fmaxf(tq - ts * mean, 0.f);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.counters[img], 1u) == (unsigned)(p.slabs - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < p.groups) {
+    const int g = threadIdx.x;
+    float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+    for (int sidx = 0; sidx < p.slabs; ++sidx) {
+      const int pb = sidx * p.pps, pe = min(p.hw, pb + p.pps);
+      if (pe <= pb) continue;
+      const float2 mm = __ldcg(reinterpret_cast<const float2*>(
+          p.partial + (((size_t)img * p.slabs + sidx) * p.groups + g) * 2));
+      chan_merge(n_a, mean_a, m2_a, (float)(pe - pb) * (float)cpg, mm.x, mm.y);
+    }
+    p.stats[((size_t)img * p.groups + g) * 2 + 0] = mean_a;
+    p.stats[((size_t)img * p.groups + g) * 2 + 1] = m2_a;
+  }
+  if (threadIdx.x == 0) p.counters[img] = 0u;
+}
+
+__global__ void __launch_bounds__(GNX_THREADS) gn_apply_kernel(const GnSplitParams p) {
+  __shared__ float s_mean[GN_MAX_GROUPS];
+  __shared__ float s_rstd[GN_MAX_GROUPS];
+  const int C = p.c0 + p.c1;
+  const int cpg = C / p.groups;
+  const int img = blockIdx.y, slab = blockIdx.x;
+  const int p_begin = slab * p.pps;
+  const int p_end = min(p.hw, p_begin + p.pps);
+  const int v = threadIdx.x % p.V, l = threadIdx.x / p.V;
+  if (threadIdx.x < p.groups) {
+    const int g = threadIdx.x;
+    const float n_r = (float)p.hw * (float)cpg;       // equal strips: same count on every rank
+    float n_a = 0.f, mean_a = 0.f, m2_a = 0.f;
+    for (int r = 0; r < p.R; ++r) {
+      const float2 mm = __ldg(reinterpret_cast<const float2*>(
+          p.stats_all + (((size_t)r * p.nimg + img) * p.groups + g) * 2));
+      chan_merge(n_a, mean_a, m2_a, n_r, mm.x, mm.y);
+    }
+    s_mean[g] = mean_a;
+    s_rstd[g] = rsqrtf(m2_a / n_a + p.eps);
+  }
+  __syncthreads();
+  if (l >= p.L) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = min(v * 8 + j, C - 1);
+    const int g = c / cpg;
+    sc[j] = s_rstd[g] * __ldg(p.gamma + c);
+    sh[j] = __ldg(p.beta + c) - s_mean[g] * sc[j];
+  }
+  const long long base = (long long)img * p.hw;
+  __nv_bfloat16* outv = p.out + (long long)img * p.out_img_stride + v * 8;
+#pragma unroll 4
+  for (int px = p_begin + l; px < p_end; px += p.L) {
+    const uint4 u = ld_vec8(p.x0, p.c0, p.x1, p.c1, base + px, v);
+    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(ww[j]);
+      f.x = f.x * sc[2 * j] + sh[2 * j];
+      f.y = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+      if (p.apply_silu) { f.x = silu_f(f.x); f.y = silu_f(f.y); }
+      o[j] = pack_bf16x2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(outv + (long long)px * C) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+static int gn_split_setup(GnSplitParams& p, const void* x0, int c0, const void* x1, int c1, int nimg,
+                          int hw, int groups) {
+  const int C = c0 + c1;
+  DL_CHECK_ARG(x0 && nimg > 0 && hw > 0, "groupnorm(split): bad args");
+  DL_CHECK_ARG(c0 % 8 == 0 && c1 % 8 == 0 && C > 0, "groupnorm(split): channels must be multiples of 8");
+  DL_CHECK_ARG(c1 == 0 || x1, "groupnorm(split): c1>0 needs x1");
+  DL_CHECK_ARG(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0,
+               "groupnorm(split): bad groups=%d for C=%d", groups, C);
+  DL_CHECK_ARG(C / 8 <= GNX_THREADS, "groupnorm(split): C=%d too wide", C);
+  memset(&p, 0, sizeof(p));
+  p.x0 = reinterpret_cast<const __nv_bfloat16*>(x0); p.c0 = c0;
+  p.x1 = reinterpret_cast<const __nv_bfloat16*>(x1); p.c1 = c1;
+  p.nimg = nimg; p.hw = hw; p.groups = groups;
+  p.V = C / 8;
+  p.L = GNX_THREADS / p.V;
+  // slab partition: a function of (hw, C) only => batch-invariant statistics
+  int slabs = (int)(((long long)hw * C * 2 + (1 << 17) - 1) >> 17);      // ~128 KB of input per CTA
+  const int max_slabs = (hw + p.L - 1) / p.L;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs > GNX_MAX_SLABS) slabs = GNX_MAX_SLABS;
+  if (slabs < 1) slabs = 1;
+  p.pps = (hw + slabs - 1) / slabs;
+  p.slabs = (hw + p.pps - 1) / p.pps;
+  return 0;
+}
+
 }  // namespace dl
+
+extern "C" size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups) {
+  return 4096 + (size_t)(nimg > 0 ? nimg : 1) * dl::GNX_MAX_SLABS * (groups > 0 ? groups : 32) * 2 * sizeof(float);
+}
+
+extern "C" int dl_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int nimg, int hw,
+                                  int groups, float* stats, void* workspace, void* stream_) {
+  using namespace dl;
+  GnSplitParams p;
+  if (int rc = gn_split_setup(p, x0, c0, x1, c1, nimg, hw, groups)) return rc;
+  DL_CHECK_ARG(stats && workspace, "groupnorm_stats: null pointer");
+  DL_CHECK_ARG(nimg <= 1024, "groupnorm_stats: nimg=%d exceeds 1024", nimg);
+  p.stats = stats;
+  p.counters = reinterpret_cast<unsigned int*>(workspace);
+  p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 4096);
+  gn_stats_kernel<<<dim3(p.slabs, nimg), GNX_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("groupnorm_stats");
+}
+
+extern "C" int dl_groupnorm_apply(const void* x0, int c0, const void* x1, int c1, int nimg, int hw,
+                                  int groups, float eps, const float* gamma, const float* beta,
+                                  int apply_silu, const float* stats_all, int nranks, void* out,
+                                  long long out_img_stride, void* stream_) {
+  using namespace dl;
+  GnSplitParams p;
+  if (int rc = gn_split_setup(p, x0, c0, x1, c1, nimg, hw, groups)) return rc;
+  DL_CHECK_ARG(stats_all && out && gamma && beta && nranks >= 1, "groupnorm_apply: bad args");
+  const long long dense = (long long)hw * (c0 + c1);
+  DL_CHECK_ARG(out_img_stride == 0 || (out_img_stride >= dense && out_img_stride % 8 == 0),
+               "groupnorm_apply: bad out_img_stride");
+  p.stats_all = stats_all; p.R = nranks; p.eps = eps; p.gamma = gamma; p.beta = beta;
+  p.apply_silu = apply_silu;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.out_img_stride = out_img_stride > 0 ? out_img_stride : dense;
+  gn_apply_kernel<<<dim3(p.slabs, nimg), GNX_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
+  return check_launch("groupnorm_apply");
+}
 
 extern "C" size_t dl_groupnorm_workspace_bytes(int nimg, int groups) {
   (void)nimg;

@@ -26,17 +26,47 @@ from .weights import Packed, pack_unet, pack_vae_decoder
 BF16 = torch.bfloat16
 
 
-class _Ctx:
-    """Per-forward scratch: device, batch and the GroupNorm workspace."""
+_gnx_ws = {}
 
-    def __init__(self, device, batch):
+
+class Padded:
+    """A row strip with one halo row above and below: t is bf16 [B, h+2, W, C]; rows 1..h are
+    the strip, rows 0 / h+1 the neighbours' boundary rows (zeros at the image border)."""
+    __slots__ = ("t",)
+
+    def __init__(self, t):
+        self.t = t
+
+
+class _Ctx:
+    """Per-forward scratch: device, batch, the GroupNorm workspace and (patch-parallel runs)
+    the strip communicator.  comm=None is the single-GPU path."""
+
+    def __init__(self, device, batch, comm=None):
         self.device = device
         self.batch = batch
+        self.comm = comm
         self.gn_ws = torch.empty(lib.groupnorm_workspace_bytes(batch, 32), device=device,
                                  dtype=torch.uint8)
+        if comm is not None:
+            # zero-initialised once per (device, batch): the stats kernel leaves its counters zero
+            import threading
+            key = (str(device), batch, threading.get_ident())    # virtual ranks (threads) never share it
+            if key not in _gnx_ws:
+                _gnx_ws[key] = torch.zeros(lib.groupnorm_split_workspace_bytes(batch, 64), device=device,
+                                           dtype=torch.uint8)
+            self.gnx_ws = _gnx_ws[key]
 
     def empty(self, *shape, dtype=BF16):
         return torch.empty(*shape, device=self.device, dtype=dtype)
+
+    def pad_rows(self, x):
+        """Strip [B,h,W,C] -> Padded copy with exchanged halo rows."""
+        B, H, W, C = x.shape
+        t = self.empty(B, H + 2, W, C)
+        t[:, 1:H + 1].copy_(x)
+        self.comm.halo_exchange(t)
+        return Padded(t)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -44,11 +74,18 @@ class _Ctx:
 # ------------------------------------------------------------------------------------------------
 def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=lib.EPI_BF16,
             out=None, ldo=None):
+    """x: dense [B,H,W,C] (zero padding all round) or a Padded strip (halo rows supplied)."""
+    halo = isinstance(x, Padded)
+    if halo:
+        x = x.t
     B, H, W, _ = x.shape
+    if halo:
+        H -= 2
     if out is None:
-        out = ctx.empty(B, H, W, n_out)
+        out = ctx.empty(B, H, W, n_out, dtype=torch.float32 if mode == lib.EPI_F32 else BF16)
     lib.igemm(x, w, out, nimg=B, h=H, w=W, taps=9, n=n_out, a1=x1, bias=b, rowadd=rowadd,
-              residual=residual, mode=mode, ldo=ldo)
+              residual=residual, mode=mode, ldo=ldo, in_rows=H + 2 if halo else 0,
+              in_row0=1 if halo else 0)
     return out
 
 
@@ -66,23 +103,39 @@ def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, ou
     return out
 
 
-def groupnorm(ctx, x, gw, gb, *, eps, silu, x1=None, groups=32):
+def groupnorm(ctx, x, gw, gb, *, eps, silu, x1=None, groups=32, halo=False):
+    """halo=True (feeds a conv3x3): under a strip communicator the result is a Padded strip."""
     B, H, W, C0 = x.shape
     C = C0 + (x1.shape[-1] if x1 is not None else 0)
-    out = ctx.empty(B, H, W, C)
-    lib.groupnorm(x, out, gw, gb, ctx.gn_ws, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu, x1=x1)
-    return out
+    if ctx.comm is None:
+        out = ctx.empty(B, H, W, C)
+        lib.groupnorm(x, out, gw, gb, ctx.gn_ws, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu, x1=x1)
+        return out
+    # row strips: local (mean, M2) -> all-gather over the patch group -> merge + normalise
+    stats = ctx.empty(B, groups, 2, dtype=torch.float32)
+    lib.groupnorm_stats(x, stats, ctx.gnx_ws, nimg=B, hw=H * W, groups=groups, x1=x1)
+    stats_all = ctx.comm.all_gather(stats)
+    if not halo:
+        out = ctx.empty(B, H, W, C)
+        lib.groupnorm_apply(x, out, gw, gb, stats_all, nimg=B, hw=H * W, groups=groups, eps=eps,
+                            silu=silu, x1=x1)
+        return out
+    t = ctx.empty(B, H + 2, W, C)
+    lib.groupnorm_apply(x, t[:, 1:], gw, gb, stats_all, nimg=B, hw=H * W, groups=groups, eps=eps,
+                        silu=silu, x1=x1, out_img_stride=(H + 2) * W * C)
+    ctx.comm.halo_exchange(t)
+    return Padded(t)
 
 
 def resnet(ctx, x, p: Packed, *, temb=None, x1=None, eps=1e-5, groups=32):
     """ResnetBlock2D on x (or on the channel concat [x | x1])."""
     cout = p["cout"]
-    h = groupnorm(ctx, x, p["norm1_w"], p["norm1_b"], eps=eps, silu=True, x1=x1, groups=groups)
+    h = groupnorm(ctx, x, p["norm1_w"], p["norm1_b"], eps=eps, silu=True, x1=x1, groups=groups, halo=True)
     rowadd = None
     if temb is not None:
         rowadd = temb[:, p["temb_off"]:p["temb_off"] + cout]     # view: ld = temb_total
     h = conv3x3(ctx, h, p["conv1_w"], p["conv1_b"], cout, rowadd=rowadd)
-    h = groupnorm(ctx, h, p["norm2_w"], p["norm2_b"], eps=eps, silu=True, groups=groups)
+    h = groupnorm(ctx, h, p["norm2_w"], p["norm2_b"], eps=eps, silu=True, groups=groups, halo=True)
     if p["sc_w"] is not None:
         sc = linear(ctx, x, p["sc_w"], p["sc_b"], cout, x1=x1)
     else:
@@ -98,10 +151,21 @@ def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
     # --- self attention
     n1 = ctx.empty(B * S, C)
     lib.layernorm(h, n1, q["ln1_w"], q["ln1_b"])
-    qkv = linear(ctx, n1, q["qkv_w"], q["qkv_b"], 3 * hs)
     a = ctx.empty(B * S, C)
-    lib.attention(qkv, qkv[:, hs:], qkv[:, 2 * hs:], a, batch=B, sq=S, skv=S, heads=heads, d=d,
-                  dh_stride=hstride, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale, v_ones=True)
+    if ctx.comm is None:
+        qkv = linear(ctx, n1, q["qkv_w"], q["qkv_b"], 3 * hs)
+        lib.attention(qkv, qkv[:, hs:], qkv[:, 2 * hs:], a, batch=B, sq=S, skv=S, heads=heads, d=d,
+                      dh_stride=hstride, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale, v_ones=True)
+    else:
+        # row strips: queries stay local, keys/values of every strip are all-gathered
+        # (SURVEY.md §8e exchange X2); key order = rank order = image row order
+        qs = linear(ctx, n1, q["qkv_w"][:hs], None, hs)
+        kvl = linear(ctx, n1, q["qkv_w"][hs:], q["qkv_b"][hs:], 2 * hs)
+        kvf = ctx.comm.gather_rows(kvl.view(B, S, 2 * hs))            # [B, R*S, 2hs]
+        skv_all = kvf.shape[1]
+        kvf = kvf.view(B * skv_all, 2 * hs)
+        lib.attention(qs, kvf, kvf[:, hs:], a, batch=B, sq=S, skv=skv_all, heads=heads, d=d,
+                      dh_stride=hstride, ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale, v_ones=True)
     h = linear(ctx, a, q["o1_w"], q["o1_b"], C, residual=h)
     # --- cross attention (K/V precomputed once per request)
     n2 = ctx.empty(B * S, C)
@@ -135,7 +199,11 @@ def transformer(ctx, x, p: Packed, kvs, *, groups=32):
 def downsample(ctx, x, p: Packed):
     B, H, W, C = x.shape
     cols = ctx.empty(B * (H // 2) * (W // 2), 9 * C)
-    lib.im2col_s2(x, cols, nimg=B, h=H, w=W)
+    if ctx.comm is None:
+        lib.im2col_s2(x, cols, nimg=B, h=H, w=W)
+    else:
+        xp = ctx.pad_rows(x)
+        lib.im2col_s2_halo(xp.t, cols, nimg=B, in_rows=H + 2, in_row0=1, h=H, w=W)
     out = linear(ctx, cols, p["w"], p["b"], C)
     return out.view(B, H // 2, W // 2, C)
 
@@ -146,11 +214,14 @@ def upsample(ctx, x, p: Packed):
     B, H, W, C = x.shape
     out = ctx.empty(B, 2 * H, 2 * W, C)
     strides = (2 * C, 4 * W * C, 4 * H * W * C)            # x, row, image strides of a phase view
+    src, halo = x, {}
+    if ctx.comm is not None:
+        src, halo = ctx.pad_rows(x).t, dict(in_rows=H + 2, in_row0=1)
     for ph in range(4):
         a, b = ph >> 1, ph & 1
         view = out[:, a:, b:, :]                            # base pointer of phase (a, b)
-        lib.igemm(x, p["w"][ph], view, nimg=B, h=H, w=W, taps=4, n=C, bias=p["b"], tap_phase=ph,
-                  ldo=C, out_strides=strides)
+        lib.igemm(src, p["w"][ph], view, nimg=B, h=H, w=W, taps=4, n=C, bias=p["b"], tap_phase=ph,
+                  ldo=C, out_strides=strides, **halo)
     return out
 
 
@@ -221,20 +292,39 @@ class UNetB200:
 
     @torch.no_grad()
     def forward(self, latents_nhwc: torch.Tensor, temb: torch.Tensor, kvs: List[List[torch.Tensor]],
-                eps_out: Optional[torch.Tensor] = None, repeat: int = 1) -> torch.Tensor:
+                eps_out: Optional[torch.Tensor] = None, repeat: int = 1, comm=None) -> torch.Tensor:
         """latents_nhwc fp32 [b,h,w,4] -> noise_pred fp32 [b*repeat,h,w,4].  repeat=2 is the
         classifier-free-guidance doubled batch `cat([latents]*2)`: the same latents are packed
-        twice, temb / kvs carry the [uncond, cond] halves."""
+        twice, temb / kvs carry the [uncond, cond] halves.
+
+        comm (patch parallel): this rank computes rows
+        [rank*h/R, (rank+1)*h/R) of every image and returns that strip [b*repeat, h/R, w, 4];
+        latents_nhwc is still the full latent (it is tiny and every rank holds it)."""
         P = self.P
         b0, H, W, Cin = latents_nhwc.shape
         B = b0 * repeat
-        ctx = _Ctx(self.device, B)
+        ctx = _Ctx(self.device, B, comm)
         g = self.groups
         ch = self.cfg.block_out_channels
         kv_it = iter(kvs)
-        xin = ctx.empty(B, H, W, 64)
-        for r in range(repeat):
-            lib.pack_latent(latents_nhwc, xin[r * b0:(r + 1) * b0], cin=Cin)
+        if comm is None:
+            xin = ctx.empty(B, H, W, 64)
+            for r in range(repeat):
+                lib.pack_latent(latents_nhwc, xin[r * b0:(r + 1) * b0], cin=Cin)
+        else:
+            n_lv = len(ch)
+            if H % (comm.world << (n_lv - 1)):
+                raise RuntimeError(f"patch parallel: {H} latent rows do not split into {comm.world} strips "
+                                   f"of a multiple of {1 << (n_lv - 1)} rows")
+            hl = H // comm.world
+            r0 = comm.rank * hl
+            lo, hi = max(r0 - 1, 0), min(r0 + hl + 1, H)      # strip + halo rows inside the image
+            xp = torch.zeros(B, hl + 2, W, 64, device=self.device, dtype=BF16)
+            for r in range(repeat):
+                for i in range(b0):
+                    lib.pack_latent(latents_nhwc[i, lo:hi], xp[r * b0 + i, lo - (r0 - 1):hi - (r0 - 1)], cin=Cin)
+            xin = Padded(xp)
+            H = hl
         h = conv3x3(ctx, xin, P["conv_in_w"], P["conv_in_b"], ch[0])
         skips = [h]
         for blk in P["down"]:
@@ -256,7 +346,7 @@ class UNetB200:
                     h = transformer(ctx, h, blk["attns"][j], next(kv_it), groups=g)
             if blk["up"] is not None:
                 h = upsample(ctx, h, blk["up"])
-        hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-5, silu=True, groups=g)
+        hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-5, silu=True, groups=g, halo=True)
         if eps_out is None:
             eps_out = torch.empty(B, H, W, Cin, device=self.device, dtype=torch.float32)
         conv3x3(ctx, hn, P["conv_out_w"], P["conv_out_b"], Cin, mode=lib.EPI_F32, out=eps_out, ldo=Cin)

@@ -23,7 +23,8 @@ EXPORTS = [
     "dl_debug_attention_trace",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
-    "dl_cfg_combine",
+    "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
+    "dl_im2col_s2_halo",
 ]
 
 
@@ -38,6 +39,7 @@ class IgemmDesc(C.Structure):
         ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_longlong), ("identity", C.c_void_p),
         ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
+        ("in_rows", C.c_int), ("in_row0", C.c_int),
     ]
 
 
@@ -72,6 +74,15 @@ def load() -> C.CDLL:
             lib.dl_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_groupnorm_split_workspace_bytes.restype = C.c_size_t
+            lib.dl_groupnorm_split_workspace_bytes.argtypes = [C.c_int, C.c_int]
+            lib.dl_groupnorm_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_groupnorm_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]
+            lib.dl_im2col_s2_halo.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_void_p, C.c_void_p]
             lib.dl_layernorm.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
             lib.dl_attention.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
@@ -205,7 +216,7 @@ def require_cuda():
 # ------------------------------------------------------------------------------------------------
 def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
           a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
-          mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None):
+          mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None, in_rows=0, in_row0=0):
     """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
     nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
     d = IgemmDesc()
@@ -230,6 +241,7 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
     d.identity = identity_matrix(residual.device).data_ptr() if residual is not None else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
+    d.in_rows, d.in_row0 = in_rows, in_row0
     with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1),
                 tag=f"M={nimg * h * w} ({nimg}x{h}x{w}) N={n} K={taps}x{d.c0 + d.c1} mode={mode}"
                     f"{' +res' if residual is not None else ''}"):
@@ -249,6 +261,34 @@ def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5,
                                    gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
                                    workspace.data_ptr(), _stream()), "groupnorm")
     _count(2)
+
+
+def groupnorm_split_workspace_bytes(nimg, groups=32):
+    return load().dl_groupnorm_split_workspace_bytes(nimg, groups)
+
+
+def groupnorm_stats(x0, stats, workspace, *, nimg, hw, groups=32, x1=None):
+    """stats fp32 [nimg, groups, 2] <- (mean, M2) of this rank's strip."""
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    with _timed("groupnorm_stats", 0.0, 2.0 * nimg * hw * (c0 + c1), tag=f"n={nimg} hw={hw} C={c0}+{c1}"):
+        _check(load().dl_groupnorm_stats(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups,
+                                         stats.data_ptr(), workspace.data_ptr(), _stream()),
+               "groupnorm_stats")
+    _count()
+
+
+def groupnorm_apply(x0, out, gamma, beta, stats_all, *, nimg, hw, groups=32, eps=1e-5, silu=True,
+                    x1=None, out_img_stride=0):
+    """stats_all fp32 [nranks, nimg, groups, 2]; out may be the interior of a halo-padded buffer."""
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    with _timed("groupnorm_apply", 0.0, 4.0 * nimg * hw * (c0 + c1), tag=f"n={nimg} hw={hw} C={c0}+{c1}"):
+        _check(load().dl_groupnorm_apply(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
+                                         gamma.data_ptr(), beta.data_ptr(), int(silu),
+                                         stats_all.data_ptr(), stats_all.shape[0], out.data_ptr(),
+                                         out_img_stride, _stream()), "groupnorm_apply")
+    _count()
 
 
 def layernorm(x, out, gamma, beta, eps=1e-5):
@@ -295,6 +335,13 @@ def im2col_s2(x, cols, *, nimg, h, w):
     with _timed("im2col_s2", 0.0, 2.0 * x.numel() + 2.0 * cols.numel()):
         _check(load().dl_im2col_s2(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
                "im2col_s2")
+    _count()
+
+
+def im2col_s2_halo(x, cols, *, nimg, in_rows, in_row0, h, w):
+    with _timed("im2col_s2", 0.0, 2.0 * x.numel() + 2.0 * cols.numel()):
+        _check(load().dl_im2col_s2_halo(x.data_ptr(), nimg, in_rows, in_row0, h, w, x.shape[-1],
+                                        cols.data_ptr(), _stream()), "im2col_s2_halo")
     _count()
 
 
