@@ -142,10 +142,12 @@ def run_pipeline_sdxl(unet: OracleUNet, vae: OracleVAEDecoder, prompt_embeds: to
         w_emb = guidance_scale_embedding(torch.full((B,), guidance_scale - 1.0), unet.cfg.time_cond_proj_dim)
     latents = latents * sched.init_noise_sigma
     if record is not None:
-        record.update(timesteps=timesteps.clone(), noise_pred=[], latents=[])
+        record.update(timesteps=timesteps.clone(), noise_pred=[], noise_pred_raw=[], latents=[])
     for i, t in enumerate(timesteps):
         x = torch.cat([latents] * 2, 0) if do_cfg else latents
         eps = unet(x, t, ctx, w_emb, text_embeds=pooled, time_ids=tids)
+        if record is not None:
+            record["noise_pred_raw"].append(eps.clone())       # the UNet output, before guidance
         if do_cfg:
             e_u, e_t = eps.chunk(2)
             eps = e_u + guidance_scale * (e_t - e_u)

@@ -535,6 +535,8 @@ class LCMPipelineB200:
                 eps2 = self.unet.forward(x, tembs[i], kvs, repeat=2)
                 eps = torch.empty_like(x)
                 lib.cfg_combine(eps2[:B], eps2[B:], cfg_scale, eps)
+                if record is not None:      # the UNet output before guidance: [uncond; text]
+                    record.setdefault("noise_pred_raw", []).append(eps2.permute(0, 3, 1, 2).clone())
             x_next = torch.empty_like(x)
             lib.lcm_step(eps, x, noise[i] if sched.has_noise(i) else None, x_next, den, sched.coeffs(i))
             if record is not None:

@@ -169,8 +169,12 @@ class PatchParallelDenoiser:
         self.world = world_comm
         self._strip_factory = strip_comm_factory
         self._strip_comms = {}
+        self._graphs = {}
+        self.force_split = False     # tests: run the strip kernels even for a one-strip group
 
-    def _strip_comm(self, topo: Topology) -> StripComm:
+    def _strip_comm(self, topo: Topology) -> Optional[StripComm]:
+        if topo.strips == 1 and not self.force_split:
+            return None                              # whole image on this rank: the fused single-GPU kernels
         if topo.cfg_ways == 1:
             return self.world
         key = topo.cfg_index
@@ -179,15 +183,9 @@ class PatchParallelDenoiser:
         return self._strip_comms[key]
 
     @torch.no_grad()
-    def denoise(self, prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps: int,
-                guidance_scale: float, record: dict = None):
-        """Inputs as `LCMPipelineB200.generate` (host or device, identical on every rank).
-        Returns the final latents NHWC fp32 (identical on every rank)."""
-        from . import lib
-        from .scheduler import LCMSchedule
+    def _prepare(self, prompt_embeds, pooled_embeds, B, H, W, guidance_scale):
+        """Per-rank conditioning of this rank's role -> (topo, comm, pe, add, w_emb, repeat, cfg_scale)."""
         pipe = self.pipe
-        dev = pipe.device
-        B, C, H, W = latents_nchw.shape
         cfg_scale = pipe.cfg_scale_for(guidance_scale)
         topo = Topology(self.world.world, self.world.rank, cfg_scale is not None)
         comm = self._strip_comm(topo)
@@ -202,47 +200,122 @@ class PatchParallelDenoiser:
                 add = (add[0][sl], add[1][sl]) if add is not None else None
             else:
                 repeat = 2
-        with torch.cuda.device(dev):
-            pe = pe_all.to(dev, torch.bfloat16).contiguous()
-            if add is not None:
-                add = (add[0].to(dev), add[1].to(dev))
-            we = w_emb.to(dev) if w_emb is not None else None
-            sched = LCMSchedule(steps)
-            kvs = pipe.unet.encode_context(pe)
-            aug = pipe.unet.addition_embedding(*add) if add is not None else None
-            tembs = pipe.unet.time_embeddings(sched.timesteps, B * repeat, we, aug)
-            x = torch.empty(B, H, W, C, device=dev, dtype=torch.float32)
-            lib.nchw_to_nhwc_f32(latents_nchw.to(dev, torch.float32).contiguous(), x)
-            noise = None
-            if steps > 1:
-                nz = step_noise_nchw.to(dev, torch.float32).contiguous()
-                noise = torch.empty(steps - 1, B, H, W, C, device=dev, dtype=torch.float32)
-                lib.nchw_to_nhwc_f32(nz[:steps - 1].reshape((steps - 1) * B, C, H, W),
-                                     noise.view((steps - 1) * B, H, W, C))
-            den = torch.empty_like(x)
-            for i in range(steps):
-                strip = pipe.unet.forward(x, tembs[i], kvs, repeat=repeat, comm=comm)
-                e_u, e_t = assemble_eps(self.world.all_gather(strip), topo, B)
-                if e_t is not None:
-                    eps = torch.empty_like(x)
-                    lib.cfg_combine(e_u.contiguous(), e_t.contiguous(), cfg_scale, eps)
-                else:
-                    eps = e_u.contiguous()
-                x_next = torch.empty_like(x)
-                lib.lcm_step(eps, x, noise[i] if sched.has_noise(i) else None, x_next, den, sched.coeffs(i))
+        return topo, comm, pe_all, add, w_emb, repeat, cfg_scale
+
+    @torch.no_grad()
+    def _loop(self, topo, comm, pe, add, we, repeat, cfg_scale, lat_nchw, noise_nchw, steps, record=None):
+        """Device tensors in, final latents NHWC out; no host sync (graph-capturable)."""
+        from . import lib
+        from .scheduler import LCMSchedule
+        pipe = self.pipe
+        dev = pipe.device
+        B, C, H, W = lat_nchw.shape
+        sched = LCMSchedule(steps)
+        kvs = pipe.unet.encode_context(pe)
+        aug = pipe.unet.addition_embedding(*add) if add is not None else None
+        tembs = pipe.unet.time_embeddings(sched.timesteps, B * repeat, we, aug)
+        x = torch.empty(B, H, W, C, device=dev, dtype=torch.float32)
+        lib.nchw_to_nhwc_f32(lat_nchw, x)
+        noise = None
+        if steps > 1:
+            noise = torch.empty(steps - 1, B, H, W, C, device=dev, dtype=torch.float32)
+            lib.nchw_to_nhwc_f32(noise_nchw[:steps - 1].reshape((steps - 1) * B, C, H, W),
+                                 noise.view((steps - 1) * B, H, W, C))
+        den = torch.empty_like(x)
+        for i in range(steps):
+            strip = pipe.unet.forward(x, tembs[i], kvs, repeat=repeat, comm=comm)
+            e_u, e_t = assemble_eps(self.world.all_gather(strip), topo, B)
+            if e_t is not None:
+                eps = torch.empty_like(x)
+                lib.cfg_combine(e_u.contiguous(), e_t.contiguous(), cfg_scale, eps)
                 if record is not None:
-                    record.setdefault("noise_pred", []).append(eps.permute(0, 3, 1, 2).clone())
-                    record.setdefault("latents", []).append(x_next.permute(0, 3, 1, 2).clone())
-                x = x_next
+                    record.setdefault("noise_pred_raw", []).append(
+                        torch.cat([e_u, e_t], 0).permute(0, 3, 1, 2).clone())
+            else:
+                eps = e_u.contiguous()
+            x_next = torch.empty_like(x)
+            lib.lcm_step(eps, x, noise[i] if sched.has_noise(i) else None, x_next, den, sched.coeffs(i))
+            if record is not None:
+                record.setdefault("noise_pred", []).append(eps.permute(0, 3, 1, 2).clone())
+                record.setdefault("latents", []).append(x_next.permute(0, 3, 1, 2).clone())
+            x = x_next
         return x
 
     @torch.no_grad()
+    def denoise(self, prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps: int,
+                guidance_scale: float, record: dict = None, use_graph: bool = False):
+        """Inputs as `LCMPipelineB200.generate` (host or device, identical on every rank).
+        Returns the final latents NHWC fp32 (identical on every rank).  use_graph: the whole
+        loop — kernels and collectives — is captured once per geometry and replayed (one image
+        at N ranks is otherwise bound by launch latency, not by the GPUs)."""
+        pipe = self.pipe
+        dev = pipe.device
+        B, C, H, W = latents_nchw.shape
+        topo, comm, pe_all, add, w_emb, repeat, cfg_scale = self._prepare(
+            prompt_embeds, pooled_embeds, B, H, W, guidance_scale)
+        with torch.cuda.device(dev):
+            pe = pe_all.to(dev, torch.bfloat16).contiguous()
+            if add is not None:
+                add = (add[0].to(dev).contiguous(), add[1].to(dev).contiguous())
+            we = w_emb.to(dev) if w_emb is not None else None
+            lat0 = latents_nchw.to(dev, torch.float32).contiguous()
+            nz = step_noise_nchw.to(dev, torch.float32).contiguous() if steps > 1 else None
+            if not use_graph or record is not None:
+                return self._loop(topo, comm, pe, add, we, repeat, cfg_scale, lat0, nz, steps, record)
+            key = (B, H, W, steps, cfg_scale)
+            g = self._graphs.get(key)
+            if g is None:
+                st = dict(pe=pe.clone(), add=None if add is None else (add[0].clone(), add[1].clone()),
+                          we=None if we is None else we.clone(), lat=lat0.clone(),
+                          nz=None if nz is None else nz.clone())
+                args = lambda: (topo, comm, st["pe"], st["add"], st["we"], repeat, cfg_scale, st["lat"],  # noqa: E731
+                                st["nz"], steps)
+                s = torch.cuda.Stream(device=dev)
+                s.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(s):
+                    self._loop(*args())                           # warm-up (lazy init, NCCL channels)
+                torch.cuda.current_stream(dev).wait_stream(s)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    st["out"] = self._loop(*args())
+                st["graph"] = graph
+                g = self._graphs[key] = st
+            g["pe"].copy_(pe)
+            if add is not None:
+                g["add"][0].copy_(add[0]); g["add"][1].copy_(add[1])
+            if we is not None:
+                g["we"].copy_(we)
+            g["lat"].copy_(lat0)
+            if nz is not None:
+                g["nz"].copy_(nz)
+            g["graph"].replay()
+            return g["out"]
+
+    @torch.no_grad()
     def generate(self, prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps: int,
-                 guidance_scale: float, record: dict = None, decode_rank: int = 0):
+                 guidance_scale: float, record: dict = None, decode_rank: int = 0, use_graph: bool = False):
         """-> u8 images [B,H,W,3] on `decode_rank` (None elsewhere)."""
         lat = self.denoise(prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps,
-                           guidance_scale, record)
+                           guidance_scale, record, use_graph=use_graph)
         if self.world.rank != decode_rank:
             return None
         with torch.cuda.device(self.pipe.device):
             return self.pipe.vae.decode(lat)
+
+
+def dist_denoiser(pipe, cfg: bool = True) -> "PatchParallelDenoiser":
+    """PatchParallelDenoiser over the default torch.distributed world: builds the two strip
+    groups of the CFG halves (every rank must call this: `new_group` is collective)."""
+    import torch.distributed as dist
+    world = DistComm()
+    groups = {}
+    if cfg and world.world % 2 == 0 and world.world > 2:
+        topo = Topology(world.world, world.rank, True)
+        for c in range(2):
+            groups[c] = dist.new_group(topo.strip_ranks(c))
+
+    def factory(topo: Topology):
+        return DistComm(groups[topo.cfg_index])
+
+    return PatchParallelDenoiser(pipe, world, factory)

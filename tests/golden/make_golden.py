@@ -57,11 +57,13 @@ def sdxl(size=512, steps=3, gs=7.5):
     img = run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, steps, gs, size, size, record=rec)
     np.savez_compressed(os.path.join(HERE, f"sdxl_{size}_{steps}step_cfg.npz"),
                         noise_pred=torch.stack(rec["noise_pred"]).numpy().astype(np.float32),
+                        noise_pred_raw=torch.stack(rec["noise_pred_raw"]).numpy().astype(np.float32),
                         latents=torch.stack(rec["latents"]).numpy().astype(np.float32), image=img)
 
 
 if __name__ == "__main__":
-    tiny()
+    if len(sys.argv) == 1 or "--tiny" in sys.argv:
+        tiny()
     if "--full" in sys.argv:
         full()
     if "--sdxl" in sys.argv:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from test_pipeline_gpu import NOISE_PRED_TOL, PSNR_MIN_DB, max_rel_err, psnr_u8
+from test_pipeline_gpu import PSNR_MIN_DB, assert_unet_outputs, guided_tol, max_rel_err, psnr_u8
 
 pytestmark = pytest.mark.gpu
 
@@ -40,9 +40,13 @@ def test_tiny_sdxl_pipeline_parity(gs):
     img = pipe.generate(pe, lat, noise, steps, gs, record=rec_c, pooled_embeds=pooled)
     torch.cuda.synchronize()
     errs = [max_rel_err(c.cpu(), o) for c, o in zip(rec_c["noise_pred"], rec_o["noise_pred"])]
+    raw = [max_rel_err(c.cpu(), o) for c, o in zip(rec_c.get("noise_pred_raw", rec_c["noise_pred"]),
+                                                   rec_o["noise_pred_raw"])]
     p = psnr_u8(img.cpu().numpy(), ref)
-    print(f"tiny SDXL gs={gs}: noise_pred max-rel-err per step {['%.2e' % e for e in errs]}  PSNR {p:.1f} dB")
-    assert max(errs) <= NOISE_PRED_TOL, errs
+    print(f"tiny SDXL gs={gs}: UNet output max-rel-err per step {['%.2e' % e for e in raw]}  guided "
+          f"{['%.2e' % e for e in errs]}  PSNR {p:.1f} dB")
+    assert_unet_outputs(raw, gs)
+    assert max(errs) <= guided_tol(gs), errs
     assert p >= PSNR_MIN_DB, p
     # graph replay == eager, byte for byte
     img2 = pipe.generate(pe, lat, noise, steps, gs, use_graph=True, pooled_embeds=pooled).clone()
@@ -67,7 +71,10 @@ def test_sdxl_base_512_3step_cfg_vs_committed_golden():
     img = pipe.generate(pe, lat, noise, 3, 7.5, record=rec, pooled_embeds=pooled)
     torch.cuda.synchronize()
     errs = [max_rel_err(rec["noise_pred"][i].cpu(), torch.from_numpy(g["noise_pred"][i])) for i in range(3)]
+    raw = [max_rel_err(rec["noise_pred_raw"][i].cpu(), torch.from_numpy(g["noise_pred_raw"][i])) for i in range(3)]
     p = psnr_u8(img.cpu().numpy(), g["image"])
-    print(f"SDXL 512^2 CFG noise_pred max-rel-err per step: {['%.2e' % e for e in errs]}  image PSNR {p:.1f} dB")
-    assert max(errs) <= NOISE_PRED_TOL, errs
+    print(f"SDXL 512^2 CFG: UNet output max-rel-err per step {['%.2e' % e for e in raw]}  guided "
+          f"{['%.2e' % e for e in errs]}  image PSNR {p:.1f} dB")
+    assert_unet_outputs(raw, 7.5)
+    assert max(errs) <= guided_tol(7.5), errs
     assert p >= PSNR_MIN_DB, p

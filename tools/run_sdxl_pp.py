@@ -1,0 +1,119 @@
+"""BASELINE config C5 on N GPUs: SDXL-base arch (random-init), 1024x1024, CFG 7.5, LCM scheduler,
+ONE image sharded over the ranks (CFG halves x row strips, NCCL over NVLink).
+  torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/run_sdxl_pp.py \
+      [--size 1024] [--steps 30] [--iters 3] [--no-graph] [--check]
+Rank 0 prints one JSON line: seconds per image (denoise loop, max over ranks, CUDA events), the
+same loop un-sharded on rank 0 for the speed-up, and (--check) the max-rel-err of the sharded
+noise predictions against the un-sharded engine on the same inputs."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--gs", type=float, default=7.5)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="tiny SDXL topology (debug)")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    from dreamlab_b200 import synthetic as syn
+    from dreamlab_b200.engine import LCMPipelineB200
+    from dreamlab_b200 import patch_parallel as pp
+    if a.tiny:
+        from oracle.unet import UNetConfig
+        from oracle.vae import VAEConfig
+        ucfg, vcfg = UNetConfig.tiny_sdxl(), VAEConfig.tiny()
+    else:
+        ucfg, vcfg = syn.sdxl_unet_cfg(), syn.sdxl_vae_cfg()
+    t0 = time.time()
+    pipe = LCMPipelineB200(syn.random_state_dict(syn.unet_shapes(ucfg), 0, torch.bfloat16), ucfg,
+                           syn.random_state_dict(syn.vae_decoder_shapes(vcfg), 1, torch.bfloat16), vcfg, dev)
+    load_s = time.time() - t0
+    pdim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+    pe, lat, noise = syn.synthetic_inputs(1, a.size, a.size, a.steps, ctx_dim=ucfg.cross_attention_dim)
+    pooled = torch.randn(1, pdim, generator=torch.Generator().manual_seed(2))
+    pe, lat, noise, pooled = pe.to(dev), lat.to(dev), noise.to(dev), pooled.to(dev)
+    den = pp.dist_denoiser(pipe) if world > 1 else pp.PatchParallelDenoiser(pipe, pp.SingleComm())
+    out = {"config": f"SDXL-base arch (random-init) {a.size}x{a.size}, {a.steps} LCM steps, CFG {a.gs}, "
+                     f"1 image over {world} GPU(s)", "n_gpus": world, "load_s": round(load_s, 1)}
+
+    def timed(fn, iters):
+        ts = []
+        for _ in range(iters):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t))
+        return sorted(ts)[len(ts) // 2]
+
+    if a.check:
+        rec, rec1 = {}, {}
+        den.denoise(pe, pooled, lat, noise, min(a.steps, 2), a.gs, record=rec)
+        torch.cuda.synchronize()
+        if rank == 0:
+            pipe.generate(pe, lat, noise[:1] if a.steps > 1 else noise, min(a.steps, 2), a.gs, record=rec1,
+                          pooled_embeds=pooled)
+            torch.cuda.synchronize()
+            key = "noise_pred_raw" if a.gs > 1 else "noise_pred"
+            out["check_max_rel_err_vs_unsharded"] = [
+                float((x - y).abs().max() / y.abs().max()) for x, y in zip(rec[key], rec1[key])]
+    use_graph = not a.no_graph
+    try:
+        den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph)      # warm-up / capture
+        torch.cuda.synchronize()
+    except Exception as e:      # noqa: BLE001
+        if not use_graph:
+            raise
+        out["graph_error"] = repr(e)[:300]
+        use_graph = False
+        den.denoise(pe, pooled, lat, noise, a.steps, a.gs)
+        torch.cuda.synchronize()
+    ms = timed(lambda: den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph), a.iters)
+    out.update(ms_per_image_denoise=round(ms, 2), cuda_graph=use_graph,
+               ms_per_unet_step=round(ms / a.steps, 3))
+    if world > 1:
+        ms_e = timed(lambda: den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=False), 1)
+        out["ms_per_image_denoise_eager"] = round(ms_e, 2)
+    if rank == 0:
+        # un-sharded reference timing of the same loop on one GPU (graph replay)
+        g1 = lambda: pipe.generate(pe, lat, noise, a.steps, a.gs, pooled_embeds=pooled, use_graph=True)  # noqa: E731
+        g1(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(max(a.iters, 1)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g1(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out["ms_per_image_1gpu_incl_vae"] = round(sorted(ts)[len(ts) // 2], 2)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
