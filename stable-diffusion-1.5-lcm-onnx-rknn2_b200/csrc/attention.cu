@@ -50,7 +50,12 @@ struct AttnParams {
 // kOnes: V carries a ones column, the PV MMA accumulates the softmax denominator (product path).
 // A compile-time flag: as a runtime branch the unused row-sum code still cost ~190 predicated
 // instructions per thread and tile in the exp loop.
-template <bool kOnes, bool kBf16Exp>
+// KS / KT: compile-time QK^T K-steps and key tile (0 = runtime values from the params).  The MMA
+// warp shares its scheduler with four busy softmax warps, so every instruction it issues costs
+// several cycles: with KS/KT known the issue paths are straight runs of UMMAs with folded
+// descriptor offsets instead of 12 / 8 predicated slots with runtime address math (measured
+// ~660 / ~330 cycles per tile for the S / PV issue before).
+template <bool kOnes, bool kBf16Exp, int KS, int KT>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -132,18 +137,21 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     const uint32_t hi_k = umma_desc_hi_sw128(1024);                       // K-major operands
     const uint32_t sq_addr = smem_u32(sQ);
     const uint32_t skv_addr = smem_u32(sKV);
+    const int n_ks = KS > 0 ? KS : p.ksteps;
+    const int kchunk16 = (KT > 0 ? KT * 128 : kchunk) >> 4;
+    const uint32_t q_lo = umma_desc_lo(sq_addr);
     auto issue_s = [&](int j, int stage) {
       const uint32_t sk_addr = skv_addr + (uint32_t)(stage * kv_bytes);
       const int sb = j % p.sbuf;
       const uint32_t d_tmem = tmem_base + (uint32_t)(sb * p.kt);
-      const uint32_t q_lo = umma_desc_lo(sq_addr), k_lo = umma_desc_lo(sk_addr);
+      const uint32_t k_lo = umma_desc_lo(sk_addr);
       if (issuer) {
 #pragma unroll
-        for (int ks = 0; ks < 12; ++ks) {               // d <= 192: at most 12 K-steps of 16
-          if (ks < p.ksteps) {
+        for (int ks = 0; ks < (KS > 0 ? KS : 12); ++ks) {   // d <= 192: at most 12 K-steps of 16
+          if (ks < n_ks) {
             // next 64-wide chunk every 4 steps (16 KB = 1024 x 16 B), 32 B = 2 units inside a row
             const uint32_t qoff = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
-            const uint32_t koff = (uint32_t)((ks >> 2) * (kchunk >> 4) + (ks & 3) * 2);
+            const uint32_t koff = (uint32_t)((ks >> 2) * kchunk16 + (ks & 3) * 2);
             umma_ss_lohi(d_tmem, q_lo + qoff, k_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
           }
         }
@@ -152,50 +160,68 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       __syncwarp();
     };
     const bool prefetch_s = (p.sbuf == 2 && p.stages >= 2);
+    // single S buffer but >= 2 smem stages: PV_j and S_{j+1} go out as ONE burst of UMMAs right
+    // after p_ready (K_{j+1} is waited for, and every operand computed, before that wait) — the
+    // in-order tensor pipe keeps S_{j+1} behind PV_j, which reads the P it would overwrite
+    const bool fused = (p.sbuf == 1 && p.stages >= 2);
     mbar_wait(q_full, 0);
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
     int stage = 0;
     uint32_t phase = 0;
+    const int pv_steps = KT > 0 ? KT / 16 : (p.kt >> 4);
+    const uint32_t o_tmem = tmem_base + o_col;
     for (int j = 0; j < n_tiles; ++j) {
       int nstage = stage + 1;
       uint32_t nphase = phase;
       if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
-      if (prefetch_s && j + 1 < n_tiles) {
+      const bool more = j + 1 < n_tiles;
+      if (prefetch_s && more) {
         mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
         issue_s(j + 1, nstage);
       }
       const int sb = j % p.sbuf;
+      // operands of PV_j (and of S_{j+1} in the fused burst), ready before the wait
+      const uint32_t sv_addr = skv_addr + (uint32_t)(stage * kv_bytes + k_bytes);
+      const uint32_t p_tmem = tmem_base + (uint32_t)(sb * p.kt);
+      // V is the MN-major B operand: LBO = stride between 64-wide d chunks, SBO = 8-key groups
+      const uint32_t v_lo = umma_desc_lo(sv_addr, (uint32_t)(KT > 0 ? KT * 128 : kchunk));
+      const uint32_t nk_lo = umma_desc_lo(skv_addr + (uint32_t)(nstage * kv_bytes));
+      const uint32_t acc0 = j > 0 ? 1u : 0u;
+      if (fused && more) mbar_wait(&kv_full[nstage], nphase);
       mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 && issuer;
       if (tr) p.trace[j * 16 + 0] = clock64();
-      {
-        const uint32_t sv_addr = skv_addr + (uint32_t)(stage * kv_bytes + k_bytes);
-        const uint32_t p_tmem = tmem_base + (uint32_t)(sb * p.kt);
-        const uint32_t o_tmem = tmem_base + o_col;
-        // V is the MN-major B operand: LBO = stride between 64-wide d chunks, SBO = 8-key groups
-        const uint32_t v_lo = umma_desc_lo(sv_addr, (uint32_t)kchunk);
-        const int pv_steps = p.kt >> 4;
-        if (issuer) {
+      if (issuer) {
 #pragma unroll
-          for (int ks = 0; ks < AT_TILE / 16; ++ks) {
-            // 16 keys = two 8-row swizzle atoms = 2048 B (+128 in 16-byte units); P advances 8
-            // packed columns
-            if (ks < pv_steps)
-              umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
-                           (j > 0 || ks > 0) ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[stage]);
-          umma_commit(pv_done);
+        for (int ks = 0; ks < (KT > 0 ? KT / 16 : AT_TILE / 16); ++ks) {
+          // 16 keys = two 8-row swizzle atoms = 2048 B (+128 in 16-byte units); P advances 8
+          // packed columns
+          if (ks < pv_steps)
+            umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
+                         ks > 0 ? 1u : acc0);
         }
-        __syncwarp();
-        if (tr) p.trace[j * 16 + 1] = clock64();
+        umma_commit(&kv_empty[stage]);
+        umma_commit(pv_done);
+        if (fused && more) {
+#pragma unroll
+          for (int ks = 0; ks < (KS > 0 ? KS : 12); ++ks) {
+            if (ks < n_ks) {
+              const uint32_t qoff = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
+              const uint32_t koff = (uint32_t)((ks >> 2) * kchunk16 + (ks & 3) * 2);
+              umma_ss_lohi(p_tmem, q_lo + qoff, nk_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&s_full[sb]);
+        }
       }
-      if (!prefetch_s && j + 1 < n_tiles) {
-        // in-order tensor pipe: S_{j+1} may overwrite the S/P buffer right behind PV_j
+      __syncwarp();
+      if (tr) p.trace[j * 16 + 1] = clock64();
+      if (!prefetch_s && !fused && more) {
+        // one smem stage: K_{j+1} can only land after PV_j released the stage
         mbar_wait(&kv_full[nstage], nphase);
         tc_fence_after();
         if (tr) p.trace[j * 16 + 2] = clock64();
@@ -320,10 +346,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       tmem_st_wait();
       if (tr) p.trace[j * 16 + 9] = clock64();
       if (j > 0) {
-        // O must hold PV_{j-1} before it is rescaled and before PV_j accumulates on top
-        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
+        // O must hold PV_{j-1} before it is rescaled.  PV_j accumulating on top needs no wait
+        // here: the tensor pipe is in-order and S_j (already consumed above) was issued after
+        // PV_{j-1}, so pv_done's phase j-1 has completed whenever s_full's phase j has — the
+        // wait below can only ever spin when the rescale is actually taken.
         if (__any_sync(0xffffffffu, corr != 1.0f)) {
+          mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
 #pragma unroll 1
           for (int c = ch * 16; c < p.dv; c += 32) {
             uint32_t oo[16];
@@ -491,17 +520,34 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024 - 3072);   // minus the static xch buffer
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               227 * 1024 - 3072);
+    const int lim = 227 * 1024 - 3072;                          // minus the static xch buffer
+    cudaError_t e = cudaSuccess;
+#define DL_ATTN_ATTR(...)                                                                       \
+  if (e == cudaSuccess)                                                                         \
+    e = cudaFuncSetAttribute(attn_tc_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)
+    DL_ATTN_ATTR(true, true, 0, 0);
+    DL_ATTN_ATTR(true, true, 3, 128);
+    DL_ATTN_ATTR(true, true, 4, 128);
+    DL_ATTN_ATTR(true, true, 5, 128);
+    DL_ATTN_ATTR(false, false, 0, 0);
+#undef DL_ATTN_ATTR
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
   dim3 grid((sq + AT_TILE - 1) / AT_TILE, heads, batch);
-  if (p.l_col >= 0) attn_tc_kernel<true, true><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
-  else attn_tc_kernel<false, false><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  static int generic = -1;
+  if (generic < 0) { const char* e = getenv("DL_ATTN_GENERIC"); generic = e ? atoi(e) : 0; }
+  if (p.l_col < 0) {
+    attn_tc_kernel<false, false, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 3 && !generic) {       // SD1.5 head dim 40
+    attn_tc_kernel<true, true, 3, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 4 && !generic) {       // SDXL head dim 64
+    attn_tc_kernel<true, true, 4, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 5 && !generic) {       // SD1.5 head dim 80
+    attn_tc_kernel<true, true, 5, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else {
+    attn_tc_kernel<true, true, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  }
   return check_launch("attention(tc)");
 }
 

@@ -16,6 +16,13 @@ import torch
 import torch.distributed as dist
 
 
+def log(msg):
+    print(f"[rank {os.environ.get('RANK', 0)} +{time.time() - T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+T0 = time.time()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", type=int, default=1024)
@@ -33,6 +40,9 @@ def main():
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
+        log("process group up")
+        dist.barrier()
+        log("first barrier done")
     from dreamlab_b200 import synthetic as syn
     from dreamlab_b200.engine import LCMPipelineB200
     from dreamlab_b200 import patch_parallel as pp
@@ -46,6 +56,7 @@ def main():
     pipe = LCMPipelineB200(syn.random_state_dict(syn.unet_shapes(ucfg), 0, torch.bfloat16), ucfg,
                            syn.random_state_dict(syn.vae_decoder_shapes(vcfg), 1, torch.bfloat16), vcfg, dev)
     load_s = time.time() - t0
+    log(f"weights packed in {load_s:.1f}s")
     pdim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
     pe, lat, noise = syn.synthetic_inputs(1, a.size, a.size, a.steps, ctx_dim=ucfg.cross_attention_dim)
     pooled = torch.randn(1, pdim, generator=torch.Generator().manual_seed(2))
@@ -75,6 +86,7 @@ def main():
         rec, rec1 = {}, {}
         den.denoise(pe, pooled, lat, noise, min(a.steps, 2), a.gs, record=rec)
         torch.cuda.synchronize()
+        log("eager sharded check pass done")
         if rank == 0:
             pipe.generate(pe, lat, noise[:1] if a.steps > 1 else noise, min(a.steps, 2), a.gs, record=rec1,
                           pooled_embeds=pooled)
@@ -83,6 +95,7 @@ def main():
             out["check_max_rel_err_vs_unsharded"] = [
                 float((x - y).abs().max() / y.abs().max()) for x, y in zip(rec[key], rec1[key])]
     use_graph = not a.no_graph
+    log(f"warm-up / capture (graph={use_graph})")
     try:
         den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph)      # warm-up / capture
         torch.cuda.synchronize()
@@ -93,12 +106,14 @@ def main():
         use_graph = False
         den.denoise(pe, pooled, lat, noise, a.steps, a.gs)
         torch.cuda.synchronize()
+    log("capture done, timing")
     ms = timed(lambda: den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph), a.iters)
     out.update(ms_per_image_denoise=round(ms, 2), cuda_graph=use_graph,
                ms_per_unet_step=round(ms / a.steps, 3))
     if world > 1:
         ms_e = timed(lambda: den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=False), 1)
         out["ms_per_image_denoise_eager"] = round(ms_e, 2)
+    log("sharded timing done")
     if rank == 0:
         # un-sharded reference timing of the same loop on one GPU (graph replay)
         g1 = lambda: pipe.generate(pe, lat, noise, a.steps, a.gs, pooled_embeds=pooled, use_graph=True)  # noqa: E731
@@ -112,7 +127,12 @@ def main():
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # destroy_process_group() hangs after NCCL collectives were captured into CUDA graphs
+    # (communicator teardown waits on the captured work); the process is done, so leave.
+    os._exit(0)
 
 
 if __name__ == "__main__":
