@@ -42,6 +42,8 @@ struct AttnParams {
   int kt;            // keys per KV tile (128 / 96 / 64): S columns, PV depth, TMA box rows
   int stages;        // K/V smem ring depth
   int sbuf;          // S/P TMEM buffers (2: S_{j+1} overlaps softmax_j; 1: two CTAs per SM)
+  int pcol;          // > 0: P lives in its own TMEM columns [pcol, pcol + kt/2) instead of over S, so
+                     // S_{j+1} is computed while the softmax warps are still in the exp pass of tile j
   int tmem_cols;
   long long* trace;  // debug: per-tile clock stamps of CTA (0,0,0), or NULL
   float scale_log2;
@@ -71,27 +73,37 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   uint8_t* sKV = smem + q_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * kv_bytes);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // [stages]
-  uint64_t* kv_empty = kv_full + p.stages; // [stages]
-  uint64_t* s_full = kv_empty + p.stages;  // [2]
+  // K and V slots are tracked separately: K_j is dead as soon as S_j is computed, V_j only after
+  // PV_j — with a shared barrier K_{j+1} could not be fetched before PV_{j-1} had retired
+  uint64_t* k_full = bars + 1;             // [stages]
+  uint64_t* k_empty = k_full + p.stages;   // [stages]
+  uint64_t* v_full = k_empty + p.stages;   // [stages]
+  uint64_t* v_empty = v_full + p.stages;   // [stages]
+  uint64_t* s_full = v_empty + p.stages;   // [2]
   uint64_t* p_ready = s_full + 2;          // [2]
   uint64_t* pv_done = p_ready + 2;         // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_taken = pv_done + 1;         // 1: the softmax warps hold S_j in registers (pcol mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_taken + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * AT_TILE;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.skv + p.kt - 1) / p.kt;
-  const uint32_t o_col = (uint32_t)(p.sbuf * p.kt);      // TMEM: S/P buffers first, then O
+  // TMEM: S/P buffers first (then the separate P buffer), then O
+  const uint32_t o_col = (uint32_t)(p.pcol > 0 ? p.pcol + (p.kt >> 1) : p.sbuf * p.kt);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < p.stages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 8); }
     mbar_init(pv_done, 1);
+    mbar_init(s_taken, 8);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
@@ -112,22 +124,32 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         tma_load_2d(sQ + c * AT_CHUNK_BYTES, &p.tmQ, q_full, col0 + c * 64, b * p.sq + q0);
     }
     __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      uint8_t* sK = sKV + (size_t)stage * kv_bytes;
-      uint8_t* sV = sK + k_bytes;
-      const int row = b * p.skv + j * p.kt;
+    // K runs one tile ahead of V: K_{j+1}'s slot is free as soon as S_{j-1} is computed, while
+    // V_j's slot waits for PV_{j-2} — in a strictly alternating order every K load queued
+    // behind a V wait and arrived a whole tile late (TMA latency under load ~3k cycles)
+    auto load_k = [&](int t) {
+      const int st = t % p.stages;
+      mbar_wait(&k_empty[st], (uint32_t)(((t / p.stages) & 1) ^ 1));
       if (issuer) {
-        mbar_expect_tx(&kv_full[stage], (uint32_t)kv_bytes);
+        uint8_t* sK = sKV + (size_t)st * kv_bytes;
+        mbar_expect_tx(&k_full[st], (uint32_t)k_bytes);
         for (int c = 0; c < p.nchunk_qk; ++c)
-          tma_load_2d(sK + c * kchunk, &p.tmK, &kv_full[stage], col0 + c * 64, row);
-        for (int c = 0; c < p.nchunk_v; ++c)
-          tma_load_2d(sV + c * kchunk, &p.tmV, &kv_full[stage], col0 + c * 64, row);
+          tma_load_2d(sK + c * kchunk, &p.tmK, &k_full[st], col0 + c * 64, b * p.skv + t * p.kt);
       }
       __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    };
+    load_k(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) load_k(j + 1);
+      const int st = j % p.stages;
+      mbar_wait(&v_empty[st], (uint32_t)(((j / p.stages) & 1) ^ 1));
+      if (issuer) {
+        uint8_t* sV = sKV + (size_t)st * kv_bytes + k_bytes;
+        mbar_expect_tx(&v_full[st], (uint32_t)v_bytes);
+        for (int c = 0; c < p.nchunk_v; ++c)
+          tma_load_2d(sV + c * kchunk, &p.tmV, &v_full[st], col0 + c * 64, b * p.skv + j * p.kt);
+      }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
@@ -155,6 +177,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             umma_ss_lohi(d_tmem, q_lo + qoff, k_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
           }
         }
+        umma_commit(&k_empty[stage]);
         umma_commit(&s_full[sb]);
       }
       __syncwarp();
@@ -163,9 +186,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // single S buffer but >= 2 smem stages: PV_j and S_{j+1} go out as ONE burst of UMMAs right
     // after p_ready (K_{j+1} is waited for, and every operand computed, before that wait) — the
     // in-order tensor pipe keeps S_{j+1} behind PV_j, which reads the P it would overwrite
-    const bool fused = (p.sbuf == 1 && p.stages >= 2);
+    const bool fused = (p.sbuf == 1 && p.stages >= 2 && p.pcol == 0);
+    // separate P buffer: S_{j+1} goes out as soon as the softmax warps have S_j in registers
+    // (s_taken), i.e. it runs under their exp pass; PV_j follows once P_j is written.  The pipe
+    // is in order, so PV_j (reads P, V_j) and S_{j+2} (writes S) never race.
+    const bool split = (p.pcol > 0);
     mbar_wait(q_full, 0);
-    mbar_wait(&kv_full[0], 0);
+    mbar_wait(&k_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
     int stage = 0;
@@ -178,19 +205,31 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       if (nstage == p.stages) { nstage = 0; nphase ^= 1; }
       const bool more = j + 1 < n_tiles;
       if (prefetch_s && more) {
-        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(&k_full[nstage], nphase);
         tc_fence_after();
         issue_s(j + 1, nstage);
       }
       const int sb = j % p.sbuf;
+      if (split && more) {
+        const bool tr2 = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 && issuer;
+        mbar_wait(&k_full[nstage], nphase);
+        if (tr2) p.trace[j * 16 + 12] = clock64();
+        mbar_wait(s_taken, (uint32_t)(j & 1));
+        tc_fence_after();
+        if (tr2) p.trace[j * 16 + 2] = clock64();
+        issue_s(j + 1, nstage);
+        if (tr2) p.trace[j * 16 + 3] = clock64();
+      }
       // operands of PV_j (and of S_{j+1} in the fused burst), ready before the wait
       const uint32_t sv_addr = skv_addr + (uint32_t)(stage * kv_bytes + k_bytes);
-      const uint32_t p_tmem = tmem_base + (uint32_t)(sb * p.kt);
+      const uint32_t p_tmem = tmem_base + (uint32_t)(split ? p.pcol : sb * p.kt);
+      const uint32_t s_next = tmem_base + (uint32_t)(sb * p.kt);
       // V is the MN-major B operand: LBO = stride between 64-wide d chunks, SBO = 8-key groups
       const uint32_t v_lo = umma_desc_lo(sv_addr, (uint32_t)(KT > 0 ? KT * 128 : kchunk));
       const uint32_t nk_lo = umma_desc_lo(skv_addr + (uint32_t)(nstage * kv_bytes));
       const uint32_t acc0 = j > 0 ? 1u : 0u;
-      if (fused && more) mbar_wait(&kv_full[nstage], nphase);
+      if (fused && more) mbar_wait(&k_full[nstage], nphase);
+      mbar_wait(&v_full[stage], phase);
       mbar_wait(&p_ready[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 && issuer;
@@ -204,7 +243,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
                          ks > 0 ? 1u : acc0);
         }
-        umma_commit(&kv_empty[stage]);
+        umma_commit(&v_empty[stage]);
         umma_commit(pv_done);
         if (fused && more) {
 #pragma unroll
@@ -212,17 +251,18 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
             if (ks < n_ks) {
               const uint32_t qoff = (uint32_t)((ks >> 2) * (AT_CHUNK_BYTES >> 4) + (ks & 3) * 2);
               const uint32_t koff = (uint32_t)((ks >> 2) * kchunk16 + (ks & 3) * 2);
-              umma_ss_lohi(p_tmem, q_lo + qoff, nk_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
+              umma_ss_lohi(s_next, q_lo + qoff, nk_lo + koff, hi_k, idesc_s, ks > 0 ? 1u : 0u);
             }
           }
+          umma_commit(&k_empty[nstage]);
           umma_commit(&s_full[sb]);
         }
       }
       __syncwarp();
       if (tr) p.trace[j * 16 + 1] = clock64();
-      if (!prefetch_s && !fused && more) {
+      if (!prefetch_s && !fused && !split && more) {
         // one smem stage: K_{j+1} can only land after PV_j released the stage
-        mbar_wait(&kv_full[nstage], nphase);
+        mbar_wait(&k_full[nstage], nphase);
         tc_fence_after();
         if (tr) p.trace[j * 16 + 2] = clock64();
         issue_s(j + 1, nstage);
@@ -244,6 +284,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j % p.sbuf;
       const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(sb * p.kt);
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 && threadIdx.x == 64)
+        p.trace[j * 16 + 11] = clock64();
       mbar_wait(&s_full[sb], (uint32_t)((j / p.sbuf) & 1));
       tc_fence_after();
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 &&
@@ -268,6 +310,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
         for (int i = 0; i < 32; ++i) sb32[i] = 0xff800000u;     // -inf: ignored by max, exp2 -> 0
       }
       tmem_ld_wait();
+      if (p.pcol > 0) {
+        // S_j is in registers: the tensor core may overwrite the S columns with S_{j+1}
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_taken);
+      }
       if (tr) p.trace[j * 16 + 5] = clock64();
       if (need_mask) {
 #pragma unroll
@@ -302,6 +350,13 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const float m_new = (m_tile > m_run + 8.0f) ? m_tile : m_run;
       const float corr = fast_exp2(m_run - m_new);
       float lsum0 = 0.f, lsum1 = 0.f;
+      const uint32_t pw_tmem = p.pcol > 0 ? tmem_base + lane_off + (uint32_t)p.pcol : s_tmem;
+      if (p.pcol > 0 && j > 0) {
+        // PV_{j-1} reads the P buffer this pass is about to overwrite (long finished in practice:
+        // it was issued a whole softmax pass ago)
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (c == 1 && hc == 32) break;
@@ -332,12 +387,12 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           pk[i] = *reinterpret_cast<const uint32_t*>(&pb);
         }
         if (c == 0 || hc == 64) {
-          tmem_st16(s_tmem + (uint32_t)(ch * (hc >> 1) + c * 16), pk);
+          tmem_st16(pw_tmem + (uint32_t)(ch * (hc >> 1) + c * 16), pk);
         } else if (hc == 48) {                                  // 16 more columns -> 8 packed
           uint32_t p8[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) p8[i] = pk[i];
-          tmem_st8(s_tmem + (uint32_t)(ch * (hc >> 1) + 16), p8);
+          tmem_st8(pw_tmem + (uint32_t)(ch * (hc >> 1) + 16), p8);
         }
       }
       l_run = l_run * corr + (lsum0 + lsum1);
@@ -479,6 +534,11 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
     if (q_bytes + kv_bytes + overhead <= half_budget) {
       p.kt = 128; p.sbuf = 1; p.tmem_cols = 256;
       p.stages = (half_budget - overhead - q_bytes) / kv_bytes;
+      // S (128) + separate P (64) + O (dv) within the CTA's 256 columns, and K_{j+1} needs its
+      // own smem stage next to V_j: SD1.5 head dim 40 (dv = 48)
+      // (DL_ATTN_MODE=5 only: measured 3 % slower than the fused PV_j + S_{j+1} burst on B200 —
+      // with both CTAs free-running their exp passes collide on the MUFU pipe)
+      if (128 + 64 + p.dv <= 256 && p.stages >= 2 && force_mode == 5) p.pcol = 128;
       done = true;
     }
   }

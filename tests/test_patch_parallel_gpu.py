@@ -133,21 +133,27 @@ def test_split_groupnorm_matches_fused():
 
 
 def test_halo_conv_matches_dense_rows():
-    """conv3x3 over a halo-padded strip == the same rows of the dense conv (bit-exact: same MMA
-    order, the halo rows just replace TMA zero fill)."""
+    """conv3x3 over a halo-padded strip == the same rows of the dense conv: bit-exact when both
+    take the same kernel path (>= 16 rows: halo-patch mode, the exchanged rows just replace TMA
+    zero fill), within bf16 rounding when the short strip falls back to the per-tap loader (the
+    fp32 accumulation order over taps / channel chunks differs)."""
     from dreamlab_b200 import lib
     torch.manual_seed(0)
-    B, H, W, C, N = 2, 16, 32, 128, 192
+    B, H, W, C, N = 2, 32, 32, 128, 192
     x = torch.randn(B, H, W, C, device="cuda").bfloat16()
     w = (torch.randn(N, 9 * C, device="cuda") * 0.05).bfloat16()
     bias = torch.randn(N, device="cuda")
     dense = torch.empty(B, H, W, N, device="cuda", dtype=torch.bfloat16)
     lib.igemm(x, w, dense, nimg=B, h=H, w=W, taps=9, n=N, bias=bias)
-    for r0, hl in [(0, 8), (8, 8), (4, 4)]:
+    for r0, hl in [(0, 16), (16, 16), (8, 16), (4, 8), (28, 4)]:
         pad = torch.zeros(B, hl + 2, W, C, device="cuda", dtype=torch.bfloat16)
         lo, hi = max(r0 - 1, 0), min(r0 + hl + 1, H)
         pad[:, lo - (r0 - 1):hi - (r0 - 1)] = x[:, lo:hi]
         out = torch.empty(B, hl, W, N, device="cuda", dtype=torch.bfloat16)
         lib.igemm(pad, w, out, nimg=B, h=hl, w=W, taps=9, n=N, bias=bias, in_rows=hl + 2, in_row0=1)
         torch.cuda.synchronize()
-        assert torch.equal(out, dense[:, r0:r0 + hl]), (r0, hl)
+        ref = dense[:, r0:r0 + hl]
+        if hl >= 16:
+            assert torch.equal(out, ref), (r0, hl)
+        else:
+            assert torch.allclose(out.float(), ref.float(), rtol=2e-2, atol=2e-2), (r0, hl)

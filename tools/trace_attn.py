@@ -20,8 +20,8 @@ run(); torch.cuda.synchronize()
 l.dl_debug_attention_trace(None)
 t = tr.cpu().view(16, 16)
 t0 = int(t[0, 4])
-names = ["mma:p_ready", "mma:pv_issued", "mma:kv_full", "mma:s_issued", "sm:s_full", "sm:ld_done", "sm:max_done",
-         "sm:bar_done", "sm:exp_issued", "sm:st_done", "sm:arrived"]
+names = ["mma:p_ready", "mma:pv_issued", "mma:s_taken", "mma:s_issued", "sm:s_full", "sm:ld_done", "sm:max_done",
+         "sm:bar_done", "sm:exp_issued", "sm:st_done", "sm:arrived", "sm:looptop", "mma:k_full"]
 print("tile " + " ".join(f"{n:>13s}" for n in names))
 for j in range(12):
-    print(f"{j:4d} " + " ".join(f"{int(t[j, k]) - t0:13d}" for k in range(11)))
+    print(f"{j:4d} " + " ".join(f"{int(t[j, k]) - t0:13d}" for k in range(13)))
