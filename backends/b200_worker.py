@@ -121,8 +121,10 @@ class B200Worker(PipelineWorker):
 
         ucfg_json, unet_sd = _load_component(os.path.join(path, "unet"))
         vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
+        # vae_tiling: the reference switches `pipe.vae.enable_tiling()` on unconditionally
+        # (`backends/cuda_worker.py:91`, `:390`)
         self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
-                                    vae_cfg_from_json(vcfg_json), self.device)
+                                    vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True)
         self._text = self._make_text_encoder(path)
         print(f"[{self._tag}] worker {worker_id} loaded: {model_name} on {self.device} "
               f"(noise dtype={dtype_str}, compute bf16)")

@@ -238,12 +238,24 @@ def run_b200(args):
         pipe.generate(gr.pe, gr.lat, gr.noise, nsteps, 1.0, use_graph=False)
         prof = lib.profile_end()
         sustained, burst, hbm, src = peaks()
-        ig = prof.get("igemm", {"ms": 0.0, "flops": 0.0, "n": 0})
+        ig = prof.get("igemm", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         tot_ms = sum(v["ms"] for v in prof.values())
         ach = ig["flops"] / (ig["ms"] / 1e3) / 1e12 if ig["ms"] > 0 else 0.0
+        # DRAM bytes per igemm launch from the committed ncu capture of this very workload
+        # (profiles/r01_ncu_dram_per_kernel_v7.*: dram__bytes_read.sum + dram__bytes_write.sum over
+        # the 922 igemm launches of one pass); only quoted for the configuration it was taken on
+        traffic, traffic_src = None, None
+        tj = os.path.join(ROOT, "profiles", "r01_ncu_dram_per_kernel_v7.json")
+        if os.path.exists(tj) and (B, size, nsteps) == (16, 512, 4):
+            k = json.load(open(tj)).get("dl::igemm_kernel")
+            if k and k["launches"] == ig["n"]:
+                traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
+                traffic_src = "profiles/r01_ncu_dram_per_kernel_v7.json (ncu, same workload, per launch)"
         roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear)",
                 "achieved": ach, "peak": sustained, "peak_kind": f"bf16 dense sustained, {src}",
-                "unit": "TFLOP/s", "frac": ach / sustained, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / sustained, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)",
+                "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": ig["bytes"] / ig["n"] if ig["n"] else None,
                 "launches": ig["n"], "share_of_step": ig["ms"] / tot_ms if tot_ms else None,
                 "step_achieved_tflops": GFLOP_IMAGE * value / world / 1e3,
                 "step_frac": GFLOP_IMAGE * value / world / 1e3 / sustained,

@@ -164,6 +164,18 @@ typedef struct dl_lcm_coeffs {
 int dl_lcm_step(const float* eps, const float* x, const float* noise, float* x_next,
                 float* denoised, long long n, const dl_lcm_coeffs* coeffs /* host */, void* stream);
 
+/* ---- tiled VAE decode (`pipe.vae.enable_tiling()`, reference `backends/cuda_worker.py:91`;
+ * diffusers AutoencoderKL.tiled_decode / blend_v / blend_h) -----------------
+ * Tiles are fp32 NHWC images.  dl_tile_blend blends the first `extent` rows (vertical = 1) or
+ * columns (vertical = 0) of tile b, in place, with the last `extent` rows / columns of tile a:
+ *   b[k] = a[len_a - extent + k] * (1 - k/extent) + b[k] * (k/extent).
+ * dl_image_crop_u8 writes the top-left crop_h x crop_w window of a tile into a u8 NHWC canvas
+ * (dst already points at the window's first pixel) with the VaeImageProcessor denormalise.     */
+int dl_tile_blend(const float* a, float* b, int nimg, int ha, int wa, int hb, int wb, int c,
+                  int extent, int vertical, void* stream);
+int dl_image_crop_u8(const float* src, int nimg, int hs, int ws, int c, int crop_h, int crop_w,
+                     void* dst_u8, long long dst_row_stride, long long dst_img_stride, void* stream);
+
 /* ---- classifier-free guidance combine of the doubled-batch UNet output (SDXL path:
  * `StableDiffusionXLPipeline.__call__` behind reference `backends/cuda_worker.py:532`) --------
  * out = eps_uncond + guidance_scale * (eps_text - eps_uncond), fp32, un-contracted            */

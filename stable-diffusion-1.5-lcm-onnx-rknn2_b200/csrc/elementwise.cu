@@ -227,6 +227,53 @@ __global__ void lcm_step_kernel(const float4* __restrict__ eps, const float4* __
   }
 }
 
+// ---- tiled VAE decode (diffusers AutoencoderKL.tiled_decode: blend_v / blend_h / crop) ----------
+// b[n, y, x, :] (y < extent) = a[n, ha - extent + y, x, :] * (1 - y/extent) + b[n, y, x, :] * (y/extent)
+// vertical = 1 blends along rows (a above b, same width), 0 along columns (a left of b, same height)
+__global__ void tile_blend_kernel(const float* __restrict__ a, float* __restrict__ b, int nimg, int ha,
+                                  int wa, int hb, int wb, int c, int extent, int vertical) {
+  const int bh = vertical ? extent : hb, bw = vertical ? wb : extent;
+  const long long total = (long long)nimg * bh * bw * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % c);
+    long long r = i / c;
+    const int x = (int)(r % bw);
+    r /= bw;
+    const int y = (int)(r % bh);
+    const int n = (int)(r / bh);
+    const int k = vertical ? y : x;
+    const float wb_ = (float)((double)k / (double)extent);
+    const float wa_ = (float)(1.0 - (double)k / (double)extent);
+    const long long ia = vertical ? (((long long)n * ha + (ha - extent + y)) * wa + x) * c + ch
+                                  : (((long long)n * ha + y) * wa + (wa - extent + x)) * c + ch;
+    const long long ib = (((long long)n * hb + y) * wb + x) * c + ch;
+    b[ib] = __fadd_rn(__fmul_rn(a[ia], wa_), __fmul_rn(b[ib], wb_));
+  }
+}
+
+// crop [0,ch) x [0,cw) of an fp32 NHWC image tile -> u8 canvas window with the VaeImageProcessor
+// tail of the untiled path (bf16-rounded decoder output, clamp(x/2+0.5,0,1)*255, round-half-even)
+__global__ void image_crop_u8_kernel(const float* __restrict__ src, int nimg, int hs, int ws, int c,
+                                     int ch, int cw, uint8_t* __restrict__ dst, long long dst_row_stride,
+                                     long long dst_img_stride) {
+  const long long total = (long long)nimg * ch * cw * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % c);
+    long long r = i / c;
+    const int x = (int)(r % cw);
+    r /= cw;
+    const int y = (int)(r % ch);
+    const int n = (int)(r / ch);
+    const float v = src[(((long long)n * hs + y) * ws + x) * c + k];
+    const float xb = __bfloat162float(__float2bfloat16(v));
+    const float f = fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f;
+    dst[(long long)n * dst_img_stride + (long long)y * dst_row_stride + (long long)x * c + k] =
+        (uint8_t)__float2int_rn(f);
+  }
+}
+
 // ---- classifier-free guidance: out = u + gs * (t - u), un-contracted like the reference ------
 __global__ void cfg_combine_kernel(const float4* __restrict__ u, const float4* __restrict__ t, float gs,
                                    float4* __restrict__ out, long long n4) {
@@ -356,6 +403,26 @@ extern "C" int dl_lcm_step(const float* eps, const float* x, const float* noise,
       reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(x_next),
       reinterpret_cast<float4*>(denoised), n / 4, *k);
   return check_launch("lcm_step");
+}
+
+extern "C" int dl_tile_blend(const float* a, float* b, int nimg, int ha, int wa, int hb, int wb, int c,
+                             int extent, int vertical, void* stream_) {
+  DL_CHECK_ARG(a && b && nimg > 0 && c > 0 && extent > 0, "tile_blend: bad args");
+  DL_CHECK_ARG(vertical ? (wa == wb && extent <= ha && extent <= hb) : (ha == hb && extent <= wa && extent <= wb),
+               "tile_blend: tiles do not line up (a %dx%d, b %dx%d, extent %d)", ha, wa, hb, wb, extent);
+  const long long total = (long long)nimg * (vertical ? extent : hb) * (vertical ? wb : extent) * c;
+  tile_blend_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(a, b, nimg, ha, wa, hb, wb, c, extent, vertical);
+  return check_launch("tile_blend");
+}
+
+extern "C" int dl_image_crop_u8(const float* src, int nimg, int hs, int ws, int c, int crop_h, int crop_w,
+                                void* dst_u8, long long dst_row_stride, long long dst_img_stride,
+                                void* stream_) {
+  DL_CHECK_ARG(src && dst_u8 && crop_h > 0 && crop_w > 0 && crop_h <= hs && crop_w <= ws, "image_crop_u8: bad args");
+  const long long total = (long long)nimg * crop_h * crop_w * c;
+  image_crop_u8_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      src, nimg, hs, ws, c, crop_h, crop_w, reinterpret_cast<uint8_t*>(dst_u8), dst_row_stride, dst_img_stride);
+  return check_launch("image_crop_u8");
 }
 
 extern "C" int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidance_scale,

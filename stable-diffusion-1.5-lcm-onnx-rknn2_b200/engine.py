@@ -389,9 +389,55 @@ class VAEDecoderB200:
         return out.view(B, H, W, C)
 
     @torch.no_grad()
-    def decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
+               tiling: bool = False) -> torch.Tensor:
         """latents fp32 NHWC [B,h,w,4] (un-scaled, as the scheduler leaves them) -> u8 [B,8h,8w,3].
-        Fuses `/ scaling_factor`, post_quant_conv and the VaeImageProcessor denormalise."""
+        tiling: `vae.enable_tiling()` semantics (reference `backends/cuda_worker.py:91`): latents
+        larger than sample_size/8 in either dim are decoded tile by tile and blended."""
+        t = self.cfg.sample_size // 8
+        if tiling and (latents_nhwc.shape[1] > t or latents_nhwc.shape[2] > t):
+            return self.tiled_decode(latents_nhwc, out_u8)
+        return self._decode(latents_nhwc, out_u8)
+
+    @torch.no_grad()
+    def tiled_decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """diffusers `AutoencoderKL.tiled_decode`: tiles of sample_size/8
+        latents at stride 0.75 tile, each decoded on its own (own GroupNorm statistics and
+        attention), blended over sample_size/4 pixels with the already blended upper / left
+        neighbour, cropped to 0.75 sample_size and written into the canvas."""
+        B, H, W, _ = latents_nhwc.shape
+        tl = self.cfg.sample_size // 8
+        stride = int(tl * (1 - 0.25))
+        blend = int(self.cfg.sample_size * 0.25)
+        limit = self.cfg.sample_size - blend
+        if out_u8 is None:
+            out_u8 = torch.empty(B, 8 * H, 8 * W, 3, device=self.device, dtype=torch.uint8)
+        prev_row = []
+        oy = 0
+        for i in range(0, H, stride):
+            row = []
+            ox = 0
+            for jn, j in enumerate(range(0, W, stride)):
+                tile = self._decode(latents_nhwc[:, i:i + tl, j:j + tl].contiguous(), f32_out=True)
+                if i > 0:
+                    up = prev_row[jn]
+                    lib.tile_blend(up, tile, min(up.shape[1], tile.shape[1], blend), vertical=True)
+                if jn > 0:
+                    left = row[jn - 1]
+                    lib.tile_blend(left, tile, min(left.shape[2], tile.shape[2], blend), vertical=False)
+                row.append(tile)
+                ch, cw = min(limit, tile.shape[1]), min(limit, tile.shape[2])
+                lib.image_crop_u8(tile, ch, cw, out_u8[:, oy:, ox:])
+                ox += cw
+            prev_row = row
+            oy += min(limit, row[0].shape[1])
+        return out_u8
+
+    @torch.no_grad()
+    def _decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
+                f32_out: bool = False) -> torch.Tensor:
+        """One untiled decode.  Fuses `/ scaling_factor`, post_quant_conv and (u8 output) the
+        VaeImageProcessor denormalise; f32_out returns the decoder output fp32 [B,8h,8w,3]."""
         P = self.P
         B, H, W, Cin = latents_nhwc.shape
         ctx = _Ctx(self.device, B)
@@ -412,6 +458,10 @@ class VAEDecoderB200:
                 h = upsample(ctx, h, blk["up"])
         hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-6, silu=True, groups=g)
         Bo, Ho, Wo, _ = hn.shape
+        if f32_out:
+            img = torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.float32)
+            conv3x3(ctx, hn, P["conv_out_w"], P["conv_out_b"], 3, mode=lib.EPI_F32, out=img, ldo=3)
+            return img
         if out_u8 is None:
             out_u8 = torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.uint8)
         conv3x3(ctx, hn, P["conv_out_w"], P["conv_out_b"], 3, mode=lib.EPI_U8_IMAGE, out=out_u8, ldo=3)
@@ -464,10 +514,13 @@ class LCMPipelineB200:
     the UNet has no time_cond_proj — `StableDiffusionXLPipeline.__call__` behind reference
     `backends/cuda_worker.py:532`) share this loop."""
 
-    def __init__(self, unet_sd, unet_cfg, vae_sd, vae_cfg, device="cuda:0"):
+    def __init__(self, unet_sd, unet_cfg, vae_sd, vae_cfg, device="cuda:0", vae_tiling: bool = False):
+        """vae_tiling: `pipe.vae.enable_tiling()` (the reference workers always switch it on,
+        `backends/cuda_worker.py:91`): requests larger than the VAE's sample_size decode tiled."""
         self.device = torch.device(device)
         self.unet = UNetB200(unet_sd, unet_cfg, device)
         self.vae = VAEDecoderB200(vae_sd, vae_cfg, device)
+        self.vae_tiling = vae_tiling
         self._graphs = {}
 
     @property
@@ -504,7 +557,7 @@ class LCMPipelineB200:
         aug = self.unet.addition_embedding(*add) if add is not None else None
         tembs = self.unet.time_embeddings(sched.timesteps, Bu, w_emb, aug)
         lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale)
-        return self.vae.decode(lat), lat
+        return self.vae.decode(lat, tiling=self.vae_tiling), lat
 
     def graph_for(self, B, h, w, steps, cfg_scale=None) -> _StaticGraph:
         key = (B, h, w, steps, cfg_scale)

@@ -24,7 +24,7 @@ EXPORTS = [
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
-    "dl_im2col_s2_halo",
+    "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8",
 ]
 
 
@@ -106,6 +106,10 @@ def load() -> C.CDLL:
                                                 C.c_void_p]
             lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_tile_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p]
+            lib.dl_image_crop_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]
             lib.dl_cfg_combine.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_longlong,
                                            C.c_void_p]
             lib.dl_latent_pool8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -242,7 +246,12 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.identity = identity_matrix(residual.device).data_ptr() if residual is not None else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
     d.in_rows, d.in_row0 = in_rows, in_row0
-    with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1),
+    m_rows = nimg * h * w
+    ncols = n // 2 if mode == EPI_GEGLU else n
+    # algorithmic bytes: every operand once (activations, weights, residual) + the output
+    nbytes = (2.0 * m_rows * (d.c0 + d.c1) + 2.0 * n * taps * (d.c0 + d.c1) + out.element_size() * m_rows * ncols
+              + (2.0 * m_rows * n if residual is not None else 0.0))
+    with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1), nbytes,
                 tag=f"M={nimg * h * w} ({nimg}x{h}x{w}) N={n} K={taps}x{d.c0 + d.c1} mode={mode}"
                     f"{' +res' if residual is not None else ''}"):
         _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
@@ -378,6 +387,23 @@ def lcm_step(eps, x, noise, x_next, denoised, coeffs):
     k = LcmCoeffs(*[float(v) for v in coeffs])
     _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
                               denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def tile_blend(a, b, extent, vertical):
+    """fp32 NHWC tiles; b's first `extent` rows (vertical) / columns blended in place with a's last."""
+    n, ha, wa, c = a.shape
+    _, hb, wb, _ = b.shape
+    _check(load().dl_tile_blend(a.data_ptr(), b.data_ptr(), n, ha, wa, hb, wb, c, extent, int(vertical),
+                                _stream()), "tile_blend")
+    _count()
+
+
+def image_crop_u8(src, crop_h, crop_w, dst_window):
+    """src fp32 [n,hs,ws,c] -> u8 canvas window (a view [n, >=crop_h, >=crop_w, c] of the canvas)."""
+    n, hs, ws, c = src.shape
+    _check(load().dl_image_crop_u8(src.data_ptr(), n, hs, ws, c, crop_h, crop_w, dst_window.data_ptr(),
+                                   dst_window.stride(1), dst_window.stride(0), _stream()), "image_crop_u8")
     _count()
 
 
