@@ -332,9 +332,18 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           } else if (valid && ncols > 0) {
             if (p.mode == DL_EPI_F32) {
               float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col;
+              if ((ncols & 3) == 0 && (p.ldo & 3) == 0 && (col & 3) == 0) {
+                // 16-byte stores: a thread owns 128 contiguous bytes of its row, so two v4 stores
+                // fill a 32-byte sector (scalar stores at a row stride touched 32 sectors per
+                // warp instruction for 4 useful bytes each)
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols) o[j] = v[j];
+                for (int j = 0; j < 32; j += 4)
+                  if (j < ncols) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < ncols) o[j] = v[j];
+              }
             } else if (p.mode == DL_EPI_U8_IMAGE) {
               // VaeImageProcessor tail: clamp(x/2+0.5,0,1)*255, round-half-even, u8 NHWC (N = 3)
               uint8_t* o = reinterpret_cast<uint8_t*>(p.out) + row * p.ldo + col;

@@ -423,43 +423,22 @@ __global__ void __launch_bounds__(GNS_THREADS) gn_sliced_kernel(const GnSlicedPa
   }
 }
 
-// one warp per row; C <= 1280 (multiple of 8): each lane holds up to 5 vectors of 8
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows, int C,
-                                 float eps, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
-  const int warps_per_block = blockDim.x >> 5;
-  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  if (row >= rows) return;
+// LayerNorm: a warp walks rows (grid-stride), each lane holds up to MAXV vectors of 8 channels
+// (C <= 256*MAXV... in practice 320 / 640 / 1280 -> MAXV 2 / 3 / 5).  The next row's vectors are
+// requested before the current row is reduced, so every warp keeps two rows of loads in flight
+// (one row per warp left the SM at ~20 KB in flight, about half of what HBM latency needs);
+// gamma / beta live in registers across rows.  Two-pass statistics in fp32 as before, so results
+// are unchanged.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long rows,
+                                                        int C, float eps, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta,
+                                                        __nv_bfloat16* __restrict__ out) {
   const int lane = threadIdx.x & 31;
+  const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const int V = C / 8;
-  constexpr int MAXV = 5;
-  float f[MAXV][8];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < V) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * C + v * 8));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(w[j]);
-        f[i][2 * j] = t.x; f[i][2 * j + 1] = t.y;
-        sum += t.x + t.y;
-      }
-    }
-  }
-  const float mean = warp_sum(sum) / (float)C;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int v = lane + i * 32;
-    if (v < V) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  float gg[MAXV][8], bb[MAXV][8];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int v = lane + i * 32;
@@ -469,14 +448,60 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, long long 
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t o[4];
+      gg[i][0] = g0.x; gg[i][1] = g0.y; gg[i][2] = g0.z; gg[i][3] = g0.w;
+      gg[i][4] = g1.x; gg[i][5] = g1.y; gg[i][6] = g1.z; gg[i][7] = g1.w;
+      bb[i][0] = b0.x; bb[i][1] = b0.y; bb[i][2] = b0.z; bb[i][3] = b0.w;
+      bb[i][4] = b1.x; bb[i][5] = b1.y; bb[i][6] = b1.z; bb[i][7] = b1.w;
+    }
+  }
+  uint4 nxt[MAXV];
+  auto fetch = [&](long long row) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o[j] = pack_bf16x2((f[i][2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j],
-                           (f[i][2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
-      *reinterpret_cast<uint4*>(out + row * C + c) = make_uint4(o[0], o[1], o[2], o[3]);
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) nxt[i] = __ldg(reinterpret_cast<const uint4*>(x + row * C + v * 8));
+    }
+  };
+  if (warp0 < rows) fetch(warp0);
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float f[MAXV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) {
+        const uint32_t w[4] = {nxt[i].x, nxt[i].y, nxt[i].z, nxt[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_bf16x2(w[j]);
+          f[i][2 * j] = t.x; f[i][2 * j + 1] = t.y;
+          sum += t.x + t.y;
+        }
+      }
+    }
+    if (row + nwarps < rows) fetch(row + nwarps);         // next row in flight during the reductions
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int v = lane + i * 32;
+      if (v < V) {
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o[j] = pack_bf16x2((f[i][2 * j] - mean) * rstd * gg[i][2 * j] + bb[i][2 * j],
+                             (f[i][2 * j + 1] - mean) * rstd * gg[i][2 * j + 1] + bb[i][2 * j + 1]);
+        *reinterpret_cast<uint4*>(out + row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 }
@@ -812,9 +837,13 @@ extern "C" int dl_layernorm(const void* x, long long rows, int c, float eps, con
   DL_CHECK_ARG(x && out && gamma && beta, "layernorm: null pointer");
   DL_CHECK_ARG(c % 8 == 0 && c > 0 && c <= 1280, "layernorm: C=%d must be a multiple of 8, <= 1280", c);
   const int wpb = 8;
-  const long long blocks = (rows + wpb - 1) / wpb;
-  layernorm_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), rows, c, eps, gamma, beta,
-      reinterpret_cast<__nv_bfloat16*>(out));
+  long long blocks = (rows + wpb - 1) / wpb;
+  const long long cap = (long long)num_sms() * 8;        // resident blocks: the warps stride over rows
+  if (blocks > cap) blocks = cap;
+  const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
+  __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
+  if (c <= 512) layernorm_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
+  else if (c <= 768) layernorm_kernel<3><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
+  else layernorm_kernel<5><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
   return check_launch("layernorm");
 }

@@ -373,6 +373,15 @@ class VAEDecoderB200:
         hn2 = hn.view(B * S, C)
         qk = linear(ctx, hn2, a["qk_w"], a["qk_b"], 2 * C)                 # [B*S, 2C]
         o = ctx.empty(B * S, C)
+        if S % 64:
+            # ragged tiles of a tiled decode (token count not a multiple of the 64-deep GEMM K
+            # chunk, e.g. a 29 x 29 corner tile): the CUDA-core flash kernel takes any length.
+            # b_v is folded into the out-proj bias exactly as below (softmax rows sum to 1).
+            v = linear(ctx, hn2, a["v_w"], None, C)
+            lib.attention(qk, qk[:, C:], v, o, batch=B, sq=S, skv=S, heads=1, d=C, dh_stride=C,
+                          ldq=2 * C, ldk=2 * C, ldv=C, ldo=C, scale=1.0 / math.sqrt(C), impl=lib.ATTN_SIMT)
+            out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C))
+            return out.view(B, H, W, C)
         scores = ctx.empty(S, S, dtype=torch.float32)
         probs = ctx.empty(S, S)
         vt = ctx.empty(C, S)
