@@ -126,8 +126,56 @@ class B200Worker(PipelineWorker):
         self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
                                     vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True)
         self._text = self._make_text_encoder(path)
+        self._load_styles({k: tuple(v.shape) for k, v in unet_sd.items()})
         print(f"[{self._tag}] worker {worker_id} loaded: {model_name} on {self.device} "
-              f"(noise dtype={dtype_str}, compute bf16)")
+              f"(noise dtype={dtype_str}, compute bf16, styles={sorted(self._style_loaded)})")
+
+    # ------------------------------------------------------------------ styles
+    def _load_styles(self, unet_shapes):
+        """Preload every registry style whose cross-attention dim matches the model (reference
+        `backends/cuda_worker.py:123-147`); a style that fails to load is skipped, not fatal."""
+        from backends import styles
+        from dreamlab_b200.lora import StyleManager
+        from safetensors.torch import load_file
+        self._style_loaded = {}
+        self._style_api = "merged"
+        self._styles = StyleManager(self.pipe.unet, unet_shapes)
+        self._registry = dict(styles.STYLE_REGISTRY) or styles.load_registry()
+        cad = self.pipe.unet.cfg.cross_attention_dim
+        for sid, sd in self._registry.items():
+            if sd.required_cross_attention_dim is not None and int(sd.required_cross_attention_dim) != int(cad):
+                print(f"[{self._tag}] skip style '{sid}': incompatible cross_attention_dim "
+                      f"(model={cad} style={sd.required_cross_attention_dim})")
+                self._style_loaded[sd.adapter_name] = False
+                continue
+            try:
+                ad = self._styles.load(sd.adapter_name, load_file(sd.lora_path))
+                self._style_loaded[sd.adapter_name] = True
+                print(f"[{self._tag}] loaded style LoRA: {sid} -> {sd.lora_path} (adapter={sd.adapter_name}, "
+                      f"{ad.num_tensors} packed tensors, {len(ad.skipped)} entries skipped)")
+            except Exception as e:                         # noqa: BLE001 - same policy as the reference
+                self._style_loaded[sd.adapter_name] = False
+                print(f"[{self._tag}] FAILED to load style LoRA {sid}: {e!r}")
+
+    def _apply_style(self, style_id, level) -> None:
+        """Exclusive style selection (reference `backends/cuda_worker.py:165-196`)."""
+        from backends.styles import clamp_level
+        if not style_id or int(level) <= 0:
+            self._styles.disable()
+            return
+        sd = self._registry.get(style_id)
+        if not sd or not self._style_loaded.get(sd.adapter_name, False):
+            self._styles.disable()
+            return
+        weight = float(sd.levels[clamp_level(level, len(sd.levels)) - 1])
+        self._styles.set_adapter(sd.adapter_name, weight)
+
+    @staticmethod
+    def _style_of(req):
+        sl = getattr(req, "style_lora", None)
+        style = getattr(sl, "style", None) if sl else None
+        level = int(getattr(sl, "level", 0) or 0) if sl else 0
+        return (style, level) if style and level > 0 else (None, 0)
 
     def _make_text_encoder(self, path):
         return _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
@@ -173,8 +221,15 @@ class B200Worker(PipelineWorker):
             noise = (torch.stack([torch.cat([d[1][i] for d in draws], 0) for i in range(steps - 1)])
                      if steps > 1 else None)
             gs = torch.tensor([float(j.req.guidance_scale) for j in jobs])
-            img, final = self._generate([str(j.req.prompt) for j in jobs], lat, noise, steps, gs,
-                                        height, width)
+            styles = {self._style_of(j.req) for j in jobs}
+            if len(styles) != 1:
+                raise RuntimeError("run_batch: jobs must share style and level")
+            self._apply_style(*next(iter(styles)))
+            try:
+                img, final = self._generate([str(j.req.prompt) for j in jobs], lat, noise, steps, gs,
+                                            height, width)
+            finally:
+                self._apply_style(None, 0)          # reset: no state bleed into the next job
             pooled = None
             if with_latents:
                 from dreamlab_b200 import lib

@@ -115,10 +115,14 @@ def _auto_num_workers() -> int:
 
 
 def _batch_key(job):
-    """Generation jobs that may share one batched pass: same size and step count."""
+    """Generation jobs that may share one batched pass: same size, step count and style."""
     req = getattr(job, "req", None)
     try:
-        return (str(req.size).lower(), int(req.num_inference_steps))
+        sl = getattr(req, "style_lora", None)
+        style = (getattr(sl, "style", None), int(getattr(sl, "level", 0) or 0)) if sl else (None, 0)
+        if not style[0] or style[1] <= 0:
+            style = (None, 0)
+        return (str(req.size).lower(), int(req.num_inference_steps), style)
     except Exception:
         return None
 

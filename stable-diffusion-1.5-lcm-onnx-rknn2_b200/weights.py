@@ -14,6 +14,7 @@ Layouts
 """
 from __future__ import annotations
 
+import threading
 from typing import Dict
 
 import torch
@@ -23,8 +24,27 @@ def ceil16(d: int) -> int:
     return (d + 15) // 16 * 16
 
 
+_tls = threading.local()
+
+
+class pack_dtype:
+    """Context: dtype of the packed GEMM operands (bf16 for the kernels; fp32 when packing LoRA
+    deltas, `lora.py`).  Thread-local: pool workers load concurrently."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        self.prev = getattr(_tls, "dtype", torch.bfloat16)
+        _tls.dtype = self.dtype
+
+    def __exit__(self, *exc):
+        _tls.dtype = self.prev
+        return False
+
+
 def _bf(t, device):
-    return t.to(device=device, dtype=torch.bfloat16).contiguous()
+    return t.to(device=device, dtype=getattr(_tls, "dtype", torch.bfloat16)).contiguous()
 
 
 def _f32(t, device):

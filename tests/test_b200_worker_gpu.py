@@ -99,3 +99,64 @@ def test_batch_equals_singles_and_pool_roundtrip(worker):
     assert [r[1] for r in res] == [100, 101, 102, 103] and all(r[0][:4] == b"\x89PNG" for r in res)
     pool._workers = []        # the fixture owns the worker
     pool.shutdown()
+
+
+def test_style_lora_levels_and_reset(tmp_path):
+    """Style LoRAs through the worker (reference `backends/cuda_worker.py:123-196, 215-232`):
+    registry preload, level -> adapter weight, exclusive selection, reset after every job; the
+    styled image equals the un-styled pipeline run on weights merged offline in fp32."""
+    import json
+    import numpy as np
+    from PIL import Image
+    from safetensors.torch import load_file, save_file
+    from dreamlab_b200 import synthetic as S
+    from dreamlab_b200.engine import LCMPipelineB200
+    from dreamlab_b200.lora import lora_weight_deltas
+    from backends.b200_worker import B200Worker, unet_cfg_from_json, vae_cfg_from_json
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from test_lora import MODS, _kohya_lora
+    root = tmp_path / "models"
+    ucfg = UNetConfig.tiny()
+    ucfg.cross_attention_dim = 768
+    mdir = S.write_model_dir(str(root / "tiny-lcm"), ucfg, VAEConfig.tiny())
+    shapes = S.unet_shapes(ucfg)
+    lora = _kohya_lora(shapes, MODS, r=4, alpha=4.0)
+    lora = {k: v * 3.0 for k, v in lora.items()}                      # strong enough to see
+    save_file({k: v.contiguous() for k, v in lora.items()}, str(tmp_path / "style.safetensors"))
+    reg = {"ink": {"title": "Ink", "lora_path": str(tmp_path / "style.safetensors"), "adapter_name": "style_ink",
+                   "levels": [0.5, 1.0], "required_cross_attention_dim": 768},
+           "xl_only": {"lora_path": str(tmp_path / "style.safetensors"), "levels": [1.0],
+                       "required_cross_attention_dim": 2048}}
+    (tmp_path / "styles.json").write_text(json.dumps(reg))
+    old = {k: os.environ.get(k) for k in ("MODEL_ROOT", "MODEL", "B200_STYLES")}
+    os.environ.update(MODEL_ROOT=str(root), MODEL="tiny-lcm", B200_STYLES=str(tmp_path / "styles.json"))
+    try:
+        w = B200Worker(worker_id=0)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert w._style_loaded == {"style_ink": True, "style_xl_only": False}
+
+    def styled(style, level, seed=5):
+        j = job(seed=seed)
+        j.req.style_lora = SimpleNamespace(style=style, level=level)
+        return np.asarray(Image.open(io.BytesIO(w.run_job(j)[0]))).astype(int)
+
+    plain = styled(None, 0)
+    lvl1, lvl2, lvl9 = styled("ink", 1), styled("ink", 2), styled("ink", 9)
+    assert np.abs(lvl1 - plain).max() > 2 and np.abs(lvl2 - lvl1).max() > 2
+    assert np.array_equal(lvl9, lvl2)                                 # level clamps to the ladder
+    assert np.array_equal(styled(None, 0), plain)                     # reset: no state bleed
+    assert np.array_equal(styled("unknown", 2), plain) and np.array_equal(styled("xl_only", 1), plain)
+    # same request on a pipeline built from offline-merged weights (fp32 merge, then packed)
+    unet_sd = load_file(os.path.join(mdir, "unet", "diffusion_pytorch_model.safetensors"))
+    vae_sd = load_file(os.path.join(mdir, "vae", "diffusion_pytorch_model.safetensors"))
+    deltas, _ = lora_weight_deltas(shapes, lora)
+    merged = {k: (v.float() + 1.0 * deltas[k] if k in deltas else v) for k, v in unet_sd.items()}
+    ref = LCMPipelineB200(merged, unet_cfg_from_json(json.load(open(os.path.join(mdir, "unet", "config.json")))),
+                          vae_sd, vae_cfg_from_json(json.load(open(os.path.join(mdir, "vae", "config.json")))), "cuda:0")
+    lat, noise = w._draw(5, 16, 16, 2)
+    pe = w._text.encode(["a cat"])
+    img = ref.generate(pe, lat, torch.stack(noise), 2, torch.tensor([1.0])).cpu().numpy()[0].astype(int)
+    assert np.abs(img - lvl2).max() <= 2, np.abs(img - lvl2).max()
