@@ -75,12 +75,20 @@ typedef struct dl_igemm_desc {
   int mode;                  /* DL_EPI_*                                                      */
   float alpha;               /* accumulator scale (0 -> 1)                                    */
   int bn;                    /* N tile (multiple of 16, <=256); 0 = auto                      */
+  float* gn_partial;         /* optional: GroupNorm (sum, sumsq) records of the bf16 OUTPUT, fp32        */
+  int gn_cpg;                /*   [nimg, gn_slots, n/gn_cpg, 2]; one slot per M tile of an image, written */
+  int gn_slots, gn_slot0;    /*   at gn_slot0 + tile (folded-upsample phases use disjoint slot ranges);   */
+  int gn_rows_per_img;       /*   channels per group 4/8/16/32.  Token-row GEMMs (nimg=1,h=1) give the
+                                rows per image (multiple of 128); 0 for NHWC convs.  The records feed
+                                dl_groupnorm_finalize: the consumer norm then reads its input once.   */
   int in_rows;               /* halo-padded row strips (SDXL patch parallel): a0/a1 */
   int in_row0;               /*   hold in_rows >= h rows per image and output row y reads input rows
                                 y + dy + in_row0; 0/0 = dense (in_rows = h)                    */
 } dl_igemm_desc;
 
 int dl_igemm(const dl_igemm_desc* desc, void* stream);
+/* M tiles per image of an h x w conv (slots a gn_partial buffer needs); 0 if tiles span images   */
+int dl_igemm_tiles_per_image(int h, int w);
 /* fills a caller-owned 256x256 bf16 device buffer (128 KB) with the identity matrix            */
 int dl_fill_identity(void* dst_bf16_256x256, void* stream);
 
@@ -100,6 +108,10 @@ int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int nimg, int h
  * dl_groupnorm_apply merges them in rank order and normalises the strip.  out_img_stride
  * (elements, 0 = dense) lets the result land inside a halo-padded buffer.  The workspace must
  * be zero-initialised once (>= dl_groupnorm_split_workspace_bytes()).                          */
+/* (sum, sumsq) records [nimg, slots, groups, 2] from the producing dl_igemm -> (mean, M2) records
+ * [nimg, groups, 2] for dl_groupnorm_apply (nranks = 1); fp64 accumulation in fixed order.      */
+int dl_groupnorm_finalize(const float* partial, int nimg, int slots, int groups, long long count,
+                          float* stats, void* stream);
 size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups);
 int dl_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
                        float* stats, void* workspace, void* stream);

@@ -36,6 +36,9 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow oursel
 
 constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
 constexpr int EPI_SLAB_BYTES = 2 * 2 * 256 * 4;    // (bias + row add) slab: [tile parity][image 0/1][256 cols]
+// GroupNorm partials of the OUTPUT tensor, emitted by the epilogue (VAE decoder: channels per
+// group 4 / 8 / 16 / 32 divide the 32-column chunk): [half][chunk-in-flight <= 4][quadrant][16] floats
+constexpr int EPI_GN_BYTES = 2 * 4 * 4 * 16 * 4;
 // staging ring per epilogue half: 2 buffers for long-K tiles, 4 for short-K tiles whose TMA
 // stores queue behind a deep load pipeline (the epilogue must not wait on each store)
 
@@ -63,7 +66,43 @@ struct IgemmParams {
   long long ldr;
   int mode;
   float alpha;
+  // GroupNorm (sum, sum of squares) records of the bf16 output: [image][slot][group][2] fp32, one
+  // slot per M tile of the image; every (slot, group) is written by exactly one CTA (fixed order)
+  float* gn_partial;
+  int gn_cpg, gn_groups, gn_slots, gn_slot0, gn_rows_per_img;
 };
+
+// Per-thread (= per output pixel) partial sums of one 32-column chunk, CPG channels per group,
+// on the bf16-rounded values the next kernel will read; then a butterfly over the warp's 32 rows.
+template <int CPG>
+__device__ __forceinline__ void gn_chunk_partials(const float (&v)[64], bool valid, float* dst16) {
+  constexpr int NG = 32 / CPG;
+  float s[NG], q[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPG; ++j) {
+      const float x = __bfloat162float(__float2bfloat16(v[g * CPG + j]));
+      a += x;
+      b = fmaf(x, x, b);
+    }
+    s[g] = valid ? a : 0.f;
+    q[g] = valid ? b : 0.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+      q[g] += __shfl_xor_sync(0xffffffffu, q[g], o);
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g) { dst16[2 * g] = s[g]; dst16[2 * g + 1] = q[g]; }
+  }
+}
 
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p) {
@@ -74,7 +113,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   const int b_tile_bytes = p.BN * BK * 2;
   const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;         // 1024-aligned
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES +
+                                               EPI_GN_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -220,6 +260,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     const int bar_id = 1 + half;
     uint8_t* my_staging = staging + half * p.epi_nbuf * EPI_BUF_BYTES;
     float* slab = reinterpret_cast<float*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES);
+    float* gn_scr = reinterpret_cast<float*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES) +
+                    half * (4 * 4 * 16);                   // this half's [chunk][quadrant][16]
+    const bool gn_on = (p.gn_partial != nullptr);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tw_mask = (1 << p.tw_log2) - 1;
@@ -303,6 +346,15 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             for (int j = 0; j < 64; ++j)
               if (j < ncols) v[j] += __ldg(ra_row + col + j);
           }
+          if (gn_on) {
+            float* dst = gn_scr + (g * 4 + quad) * 16;
+            switch (p.gn_cpg) {
+              case 4: gn_chunk_partials<4>(v, valid, dst); break;
+              case 8: gn_chunk_partials<8>(v, valid, dst); break;
+              case 16: gn_chunk_partials<16>(v, valid, dst); break;
+              default: gn_chunk_partials<32>(v, valid, dst); break;
+            }
+          }
           if (staged) {
             uint4 ov[4];
             if (p.mode == DL_EPI_GEGLU) {
@@ -369,6 +421,26 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         if (staged) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
+          if (gn_on) {
+            // fold the four quadrants (32 rows each) in fixed order; one writer per (slot, group)
+            const int ng2 = 2 * (32 / p.gn_cpg);
+            const int th = threadIdx.x - 64 - 128 * half;
+            if (th < g * ng2) {
+              const int gi = th / ng2, k = th - gi * ng2;
+              const float* src = gn_scr + gi * 64 + k;
+              const float tot = (src[0] + src[16]) + (src[32] + src[48]);
+              const int col_g = col0 + c_group + gi * 2 * step;          // first column of that chunk
+              int img = n0, slot = ty * p.tiles_x + tx;
+              if (p.gn_rows_per_img > 0) {                               // token rows: nimg=1, h=1, w=M
+                const long long row0 = (long long)tx << 7;
+                img = (int)(row0 / p.gn_rows_per_img);
+                slot = (int)((row0 % p.gn_rows_per_img) >> 7);
+              }
+              if (col_g < p.N && img < (p.gn_rows_per_img > 0 ? 0x7fffffff : p.NIMG))
+                p.gn_partial[(((long long)img * p.gn_slots + p.gn_slot0 + slot) * p.gn_groups +
+                              col_g / p.gn_cpg + (k >> 1)) * 2 + (k & 1)] = tot;
+            }
+          }
           if (leader) {
 #pragma unroll 1
             for (int gg = 0; gg < g; ++gg) {
@@ -498,7 +570,7 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
   const int base_kb = d->taps * ((d->c0 + d->c1) / BK);
   p.epi_nbuf = (base_kb <= 20) ? 4 : 2;
-  const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES;
+  const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES + EPI_GN_BYTES;
   p.stages = (SMEM_BUDGET - staging_bytes) / stage_bytes;
   if (p.stages > 8) p.stages = 8;
   p.res_chunks = d->residual ? (bn + BK - 1) / BK : 0;
@@ -514,6 +586,20 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
   p.mode = d->mode;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+  if (d->gn_partial) {
+    const int cpg = d->gn_cpg;
+    DL_CHECK_ARG(d->mode == DL_EPI_BF16, "igemm: GroupNorm partials need DL_EPI_BF16");
+    DL_CHECK_ARG((cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && d->n % 32 == 0 && d->n % cpg == 0,
+                 "igemm: GroupNorm partials need 4/8/16/32 channels per group and n %% 32 == 0 (cpg=%d n=%d)", cpg, d->n);
+    DL_CHECK_ARG(tn == 1 || d->gn_rows_per_img > 0, "igemm: GroupNorm partials need one image per M tile");
+    DL_CHECK_ARG(d->gn_rows_per_img == 0 || (d->nimg == 1 && d->h == 1 && d->gn_rows_per_img % 128 == 0),
+                 "igemm: gn_rows_per_img needs token rows (nimg=1,h=1) and a multiple of 128");
+    p.gn_partial = d->gn_partial; p.gn_cpg = cpg; p.gn_groups = d->n / cpg;
+    p.gn_slots = d->gn_slots; p.gn_slot0 = d->gn_slot0; p.gn_rows_per_img = d->gn_rows_per_img;
+    const int per_img = d->gn_rows_per_img > 0 ? d->gn_rows_per_img / 128 : p.tiles_x * p.tiles_y;
+    DL_CHECK_ARG(d->gn_slot0 >= 0 && d->gn_slot0 + per_img <= d->gn_slots,
+                 "igemm: GroupNorm partial slots [%d, %d) exceed gn_slots=%d", d->gn_slot0, d->gn_slot0 + per_img, d->gn_slots);
+  }
 
 
   // ---- tensor maps ----
@@ -594,6 +680,14 @@ extern "C" int dl_fill_identity(void* dst_bf16_256x256, void* stream) {
   dl::fill_identity_kernel<<<(256 * 256 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<__nv_bfloat16*>(dst_bf16_256x256), 256);
   return dl::check_launch("fill_identity");
+}
+
+extern "C" int dl_igemm_tiles_per_image(int h, int w) {
+  // M tiles one image of h x w pixels is cut into (0: several images share a tile, no partials)
+  const int tw = dl::pick_extent(w, 128);
+  const int th = dl::pick_extent(h, 128 / tw);
+  if (tw * th != 128) return 0;
+  return ((w + tw - 1) / tw) * ((h + th - 1) / th);
 }
 
 extern "C" int dl_igemm(const dl_igemm_desc* d, void* stream) {

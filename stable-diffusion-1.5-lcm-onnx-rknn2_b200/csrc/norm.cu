@@ -663,6 +663,32 @@ __global__ void __launch_bounds__(GNX_THREADS) gn_apply_kernel(const GnSplitPara
   }
 }
 
+// (sum, sumsq) per (image, M tile, group) from the producing conv's epilogue -> (mean, M2)
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int slots,
+                                                          int groups, double count, float* __restrict__ stats) {
+  __shared__ double sh[2][128];
+  const int img = blockIdx.x / groups, g = blockIdx.x % groups;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < slots; i += 128) {
+    const float2 r = __ldg(reinterpret_cast<const float2*>(partial + (((long long)img * slots + i) * groups + g) * 2));
+    s += (double)r.x;
+    q += (double)r.y;
+  }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {                      // fixed tree: deterministic
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = sh[0][0] / count;
+    const double m2 = sh[1][0] - sh[0][0] * mean;
+    stats[((long long)img * groups + g) * 2 + 0] = (float)mean;
+    stats[((long long)img * groups + g) * 2 + 1] = (float)(m2 > 0.0 ? m2 : 0.0);
+  }
+}
+
 static int gn_split_setup(GnSplitParams& p, const void* x0, int c0, const void* x1, int c1, int nimg,
                           int hw, int groups) {
   const int C = c0 + c1;
@@ -690,6 +716,15 @@ static int gn_split_setup(GnSplitParams& p, const void* x0, int c0, const void* 
 }
 
 }  // namespace dl
+
+extern "C" int dl_groupnorm_finalize(const float* partial, int nimg, int slots, int groups, long long count,
+                                     float* stats, void* stream_) {
+  using namespace dl;
+  DL_CHECK_ARG(partial && stats && nimg > 0 && slots > 0 && groups > 0 && count > 0, "groupnorm_finalize: bad args");
+  gn_finalize_kernel<<<nimg * groups, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(partial, slots, groups,
+                                                                                       (double)count, stats);
+  return check_launch("groupnorm_finalize");
+}
 
 extern "C" size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups) {
   return 4096 + (size_t)(nimg > 0 ? nimg : 1) * dl::GNX_MAX_SLABS * (groups > 0 ? groups : 32) * 2 * sizeof(float);

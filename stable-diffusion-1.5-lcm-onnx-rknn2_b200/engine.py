@@ -42,10 +42,14 @@ class _Ctx:
     """Per-forward scratch: device, batch, the GroupNorm workspace and (patch-parallel runs)
     the strip communicator.  comm=None is the single-GPU path."""
 
-    def __init__(self, device, batch, comm=None):
+    def __init__(self, device, batch, comm=None, gn_fuse=0):
         self.device = device
         self.batch = batch
         self.comm = comm
+        # > 0: convs emit GroupNorm partial statistics of their output for norms with this many
+        # groups (VAE decoder: 4/8/16 channels per group line up with the epilogue's 32-column
+        # chunks); the consumer norm then reads its input once instead of twice
+        self.gn_fuse = gn_fuse if comm is None else 0
         self.gn_ws = torch.empty(lib.groupnorm_workspace_bytes(batch, 32), device=device,
                                  dtype=torch.uint8)
         if comm is not None:
@@ -72,8 +76,16 @@ class _Ctx:
 # ------------------------------------------------------------------------------------------------
 # building blocks
 # ------------------------------------------------------------------------------------------------
+def _gn_request(ctx, B, n_out, slots, phases=1):
+    """Partial-statistics buffer for an igemm whose output feeds a GroupNorm, or None."""
+    g = ctx.gn_fuse
+    if not g or n_out % g or n_out % 32 or (n_out // g) not in (4, 8, 16, 32) or slots <= 0:
+        return None
+    return ctx.empty(B, slots * phases, g, 2, dtype=torch.float32)
+
+
 def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=lib.EPI_BF16,
-            out=None, ldo=None):
+            out=None, ldo=None, feeds_norm=False):
     """x: dense [B,H,W,C] (zero padding all round) or a Padded strip (halo rows supplied)."""
     halo = isinstance(x, Padded)
     if halo:
@@ -83,23 +95,36 @@ def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=li
         H -= 2
     if out is None:
         out = ctx.empty(B, H, W, n_out, dtype=torch.float32 if mode == lib.EPI_F32 else BF16)
+    part = None
+    if feeds_norm and ctx.gn_fuse and mode == lib.EPI_BF16 and not halo:
+        part = _gn_request(ctx, B, n_out, lib.igemm_tiles_per_image(H, W))
     lib.igemm(x, w, out, nimg=B, h=H, w=W, taps=9, n=n_out, a1=x1, bias=b, rowadd=rowadd,
               residual=residual, mode=mode, ldo=ldo, in_rows=H + 2 if halo else 0,
-              in_row0=1 if halo else 0)
+              in_row0=1 if halo else 0, gn_partial=part, gn_cpg=(n_out // ctx.gn_fuse) if part is not None else 0)
+    if part is not None:
+        out._gn = part
     return out
 
 
 def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, out_cols=None,
-           alpha=1.0, out=None):
-    """x: [..., K] bf16 rows (any leading shape); returns [..., n_out] (or n_out/2 for GEGLU)."""
+           alpha=1.0, out=None, norm_rows_per_img=0):
+    """x: [..., K] bf16 rows (any leading shape); returns [..., n_out] (or n_out/2 for GEGLU).
+    norm_rows_per_img > 0: the output (token rows of images of that many pixels) feeds a GroupNorm."""
     lead = x.shape[:-1]
     M = x.numel() // x.shape[-1]
     cols = out_cols if out_cols is not None else (n_out // 2 if mode == lib.EPI_GEGLU else n_out)
     if out is None:
         out = ctx.empty(*lead, cols, dtype=torch.float32 if mode == lib.EPI_F32 else BF16)
+    part = None
+    if norm_rows_per_img and norm_rows_per_img % 128 == 0 and mode == lib.EPI_BF16 and M % norm_rows_per_img == 0:
+        part = _gn_request(ctx, M // norm_rows_per_img, n_out, norm_rows_per_img // 128)
     lib.igemm(x, w, out, nimg=1, h=1, w=M, taps=1, n=n_out, a1=x1, bias=b, residual=residual,
               mode=mode, alpha=alpha, a0_stride=x.stride(-2), a1_stride=None if x1 is None else x1.stride(-2),
-              ldo=cols, ldr=None if residual is None else residual.shape[-1])
+              ldo=cols, ldr=None if residual is None else residual.shape[-1], gn_partial=part,
+              gn_cpg=(n_out // ctx.gn_fuse) if part is not None else 0,
+              gn_rows_per_img=norm_rows_per_img if part is not None else 0)
+    if part is not None:
+        out._gn = part
     return out
 
 
@@ -107,6 +132,14 @@ def groupnorm(ctx, x, gw, gb, *, eps, silu, x1=None, groups=32, halo=False):
     """halo=True (feeds a conv3x3): under a strip communicator the result is a Padded strip."""
     B, H, W, C0 = x.shape
     C = C0 + (x1.shape[-1] if x1 is not None else 0)
+    part = getattr(x, "_gn", None)
+    if ctx.comm is None and part is not None and x1 is None and part.shape[2] == groups:
+        # the producing conv left (sum, sumsq) per M tile: one tiny reduction, then ONE pass over x
+        stats = ctx.empty(1, B, groups, 2, dtype=torch.float32)
+        lib.groupnorm_finalize(part, stats, H * W * (C // groups))
+        out = ctx.empty(B, H, W, C)
+        lib.groupnorm_apply(x, out, gw, gb, stats, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu)
+        return out
     if ctx.comm is None:
         out = ctx.empty(B, H, W, C)
         lib.groupnorm(x, out, gw, gb, ctx.gn_ws, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu, x1=x1)
@@ -134,14 +167,14 @@ def resnet(ctx, x, p: Packed, *, temb=None, x1=None, eps=1e-5, groups=32):
     rowadd = None
     if temb is not None:
         rowadd = temb[:, p["temb_off"]:p["temb_off"] + cout]     # view: ld = temb_total
-    h = conv3x3(ctx, h, p["conv1_w"], p["conv1_b"], cout, rowadd=rowadd)
+    h = conv3x3(ctx, h, p["conv1_w"], p["conv1_b"], cout, rowadd=rowadd, feeds_norm=True)
     h = groupnorm(ctx, h, p["norm2_w"], p["norm2_b"], eps=eps, silu=True, groups=groups, halo=True)
     if p["sc_w"] is not None:
         sc = linear(ctx, x, p["sc_w"], p["sc_b"], cout, x1=x1)
     else:
         assert x1 is None
         sc = x
-    return conv3x3(ctx, h, p["conv2_w"], p["conv2_b"], cout, residual=sc)
+    return conv3x3(ctx, h, p["conv2_w"], p["conv2_b"], cout, residual=sc, feeds_norm=True)
 
 
 def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
@@ -217,11 +250,16 @@ def upsample(ctx, x, p: Packed):
     src, halo = x, {}
     if ctx.comm is not None:
         src, halo = ctx.pad_rows(x).t, dict(in_rows=H + 2, in_row0=1)
+    T = lib.igemm_tiles_per_image(H, W) if ctx.gn_fuse else 0
+    part = _gn_request(ctx, B, C, T, phases=4)
     for ph in range(4):
         a, b = ph >> 1, ph & 1
         view = out[:, a:, b:, :]                            # base pointer of phase (a, b)
         lib.igemm(src, p["w"][ph], view, nimg=B, h=H, w=W, taps=4, n=C, bias=p["b"], tap_phase=ph,
-                  ldo=C, out_strides=strides, **halo)
+                  ldo=C, out_strides=strides, gn_partial=part, gn_cpg=(C // ctx.gn_fuse) if part is not None else 0,
+                  gn_slot0=ph * T, **halo)
+    if part is not None:
+        out._gn = part
     return out
 
 
@@ -364,6 +402,8 @@ class VAEDecoderB200:
         self.cfg = cfg
         self.P = pack_vae_decoder(state_dict, cfg, self.device)
         self.groups = cfg.norm_num_groups
+        import os
+        self.fuse_gn_stats = os.environ.get("DL_VAE_GN_FUSE", "1") not in ("0", "false")
 
     def _mid_attention(self, ctx, x, a: Packed):
         """heads=1, d=C (512): QK^T and PV through the tcgen05 GEMM, fp32 scores, per image."""
@@ -394,8 +434,11 @@ class VAEDecoderB200:
                       mode=lib.EPI_F32, alpha=1.0 / math.sqrt(C), ldo=S)
             lib.softmax_rows(scores, probs)
             lib.igemm(probs, vt, o[rows], nimg=1, h=1, w=S, taps=1, n=C, a0_stride=S, ldo=C)
-        out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C))
-        return out.view(B, H, W, C)
+        out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C), norm_rows_per_img=S)
+        res = out.view(B, H, W, C)
+        if hasattr(out, "_gn"):
+            res._gn = out._gn
+        return res
 
     @torch.no_grad()
     def decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
@@ -449,14 +492,14 @@ class VAEDecoderB200:
         VaeImageProcessor denormalise; f32_out returns the decoder output fp32 [B,8h,8w,3]."""
         P = self.P
         B, H, W, Cin = latents_nhwc.shape
-        ctx = _Ctx(self.device, B)
         g = self.groups
+        ctx = _Ctx(self.device, B, gn_fuse=g if self.fuse_gn_stats else 0)
         ch = self.cfg.block_out_channels
         z = ctx.empty(B, H, W, 64)
         lib.pack_latent(latents_nhwc, z, cin=Cin, scale=1.0 / self.cfg.scaling_factor,
                         mat=P["pq_w"], vec=P["pq_b"])
         # `/ scaling_factor` is computed as a multiply by the fp32 reciprocal
-        h = conv3x3(ctx, z, P["conv_in_w"], P["conv_in_b"], ch[-1])
+        h = conv3x3(ctx, z, P["conv_in_w"], P["conv_in_b"], ch[-1], feeds_norm=True)
         h = resnet(ctx, h, P["mid_res"][0], eps=1e-6, groups=g)
         h = self._mid_attention(ctx, h, P["mid_attn"])
         h = resnet(ctx, h, P["mid_res"][1], eps=1e-6, groups=g)

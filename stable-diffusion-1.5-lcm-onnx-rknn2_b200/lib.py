@@ -24,7 +24,8 @@ EXPORTS = [
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
-    "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8",
+    "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8", "dl_igemm_tiles_per_image",
+    "dl_groupnorm_finalize",
 ]
 
 
@@ -39,6 +40,8 @@ class IgemmDesc(C.Structure):
         ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int),
         ("residual", C.c_void_p), ("ldr", C.c_longlong), ("identity", C.c_void_p),
         ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
+        ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int), ("gn_slots", C.c_int), ("gn_slot0", C.c_int),
+        ("gn_rows_per_img", C.c_int),
         ("in_rows", C.c_int), ("in_row0", C.c_int),
     ]
 
@@ -74,6 +77,9 @@ def load() -> C.CDLL:
             lib.dl_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_igemm_tiles_per_image.argtypes = [C.c_int, C.c_int]
+            lib.dl_groupnorm_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                                  C.c_void_p, C.c_void_p]
             lib.dl_groupnorm_split_workspace_bytes.restype = C.c_size_t
             lib.dl_groupnorm_split_workspace_bytes.argtypes = [C.c_int, C.c_int]
             lib.dl_groupnorm_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -220,7 +226,8 @@ def require_cuda():
 # ------------------------------------------------------------------------------------------------
 def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
           a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
-          mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None, in_rows=0, in_row0=0):
+          mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None, in_rows=0, in_row0=0,
+          gn_partial=None, gn_cpg=0, gn_slot0=0, gn_rows_per_img=0):
     """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
     nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
     d = IgemmDesc()
@@ -246,6 +253,9 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.identity = identity_matrix(residual.device).data_ptr() if residual is not None else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
     d.in_rows, d.in_row0 = in_rows, in_row0
+    if gn_partial is not None:         # [nimg, slots, groups, 2] fp32
+        d.gn_partial, d.gn_cpg, d.gn_slots = gn_partial.data_ptr(), gn_cpg, gn_partial.shape[1]
+        d.gn_slot0, d.gn_rows_per_img = gn_slot0, gn_rows_per_img
     m_rows = nimg * h * w
     ncols = n // 2 if mode == EPI_GEGLU else n
     # algorithmic bytes: every operand once (activations, weights, residual) + the output
@@ -270,6 +280,18 @@ def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5,
                                    gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
                                    workspace.data_ptr(), _stream()), "groupnorm")
     _count(2)
+
+
+def igemm_tiles_per_image(h, w):
+    return load().dl_igemm_tiles_per_image(h, w)
+
+
+def groupnorm_finalize(partial, stats, count):
+    """partial fp32 [nimg, slots, groups, 2] (sum, sumsq) -> stats fp32 [nimg, groups, 2] (mean, M2)."""
+    nimg, slots, groups, _ = partial.shape
+    _check(load().dl_groupnorm_finalize(partial.data_ptr(), nimg, slots, groups, int(count), stats.data_ptr(),
+                                        _stream()), "groupnorm_finalize")
+    _count()
 
 
 def groupnorm_split_workspace_bytes(nimg, groups=32):

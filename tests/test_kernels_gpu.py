@@ -337,3 +337,41 @@ def test_latent_pool8():
     ref = torch.frombuffer(bytearray(pooled_latent_bytes(lat)), dtype=torch.float16).view(1, 4, 8, 8)
     assert (out.cpu().float() - ref.float()).abs().max().item() < 1e-3
     assert len(out.cpu().numpy().tobytes()) == 512
+
+
+@pytest.mark.parametrize("B,H,W,C,N,res", [(2, 32, 32, 128, 128, True), (1, 64, 48, 64, 256, False),
+                                           (3, 16, 16, 256, 512, True), (2, 24, 48, 128, 128, False)])
+def test_igemm_groupnorm_partials(B, H, W, C, N, res):
+    """The conv epilogue's GroupNorm records of its own bf16 output (sum, sumsq per M tile and
+    group) -> dl_groupnorm_finalize -> (mean, M2) equal to statistics taken from the output
+    tensor itself, with and without the fused residual."""
+    lib = L()
+    G = 32
+    cpg = N // G
+    x = bf(rand(B, H, W, C, seed=1))
+    wt = bf(rand(N, 9 * C, seed=3, scale=(9 * C) ** -0.5))
+    bias = rand(N, seed=4)
+    r = bf(rand(B, H, W, N, seed=5)) if res else None
+    out = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    slots = lib.igemm_tiles_per_image(H, W)
+    assert slots > 0
+    part = torch.full((B, slots, G, 2), float("nan"), device=DEV)
+    lib.igemm(x, wt, out, nimg=B, h=H, w=W, taps=9, n=N, bias=bias, residual=r, gn_partial=part, gn_cpg=cpg)
+    stats = torch.empty(B, G, 2, device=DEV)
+    lib.groupnorm_finalize(part, stats, H * W * cpg)
+    torch.cuda.synchronize()
+    assert not torch.isnan(part).any()                       # every (slot, group) was written
+    o = out.float().view(B, H * W, G, cpg).permute(0, 2, 1, 3).reshape(B, G, -1).double()
+    mean = o.mean(-1)
+    m2 = ((o - mean[..., None]) ** 2).sum(-1)
+    assert torch.allclose(stats[..., 0].double(), mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[..., 1].double(), m2, rtol=1e-4, atol=1e-3)
+    # and the one-pass norm built on them matches the fused two-phase kernel
+    gw, gb = rand(N, seed=6), rand(N, seed=7)
+    a = torch.empty_like(out)
+    lib.groupnorm_apply(out, a, gw, gb, stats.unsqueeze(0), nimg=B, hw=H * W, groups=G, eps=1e-6, silu=True)
+    ws = torch.empty(lib.groupnorm_workspace_bytes(B, G), device=DEV, dtype=torch.uint8)
+    b = torch.empty_like(out)
+    lib.groupnorm(out, b, gw, gb, ws, nimg=B, hw=H * W, groups=G, eps=1e-6, silu=True)
+    torch.cuda.synchronize()
+    assert (a.float() - b.float()).abs().max().item() <= 0.0625
