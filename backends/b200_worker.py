@@ -126,6 +126,13 @@ class B200Worker(PipelineWorker):
         self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
                                     vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True)
         self._text = self._make_text_encoder(path)
+        # the attributes the reference's worker tests look for on `pipe` (`tests/test_sdxl_worker.py:127-130`)
+        towers = getattr(self._text, "models", None) or (getattr(self._text, "model", None),)
+        self.pipe.text_encoder = towers[0] if towers else None
+        if len(towers) > 1:
+            self.pipe.text_encoder_2 = towers[1]
+        elif self.pipe.is_sdxl:
+            self.pipe.text_encoder_2 = None
         self._load_styles({k: tuple(v.shape) for k, v in unet_sd.items()})
         print(f"[{self._tag}] worker {worker_id} loaded: {model_name} on {self.device} "
               f"(noise dtype={dtype_str}, compute bf16, styles={sorted(self._style_loaded)})")

@@ -206,18 +206,28 @@ def write_model_dir(path: str, unet_cfg=None, vae_cfg=None, seed: int = 0, dtype
     os.makedirs(os.path.join(path, "unet"), exist_ok=True)
     os.makedirs(os.path.join(path, "vae"), exist_ok=True)
     with open(os.path.join(path, "model_index.json"), "w") as f:
-        json.dump({"_class_name": "StableDiffusionPipeline", "unet": ["diffusers", "UNet2DConditionModel"],
+        sdxl = getattr(unet_cfg, "addition_embed_type", None) == "text_time"
+        json.dump({"_class_name": "StableDiffusionXLPipeline" if sdxl else "StableDiffusionPipeline",
+                   "unet": ["diffusers", "UNet2DConditionModel"],
                    "vae": ["diffusers", "AutoencoderKL"], "scheduler": ["diffusers", "LCMScheduler"]}, f)
     down = ["CrossAttnDownBlock2D" if a else "DownBlock2D" for a in unet_cfg.down_attn]
+    ucj = {"_class_name": "UNet2DConditionModel", "in_channels": unet_cfg.in_channels,
+           "out_channels": unet_cfg.out_channels,
+           "block_out_channels": list(unet_cfg.block_out_channels), "down_block_types": down,
+           "layers_per_block": unet_cfg.layers_per_block,
+           "cross_attention_dim": unet_cfg.cross_attention_dim,
+           "attention_head_dim": (list(unet_cfg.attention_head_dim)
+                                  if isinstance(unet_cfg.attention_head_dim, (tuple, list)) else unet_cfg.attention_head_dim),
+           "norm_num_groups": unet_cfg.norm_num_groups, "norm_eps": unet_cfg.norm_eps,
+           "time_cond_proj_dim": unet_cfg.time_cond_proj_dim}
+    if getattr(unet_cfg, "addition_embed_type", None):          # SDXL-class keys
+        ucj.update(transformer_layers_per_block=list(unet_cfg.transformer_layers_per_block),
+                   use_linear_projection=bool(unet_cfg.use_linear_projection),
+                   addition_embed_type=unet_cfg.addition_embed_type,
+                   addition_time_embed_dim=unet_cfg.addition_time_embed_dim,
+                   projection_class_embeddings_input_dim=unet_cfg.projection_class_embeddings_input_dim)
     with open(os.path.join(path, "unet", "config.json"), "w") as f:
-        json.dump({"_class_name": "UNet2DConditionModel", "in_channels": unet_cfg.in_channels,
-                   "out_channels": unet_cfg.out_channels,
-                   "block_out_channels": list(unet_cfg.block_out_channels), "down_block_types": down,
-                   "layers_per_block": unet_cfg.layers_per_block,
-                   "cross_attention_dim": unet_cfg.cross_attention_dim,
-                   "attention_head_dim": unet_cfg.attention_head_dim,
-                   "norm_num_groups": unet_cfg.norm_num_groups, "norm_eps": unet_cfg.norm_eps,
-                   "time_cond_proj_dim": unet_cfg.time_cond_proj_dim}, f)
+        json.dump(ucj, f)
     with open(os.path.join(path, "vae", "config.json"), "w") as f:
         json.dump({"_class_name": "AutoencoderKL", "latent_channels": vae_cfg.latent_channels,
                    "out_channels": vae_cfg.out_channels,
