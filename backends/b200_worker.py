@@ -187,9 +187,14 @@ class B200Worker(PipelineWorker):
     def _make_text_encoder(self, path):
         return _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
 
+    # one CUDA-graph replay per request batch (captured per (batch, size, steps) on first use; LRU
+    # of LCMPipelineB200.max_graphs geometries): at small batches the eager path is bound by
+    # launch latency, not by the GPU.  B200_CUDA_GRAPH=0 runs eagerly.
+    _use_graph = os.environ.get("B200_CUDA_GRAPH", "1").lower() not in ("0", "false", "no", "off")
+
     def _generate(self, prompts, lat, noise, steps, gs, height, width):
         pe = self._text.encode(prompts)
-        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True)
+        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, use_graph=self._use_graph)
 
     # ------------------------------------------------------------------ jobs
     def _parse(self, req):
@@ -213,9 +218,15 @@ class B200Worker(PipelineWorker):
         noise = [z.to(self.dtype).float() for z in noise]
         return lat, noise
 
+    supports_deferred = True      # run_batch(..., deferred=True) -> thunks (see WorkerPool)
+
     @torch.no_grad()
-    def run_batch(self, jobs: Sequence, with_latents: bool = False) -> List[tuple]:
-        """All jobs must share size / steps; guidance may differ per job."""
+    def run_batch(self, jobs: Sequence, with_latents: bool = False, deferred: bool = False) -> List:
+        """All jobs must share size / steps / style; guidance may differ per job.
+        deferred=True returns one zero-argument callable per job that PNG-encodes its image when
+        called: the pool runs them on encoder threads while this worker's thread already drives
+        the next batch on the GPU (PIL's ~20 ms per 512^2 image would otherwise cap a worker at
+        ~50 img/s)."""
         with torch.cuda.device(self.device):
             parsed = [self._parse(j.req) for j in jobs]
             width, height = parsed[0][0], parsed[0][1]
@@ -244,11 +255,18 @@ class B200Worker(PipelineWorker):
                 lib.latent_pool8(final, pooled)
                 pooled = pooled.cpu().numpy()
             img = img.cpu().numpy()
-        out = []
-        for i, (_, _, seed) in enumerate(parsed):
+
+        def finish(i):
+            seed = parsed[i][2]
             png = _encode_png(img[i])
-            out.append((png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed))
-        return out
+            return (png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed)
+
+        if deferred:
+            import functools
+            return [functools.partial(finish, i) for i in range(len(jobs))]
+        if len(jobs) == 1:
+            return [finish(0)]
+        return list(_encoders().map(finish, range(len(jobs))))      # PIL releases the GIL in zlib
 
     def run_job(self, job) -> Tuple[bytes, int]:
         return self.run_batch([job])[0]
@@ -274,7 +292,21 @@ class B200SDXLWorker(B200Worker):
 
     def _generate(self, prompts, lat, noise, steps, gs, height, width):
         pe, pooled = self._text.encode(prompts)
-        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, pooled_embeds=pooled)
+        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, pooled_embeds=pooled,
+                                  use_graph=self._use_graph)
+
+
+_ENCODERS = None
+
+
+def _encoders():
+    """Process-wide PNG encoder threads (shared by all workers and the pool)."""
+    global _ENCODERS
+    if _ENCODERS is None:
+        from concurrent.futures import ThreadPoolExecutor
+        n = int(os.environ.get("B200_PNG_THREADS", "0")) or min(16, os.cpu_count() or 4)
+        _ENCODERS = ThreadPoolExecutor(max_workers=n, thread_name_prefix="png")
+    return _ENCODERS
 
 
 def _encode_png(arr) -> bytes:

@@ -236,7 +236,15 @@ class WorkerPool:
         try:
             if worker is not None and type(job) is GenerationJob and _is_real_batcher(worker):
                 batch = self._take_batch(job, worker)
-            if len(batch) > 1:
+            if (worker is not None and type(job) is GenerationJob and _is_real_batcher(worker)
+                    and getattr(type(worker), "supports_deferred", False) is True):
+                # GPU pass here, PNG encoding on the encoder threads: this thread moves on to the
+                # next batch while the images of this one are still being compressed
+                thunks = worker.run_batch(batch, deferred=True)
+                from backends.b200_worker import _encoders
+                for j, th in zip(batch, thunks):
+                    _encoders().submit(_resolve, j, th)
+            elif len(batch) > 1:
                 results = worker.run_batch(batch)
                 for j, r in zip(batch, results):
                     if not j.fut.done():
@@ -319,6 +327,18 @@ class WorkerPool:
             if t.is_alive():
                 t.join(timeout=5.0)
         self._unload_current_worker()
+
+
+def _resolve(job, thunk):
+    """Encoder-thread side of a deferred result."""
+    try:
+        r = thunk()
+        if not job.fut.done():
+            job.fut.set_result(r)
+    except Exception as e:                                  # noqa: BLE001 - forwarded to the caller
+        logger.error("[WorkerPool] Job failed while encoding: %s", e, exc_info=True)
+        if not job.fut.done():
+            job.fut.set_exception(e)
 
 
 def _is_real_batcher(worker) -> bool:

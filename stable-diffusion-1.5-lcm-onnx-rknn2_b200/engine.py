@@ -611,12 +611,17 @@ class LCMPipelineB200:
         lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale)
         return self.vae.decode(lat, tiling=self.vae_tiling), lat
 
+    max_graphs = 12       # captured geometries kept per pipeline (each owns its activation pool)
+
     def graph_for(self, B, h, w, steps, cfg_scale=None) -> _StaticGraph:
         key = (B, h, w, steps, cfg_scale)
-        g = self._graphs.get(key)
+        g = self._graphs.pop(key, None)
         if g is None:
+            while len(self._graphs) >= self.max_graphs:          # least recently used goes first
+                self._graphs.pop(next(iter(self._graphs)))
             with torch.cuda.device(self.device):
-                g = self._graphs[key] = _StaticGraph(self, B, h, w, steps, cfg_scale)
+                g = _StaticGraph(self, B, h, w, steps, cfg_scale)
+        self._graphs[key] = g                                     # dict order = recency
         return g
 
     @torch.no_grad()

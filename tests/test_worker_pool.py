@@ -163,3 +163,48 @@ def test_singleton_first_call_wins():
     p2 = get_worker_pool(worker_factory=Mock(), mode_config=make_config(), registry=make_registry())
     assert p1 is p2
     reset_worker_pool()
+
+
+class DeferredWorker(FakeWorker):
+    """Worker offering deferred results (B200Worker.run_batch(..., deferred=True))."""
+    supports_deferred = True
+
+    def __init__(self, worker_id, encode_s=0.15):
+        super().__init__(worker_id)
+        self.encode_s = encode_s
+        self.gpu_done = []
+
+    def run_batch(self, jobs, with_latents=False, deferred=False):
+        with self.lock:
+            self.batches.append(len(jobs))
+            self.gpu_done.append(time.perf_counter())
+
+        def finish(j):
+            if j.req.prompt == "boom":
+                raise ValueError("encode failed")
+            time.sleep(self.encode_s)                      # PNG compression stand-in
+            return (f"png-{j.req.prompt}".encode(), self.worker_id)
+        if deferred:
+            import functools
+            return [functools.partial(finish, j) for j in jobs]
+        return [finish(j) for j in jobs]
+
+
+def test_deferred_png_encoding_overlaps_the_next_gpu_pass(pool_factory):
+    """the worker thread must not sit in PNG encoding.  Two incompatible
+    (different size) requests = two GPU passes; with deferred results the second pass starts
+    before the first one's encode has finished, and both futures resolve correctly."""
+    w = DeferredWorker(0, encode_s=0.3)
+    pool = pool_factory(worker_factory=lambda worker_id: w, num_workers=1, max_batch=16)
+    t0 = time.perf_counter()
+    f1 = pool.submit_job(GenerationJob(req=req("a", size="512x512")))
+    f2 = pool.submit_job(GenerationJob(req=req("b", size="768x768")))
+    assert f1.result(timeout=5) == (b"png-a", 0) and f2.result(timeout=5) == (b"png-b", 0)
+    total = time.perf_counter() - t0
+    assert len(w.gpu_done) == 2 and w.gpu_done[1] - w.gpu_done[0] < 0.25     # no wait for the encode
+    assert total < 0.55                                                      # 2 x 0.3 s encodes overlapped
+    # an exception raised on the encoder thread reaches the caller's future; the pool keeps serving
+    fb = pool.submit_job(GenerationJob(req=req("boom")))
+    with pytest.raises(ValueError, match="encode failed"):
+        fb.result(timeout=5)
+    assert pool.submit_job(GenerationJob(req=req("c"))).result(timeout=5) == (b"png-c", 0)
