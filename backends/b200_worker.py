@@ -316,11 +316,44 @@ def _encode_png(arr) -> bytes:
     return buf.getvalue()
 
 
+def _load_clip(te_dir: str, device: str):
+    """`text_encoder/` of a diffusers model dir -> on-device CLIP tower (dreamlab_b200.clip)."""
+    from safetensors.torch import load_file
+    from dreamlab_b200.clip import CLIPTextB200, clip_cfg_from_json
+    with open(os.path.join(te_dir, "config.json")) as f:
+        cfg = clip_cfg_from_json(json.load(f))
+    for name in ("model.safetensors", "model.fp16.safetensors"):
+        p = os.path.join(te_dir, name)
+        if os.path.exists(p):
+            return CLIPTextB200(load_file(p), cfg, device)
+    raise RuntimeError(f"no safetensors weights under {te_dir}")
+
+
+def _hash_tokens(prompts: List[str], eos: int = 49407, bos: int = 49406) -> torch.Tensor:
+    """Deterministic stand-in token ids when the model dir ships no tokenizer files (offline
+    fixtures): good for synthetic load, meaningless for real prompts."""
+    ids = torch.full((len(prompts), 77), eos, dtype=torch.long)
+    for i, p in enumerate(prompts):
+        ids[i, 0] = bos
+        for j, b in enumerate(p.encode("utf-8")[:75]):
+            ids[i, 1 + j] = (b * 193 + j * 7919) % bos
+    return ids
+
+
+def _seeded_embeds(prompts: List[str], dims, device):
+    out = [[] for _ in dims]
+    for p in prompts:
+        g = torch.Generator().manual_seed(int.from_bytes(p.encode("utf-8")[:7] or b"\0", "little"))
+        for o, shape in zip(out, dims):
+            o.append(torch.randn(1, *shape, generator=g))
+    return [torch.cat(o, 0).to(device) for o in out]
+
+
 class _TextEncoder:
-    """Prompt -> [B,77,D] embeddings.  The step *before* the hot path:
-    the stock `transformers` CLIP text tower is used as a library.  When the model directory
-    ships no tokenizer files (offline fixtures), token ids come from a deterministic hash of
-    the prompt bytes — good for synthetic load, meaningless for real prompts."""
+    """Prompt -> [B,77,D] embeddings: the step *before* the hot path, on
+    the device through `dreamlab_b200.clip.CLIPTextB200` when the model dir ships `text_encoder/`
+    (tokenisation is the stock `transformers` CLIPTokenizer, pure host code).  Without a text
+    tower (offline fixtures): seeded N(0,1) embeddings keyed by the prompt."""
 
     def __init__(self, model_dir: str, device: str, dim: int):
         self.device, self.dim = device, dim
@@ -328,70 +361,60 @@ class _TextEncoder:
         self.tokenizer = None
         te = os.path.join(model_dir, "text_encoder")
         if os.path.exists(os.path.join(te, "config.json")):
-            from transformers import CLIPTextModel
-            self.model = CLIPTextModel.from_pretrained(te, torch_dtype=torch.float16).to(device).eval()
+            self.model = _load_clip(te, device)
             tk = os.path.join(model_dir, "tokenizer")
             if os.path.exists(os.path.join(tk, "vocab.json")):
                 from transformers import CLIPTokenizer
                 self.tokenizer = CLIPTokenizer.from_pretrained(tk)
 
-    def _hash_tokens(self, prompts: List[str]) -> torch.Tensor:
-        ids = torch.full((len(prompts), 77), 49407, dtype=torch.long)
-        for i, p in enumerate(prompts):
-            ids[i, 0] = 49406
-            for j, b in enumerate(p.encode("utf-8")[:75]):
-                ids[i, 1 + j] = (b * 193 + j * 7919) % 49406
-        return ids
-
     @torch.no_grad()
     def encode(self, prompts: List[str]) -> torch.Tensor:
         if self.model is None:
-            # no text tower in the model dir: seeded N(0,1) embeddings keyed by the prompt
-            out = []
-            for p in prompts:
-                g = torch.Generator().manual_seed(int.from_bytes(p.encode("utf-8")[:7] or b"\0", "little"))
-                out.append(torch.randn(1, 77, self.dim, generator=g))
-            return torch.cat(out, 0).to(self.device)
+            return _seeded_embeds(prompts, [(77, self.dim)], self.device)[0]
         if self.tokenizer is not None:
             ids = self.tokenizer(prompts, padding="max_length", max_length=77, truncation=True,
                                  return_tensors="pt").input_ids
         else:
-            ids = self._hash_tokens(prompts)
-        return self.model(ids.to(self.device))[0].float()
+            ids = _hash_tokens(prompts)
+        return self.model.forward(ids)["last_hidden_state"].float()
 
 
 class _SDXLTextEncoder:
     """Prompt -> ([B,77,D] embeddings, [B,P] pooled) for SDXL: penultimate hidden states of
     `text_encoder` (CLIP-L, 768) and `text_encoder_2` (OpenCLIP-bigG, 1280) concatenated, pooled =
-    `text_encoder_2`'s projected embedding.  Stock `transformers` towers are
-    used as a library *before* the hot path; without them in the model dir (offline fixtures),
-    seeded N(0,1) embeddings keyed by the prompt."""
+    `text_encoder_2`'s projected embedding; both towers run on the device
+    (`dreamlab_b200.clip`).  Without them in the model dir (offline fixtures): seeded N(0,1)
+    embeddings keyed by the prompt."""
 
     def __init__(self, model_dir: str, device: str, dim: int, pooled_dim: int):
         self.device, self.dim, self.pooled_dim = device, dim, pooled_dim
         self.models = None
+        self.tokenizers = (None, None)
         te1, te2 = os.path.join(model_dir, "text_encoder"), os.path.join(model_dir, "text_encoder_2")
         if os.path.exists(os.path.join(te1, "config.json")) and os.path.exists(os.path.join(te2, "config.json")):
-            from transformers import CLIPTextModel, CLIPTextModelWithProjection, CLIPTokenizer
-            self.models = (CLIPTextModel.from_pretrained(te1, torch_dtype=torch.float16).to(device).eval(),
-                           CLIPTextModelWithProjection.from_pretrained(te2, torch_dtype=torch.float16).to(device).eval())
-            self.tokenizers = tuple(CLIPTokenizer.from_pretrained(os.path.join(model_dir, t))
-                                    for t in ("tokenizer", "tokenizer_2"))
+            self.models = (_load_clip(te1, device), _load_clip(te2, device))
+            toks = []
+            for t in ("tokenizer", "tokenizer_2"):
+                tk = os.path.join(model_dir, t)
+                if os.path.exists(os.path.join(tk, "vocab.json")):
+                    from transformers import CLIPTokenizer
+                    toks.append(CLIPTokenizer.from_pretrained(tk))
+                else:
+                    toks.append(None)
+            self.tokenizers = tuple(toks)
 
     @torch.no_grad()
     def encode(self, prompts: List[str]):
         if self.models is None:
-            pe, pooled = [], []
-            for p in prompts:
-                g = torch.Generator().manual_seed(int.from_bytes(p.encode("utf-8")[:7] or b"\0", "little"))
-                pe.append(torch.randn(1, 77, self.dim, generator=g))
-                pooled.append(torch.randn(1, self.pooled_dim, generator=g))
-            return torch.cat(pe, 0).to(self.device), torch.cat(pooled, 0).to(self.device)
+            return tuple(_seeded_embeds(prompts, [(77, self.dim), (self.pooled_dim,)], self.device))
         hs, pooled = [], None
         for tok, m in zip(self.tokenizers, self.models):
-            ids = tok(prompts, padding="max_length", max_length=77, truncation=True,
-                      return_tensors="pt").input_ids.to(self.device)
-            out = m(ids, output_hidden_states=True)
-            hs.append(out.hidden_states[-2].float())
-            pooled = out[0].float()          # the last tower's projected pooled embedding
+            if tok is not None:
+                ids = tok(prompts, padding="max_length", max_length=77, truncation=True,
+                          return_tensors="pt").input_ids
+            else:
+                ids = _hash_tokens(prompts, eos=m.cfg.vocab_size - 1, bos=m.cfg.vocab_size - 2)
+            out = m.forward(ids, want_hidden=-2)
+            hs.append(out["hidden"].float())
+            pooled = out.get("text_embeds", out["pooler_output"]).float()   # the last tower's pooled embedding
         return torch.cat(hs, -1), pooled

@@ -130,7 +130,7 @@ int dl_layernorm(const void* x, long long rows, int c, float eps, const float* g
  * impl: DL_ATTN_TC = tcgen05 flash kernel (product path), DL_ATTN_SIMT = CUDA-core checker.
  * v_ones = 1: column d of every V head holds 1.0 (per-head stride >= ceil16(d+1)); the PV MMA
  * then accumulates the softmax denominator on the tensor core instead of the CUDA cores.       */
-enum { DL_ATTN_TC = 0, DL_ATTN_SIMT = 1 };
+enum { DL_ATTN_TC = 0, DL_ATTN_SIMT = 1, DL_ATTN_SIMT_CAUSAL = 2 /* keys <= query: CLIP text tower */ };
 int dl_attention(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                  long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                  int skv, int heads, int d, float scale, int impl, int v_ones, void* stream);
@@ -175,6 +175,14 @@ typedef struct dl_lcm_coeffs {
 } dl_lcm_coeffs;
 int dl_lcm_step(const float* eps, const float* x, const float* noise, float* x_next,
                 float* denoised, long long n, const dl_lcm_coeffs* coeffs /* host */, void* stream);
+
+/* ---- CLIP text tower pieces (the step before the hot path: diffusers `encode_prompt` ->
+ * transformers CLIPTextModel) ------------------------------------------------
+ * out[i, :] = bf16(tok_emb[ids[i], :] + pos_emb[i % seq, :]);  dl_act_bf16 mode 0 = quick_gelu
+ * x*sigmoid(1.702x) (CLIP-L), 1 = exact GELU (OpenCLIP bigG), elementwise over n bf16 values.    */
+int dl_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_emb, int n, int seq,
+                    int vocab, int dim, void* out, void* stream);
+int dl_act_bf16(const void* x, void* out, long long n, int mode, void* stream);
 
 /* ---- tiled VAE decode (`pipe.vae.enable_tiling()`, reference `backends/cuda_worker.py:91`;
  * diffusers AutoencoderKL.tiled_decode / blend_v / blend_h) -----------------

@@ -23,7 +23,7 @@ namespace dl {
 
 int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                      long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
-                     int skv, int heads, int d, float scale, cudaStream_t stream);
+                     int skv, int heads, int d, float scale, int causal, cudaStream_t stream);
 
 constexpr int AT_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_TILE = 128;                 // queries per CTA and keys per KV tile
@@ -626,9 +626,9 @@ extern "C" int dl_attention(const void* q, long long ldq, const void* k, long lo
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DL_CHECK_ARG(q && k && v && out, "attention: null pointer");
   DL_CHECK_ARG(batch > 0 && sq > 0 && skv > 0 && heads > 0 && d > 0, "attention: bad dims");
-  if (impl == DL_ATTN_SIMT)
+  if (impl == DL_ATTN_SIMT || impl == DL_ATTN_SIMT_CAUSAL)
     return attn_simt_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d,
-                            scale, stream);
+                            scale, impl == DL_ATTN_SIMT_CAUSAL ? 1 : 0, stream);
   DL_CHECK_ARG(impl == DL_ATTN_TC, "attention: unknown impl %d", impl);
   return attn_tc_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d,
                         scale, v_ones, stream);

@@ -15,7 +15,7 @@ attn_simt_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
                  const __nv_bfloat16* __restrict__ k, long long ldk,
                  const __nv_bfloat16* __restrict__ v, long long ldv, int dh_stride,
                  __nv_bfloat16* __restrict__ out, long long ldo, int sq, int skv, int d,
-                 float scale) {
+                 float scale, int causal) {
   extern __shared__ float sm[];
   const int dp = d + 1;                          // padded row: conflict-free column reads
   float* sK = sm;                                // [32][dp]
@@ -44,8 +44,9 @@ attn_simt_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
     __syncthreads();
     float s = 0.f;
     for (int i = 0; i < d; ++i) s += sQ[warp * d + i] * sK[lane * dp + i];
-    if (k0 + lane >= skv) s = -INFINITY;
+    if (k0 + lane >= skv || (causal && k0 + lane > qi)) s = -INFINITY;   // causal: keys <= query
     const float m_new = fmaxf(m, warp_max(s));
+    if (m_new == -INFINITY) continue;                    // a whole key block in the masked future
     const float p = __expf(s - m_new);
     const float corr = __expf(m - m_new);
     l = l * corr + warp_sum(p);
@@ -74,7 +75,7 @@ attn_simt_kernel(const __nv_bfloat16* __restrict__ q, long long ldq,
 
 int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                      long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
-                     int skv, int heads, int d, float scale, cudaStream_t stream) {
+                     int skv, int heads, int d, float scale, int causal, cudaStream_t stream) {
   DL_CHECK_ARG(d <= SA_MAXD, "attention(simt): d=%d exceeds %d", d, SA_MAXD);
   const size_t smem = (size_t)(2 * SA_KEYS * (d + 1) + SA_WARPS * d) * sizeof(float);
   static bool attr_set[64] = {false};
@@ -88,7 +89,7 @@ int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk,
   attn_simt_kernel<<<grid, SA_WARPS * 32, smem, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(q), ldq, reinterpret_cast<const __nv_bfloat16*>(k), ldk,
       reinterpret_cast<const __nv_bfloat16*>(v), ldv, dh_stride,
-      reinterpret_cast<__nv_bfloat16*>(out), ldo, sq, skv, d, scale);
+      reinterpret_cast<__nv_bfloat16*>(out), ldo, sq, skv, d, scale, causal);
   return check_launch("attention(simt)");
 }
 

@@ -227,6 +227,54 @@ __global__ void lcm_step_kernel(const float4* __restrict__ eps, const float4* __
   }
 }
 
+// ---- CLIP text tower pieces (transformers CLIPTextModel: embeddings, MLP activation) -----------
+// out[i, :] = bf16( tok[ids[i], :] + pos[i % seq, :] ), 8 channels per thread
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const __nv_bfloat16* __restrict__ tok,
+                                    const __nv_bfloat16* __restrict__ pos, int n, int seq, int vocab, int V,
+                                    uint4* __restrict__ out) {
+  const long long total = (long long)n * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const int r = (int)(i / V);
+    long long id = ids[r];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(tok + id * (long long)V * 8) + v);
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + (long long)(r % seq) * V * 8) + v);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_bf16x2(aw[j]), fb = unpack_bf16x2(bw[j]);
+      o[j] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// mode 0: quick_gelu x * sigmoid(1.702 x) (CLIP-L);  mode 1: exact (erf) GELU (OpenCLIP bigG)
+__global__ void act_bf16_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, long long n8, int mode) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = x[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = unpack_bf16x2(w[j]);
+      if (mode == 0) {
+        f.x = f.x / (1.0f + __expf(-1.702f * f.x));
+        f.y = f.y / (1.0f + __expf(-1.702f * f.y));
+      } else {
+        f.x = 0.5f * f.x * (1.0f + erff(f.x * 0.70710678118654752f));
+        f.y = 0.5f * f.y * (1.0f + erff(f.y * 0.70710678118654752f));
+      }
+      o[j] = pack_bf16x2(f.x, f.y);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---- tiled VAE decode (diffusers AutoencoderKL.tiled_decode: blend_v / blend_h / crop) ----------
 // b[n, y, x, :] (y < extent) = a[n, ha - extent + y, x, :] * (1 - y/extent) + b[n, y, x, :] * (y/extent)
 // vertical = 1 blends along rows (a above b, same width), 0 along columns (a left of b, same height)
@@ -403,6 +451,23 @@ extern "C" int dl_lcm_step(const float* eps, const float* x, const float* noise,
       reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(x_next),
       reinterpret_cast<float4*>(denoised), n / 4, *k);
   return check_launch("lcm_step");
+}
+
+extern "C" int dl_embed_tokens(const long long* ids, const void* tok_emb, const void* pos_emb, int n, int seq,
+                               int vocab, int dim, void* out, void* stream_) {
+  DL_CHECK_ARG(ids && tok_emb && pos_emb && out && n > 0 && seq > 0 && vocab > 0 && dim % 8 == 0,
+               "embed_tokens: bad args");
+  embed_tokens_kernel<<<grid_for((long long)n * (dim / 8), 256), 256, 0, STREAM>>>(
+      ids, reinterpret_cast<const __nv_bfloat16*>(tok_emb), reinterpret_cast<const __nv_bfloat16*>(pos_emb), n, seq,
+      vocab, dim / 8, reinterpret_cast<uint4*>(out));
+  return check_launch("embed_tokens");
+}
+
+extern "C" int dl_act_bf16(const void* x, void* out, long long n, int mode, void* stream_) {
+  DL_CHECK_ARG(x && out && n % 8 == 0 && (mode == 0 || mode == 1), "act_bf16: bad args");
+  act_bf16_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(reinterpret_cast<const uint4*>(x),
+                                                           reinterpret_cast<uint4*>(out), n / 8, mode);
+  return check_launch("act_bf16");
 }
 
 extern "C" int dl_tile_blend(const float* a, float* b, int nimg, int ha, int wa, int hb, int wb, int c,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdreamlab_b200.so")
 
 EPI_BF16, EPI_GEGLU, EPI_F32, EPI_U8_IMAGE = 0, 1, 2, 3
-ATTN_TC, ATTN_SIMT = 0, 1
+ATTN_TC, ATTN_SIMT, ATTN_SIMT_CAUSAL = 0, 1, 2
 
 EXPORTS = [
     "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_fill_identity",
@@ -25,7 +25,7 @@ EXPORTS = [
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
     "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8", "dl_igemm_tiles_per_image",
-    "dl_groupnorm_finalize",
+    "dl_groupnorm_finalize", "dl_embed_tokens", "dl_act_bf16",
 ]
 
 
@@ -112,6 +112,9 @@ def load() -> C.CDLL:
                                                 C.c_void_p]
             lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_embed_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+            lib.dl_act_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
             lib.dl_tile_blend.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_int, C.c_void_p]
             lib.dl_image_crop_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -409,6 +412,18 @@ def lcm_step(eps, x, noise, x_next, denoised, coeffs):
     k = LcmCoeffs(*[float(v) for v in coeffs])
     _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
                               denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def embed_tokens(ids, tok_emb, pos_emb, out, seq):
+    """ids int64 [n]; tok_emb bf16 [V, D]; pos_emb bf16 [seq, D]; out bf16 [n, D]."""
+    _check(load().dl_embed_tokens(ids.data_ptr(), tok_emb.data_ptr(), pos_emb.data_ptr(), ids.numel(), seq,
+                                  tok_emb.shape[0], tok_emb.shape[1], out.data_ptr(), _stream()), "embed_tokens")
+    _count()
+
+
+def act_bf16(x, out, mode):
+    _check(load().dl_act_bf16(x.data_ptr(), out.data_ptr(), x.numel(), mode, _stream()), "act_bf16")
     _count()
 
 

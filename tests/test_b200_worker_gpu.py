@@ -160,3 +160,45 @@ def test_style_lora_levels_and_reset(tmp_path):
     pe = w._text.encode(["a cat"])
     img = ref.generate(pe, lat, torch.stack(noise), 2, torch.tensor([1.0])).cpu().numpy()[0].astype(int)
     assert np.abs(img - lvl2).max() <= 2, np.abs(img - lvl2).max()
+
+
+def test_worker_runs_its_text_tower_on_the_device(tmp_path):
+    """A model dir with `text_encoder/` (transformers layout): the worker encodes prompts with the
+    on-device CLIP tower (no `transformers` model in the request path) and the embeddings match
+    transformers' CLIPTextModel on the same ids."""
+    from safetensors.torch import save_file
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from dreamlab_b200 import synthetic as S
+    from dreamlab_b200.clip import CLIPTextB200
+    from backends.b200_worker import B200Worker, _hash_tokens
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    root = tmp_path / "models"
+    ucfg = UNetConfig.tiny()
+    ucfg.cross_attention_dim = 768
+    mdir = S.write_model_dir(str(root / "tiny-lcm"), ucfg, VAEConfig.tiny())
+    torch.manual_seed(0)
+    ccfg = CLIPTextConfig(hidden_size=768, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=12)
+    clip = CLIPTextModel(ccfg).eval()
+    os.makedirs(os.path.join(mdir, "text_encoder"))
+    with open(os.path.join(mdir, "text_encoder", "config.json"), "w") as f:
+        f.write(ccfg.to_json_string())
+    save_file({k: v.contiguous() for k, v in clip.state_dict().items()},
+              os.path.join(mdir, "text_encoder", "model.safetensors"))
+    old = {k: os.environ.get(k) for k in ("MODEL_ROOT", "MODEL")}
+    os.environ.update(MODEL_ROOT=str(root), MODEL="tiny-lcm")
+    try:
+        w = B200Worker(worker_id=0)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert isinstance(w._text.model, CLIPTextB200) and w.pipe.text_encoder is w._text.model
+    prompts = ["a cat", "a much longer prompt about mountains, rivers and a small red house"]
+    got = w._text.encode(prompts).cpu()
+    with torch.no_grad():
+        ref = clip(_hash_tokens(prompts)).last_hidden_state
+    err = ((got - ref).abs().max() / ref.abs().max()).item()
+    assert err <= 2e-2, err
+    a, b = w.run_job(job(prompt=prompts[0], seed=3)), w.run_job(job(prompt=prompts[1], seed=3))
+    assert a[0][:4] == b"\x89PNG" and a[0] != b[0]                   # the prompt conditions the image
+    assert w.run_job(job(prompt=prompts[0], seed=3))[0] == a[0]
