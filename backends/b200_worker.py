@@ -221,7 +221,8 @@ class B200Worker(PipelineWorker):
     supports_deferred = True      # run_batch(..., deferred=True) -> thunks (see WorkerPool)
 
     @torch.no_grad()
-    def run_batch(self, jobs: Sequence, with_latents: bool = False, deferred: bool = False) -> List:
+    def run_batch(self, jobs: Sequence, with_latents: bool = False, deferred: bool = False,
+                  raw: bool = False) -> List:
         """All jobs must share size / steps / style; guidance may differ per job.
         deferred=True returns one zero-argument callable per job that PNG-encodes its image when
         called: the pool runs them on encoder threads while this worker's thread already drives
@@ -258,6 +259,8 @@ class B200Worker(PipelineWorker):
 
         def finish(i):
             seed = parsed[i][2]
+            if raw:
+                return (img[i], seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (img[i], seed)
             png = _encode_png(img[i])
             return (png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed)
 
@@ -273,6 +276,12 @@ class B200Worker(PipelineWorker):
 
     def run_job_with_latents(self, job) -> Tuple[bytes, int, bytes]:
         return self.run_batch([job], with_latents=True)[0]
+
+    def run_job_array(self, job):
+        """Extension for callers that score pixels instead of shipping a file (the Yume dream
+        loop renders 64x64 1-step candidates through `run_job` and immediately decodes the PNG
+        again, `yume/dream_worker.py:294-299`): -> (uint8 HxWx3 array, seed), no PNG round trip."""
+        return self.run_batch([job], raw=True)[0]
 
 
 class B200SDXLWorker(B200Worker):

@@ -202,3 +202,17 @@ def test_worker_runs_its_text_tower_on_the_device(tmp_path):
     a, b = w.run_job(job(prompt=prompts[0], seed=3)), w.run_job(job(prompt=prompts[1], seed=3))
     assert a[0][:4] == b"\x89PNG" and a[0] != b[0]                   # the prompt conditions the image
     assert w.run_job(job(prompt=prompts[0], seed=3))[0] == a[0]
+
+
+def test_yume_style_quick_job(worker):
+    """The dream loop's candidates (`yume/dream_worker.py:262-299`): ad-hoc request objects without
+    `style_lora`, 64x64, ONE step; `run_job_array` returns the same pixels without the PNG round trip."""
+    import numpy as np
+    from PIL import Image
+    req = SimpleNamespace(prompt="dream of electric sheep", size="64x64", num_inference_steps=1,
+                          guidance_scale=1.0, seed=11)                 # no style_lora attribute
+    j = SimpleNamespace(req=req, fut=None, submitted_at=0.0)
+    png, seed = worker.run_job(j)
+    arr, seed2 = worker.run_job_array(j)
+    assert seed == seed2 == 11 and arr.shape == (64, 64, 3) and arr.dtype == np.uint8
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(png))), arr)
