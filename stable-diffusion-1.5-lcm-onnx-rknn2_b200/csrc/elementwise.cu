@@ -22,27 +22,36 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, int batch, int dim,
   out[(size_t)b * dim + half + k] = sinf(a);
 }
 
-// ---- out[m,n] = act_out(sum_k act_in(x[m,k]) w[n,k] + bias[n] + add[m,n]) ; one warp per n ----
-template <int MMAX>
+// ---- out[m,n] = act_out(sum_k act_in(x[m,k]) w[n,k] + bias[n] + add[m,n]) --------------------
+// One warp per NR consecutive output columns: the x chunk a lane loads (MMAX rows x 8 values) is
+// reused for NR weight rows, so the L1 traffic for x — 30x the weight bytes with one column per
+// warp — drops NR-fold; act_in is applied once per loaded value, not once per output column.
+template <int MMAX, int NR>
 __global__ void small_linear_kernel(const float* __restrict__ x, int m, int k,
                                     const __nv_bfloat16* __restrict__ w,
                                     const float* __restrict__ bias, const float* __restrict__ add,
                                     int n, int silu_in, int silu_out, float* __restrict__ out) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  float acc[MMAX];
+  const int n0 = warp * NR;
+  if (n0 >= n) return;
+  float acc[NR][MMAX];
 #pragma unroll
-  for (int i = 0; i < MMAX; ++i) acc[i] = 0.f;
-  const __nv_bfloat16* wr = w + (size_t)warp * k;
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int i = 0; i < MMAX; ++i) acc[r][i] = 0.f;
   for (int kk = lane * 8; kk < k; kk += 256) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(wr + kk));
-    const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-    float wf[8];
+    float wf[NR][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(ww[j]);
-      wf[2 * j] = f.x; wf[2 * j + 1] = f.y;
+    for (int r = 0; r < NR; ++r) {
+      const int row = min(n0 + r, n - 1);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(w + (size_t)row * k + kk));
+      const uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(ww[j]);
+        wf[r][2 * j] = f.x; wf[r][2 * j + 1] = f.y;
+      }
     }
 #pragma unroll
     for (int i = 0; i < MMAX; ++i) {
@@ -50,21 +59,28 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int m, int k,
         const float4 a0 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * k + kk));
         const float4 a1 = __ldg(reinterpret_cast<const float4*>(x + (size_t)i * k + kk + 4));
         float xv[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        if (silu_in) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xx = silu_in ? silu_f(xv[j]) : xv[j];
-          acc[i] += xx * wf[j];
+          for (int j = 0; j < 8; ++j) xv[j] = silu_f(xv[j]);
         }
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[r][i] += xv[j] * wf[r][j];
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < MMAX; ++i) {
-    const float s = warp_sum(acc[i]);
-    if (lane == 0 && i < m) {
-      float r = s + (bias ? bias[warp] : 0.f) + (add ? add[(size_t)i * n + warp] : 0.f);
-      if (silu_out) r = silu_f(r);
-      out[(size_t)i * n + warp] = r;
+  for (int r = 0; r < NR; ++r) {
+    const int col = n0 + r;
+#pragma unroll
+    for (int i = 0; i < MMAX; ++i) {
+      const float s = warp_sum(acc[r][i]);
+      if (lane == 0 && i < m && col < n) {
+        float v = s + (bias ? bias[col] : 0.f) + (add ? add[(size_t)i * n + col] : 0.f);
+        if (silu_out) v = silu_f(v);
+        out[(size_t)i * n + col] = v;
+      }
     }
   }
 }
@@ -378,11 +394,12 @@ extern "C" int dl_small_linear(const float* x, int m, int k, const void* w, cons
   DL_CHECK_ARG(k % 8 == 0, "small_linear: k=%d must be a multiple of 8", k);
   DL_CHECK_ARG(m >= 1 && m <= 64, "small_linear: m=%d must be in [1,64]", m);
   const int threads = 256;
-  const int blocks = (n * 32 + threads - 1) / threads;
+  constexpr int NR = 4;
+  const int blocks = (((n + NR - 1) / NR) * 32 + threads - 1) / threads;
   const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(w);
   for (int m0 = 0; m0 < m; m0 += 16) {
     const int mm = (m - m0) < 16 ? (m - m0) : 16;
-    small_linear_kernel<16><<<blocks, threads, 0, STREAM>>>(
+    small_linear_kernel<16, NR><<<blocks, threads, 0, STREAM>>>(
         x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
         silu_out, out + (size_t)m0 * n);
   }
