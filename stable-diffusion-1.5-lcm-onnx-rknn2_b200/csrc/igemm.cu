@@ -57,6 +57,9 @@ struct IgemmParams {
   signed char tdy[9], tdx[9];   // per-tap input offsets (3x3: -1..1; folded upsample: 2x2 phase taps)
   int N, BN, n_tiles, m_tiles;
   int stages, tmem_cols, acc_bufs;
+  int msub;              // M sub-tiles per CTA tile (1, or 2: two 128-pixel tiles share one weight
+                         // tile per k-block — narrow-N layers are bound by operand delivery, and a
+                         // second A tile doubles the MMA work per delivered B byte)
   void* out;
   long long ldo;
   const float* bias;
@@ -104,6 +107,10 @@ __device__ __forceinline__ void gn_chunk_partials(const float (&v)[64], bool val
   }
 }
 
+// MS: M sub-tiles per CTA tile, compile-time so that the one-sub-tile instance keeps its fully
+// uniform issue loops (a runtime MS turned the coordinate arrays into local memory and cost the
+// ordinary layers ~25 %)
+template <int MS>
 __global__ void __launch_bounds__(IGEMM_THREADS, 1)
 igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -111,7 +118,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   const int b_tile_bytes = p.BN * BK * 2;
-  const int stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  const int stage_bytes = MS * A_TILE_BYTES + b_tile_bytes;
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;         // 1024-aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES +
                                                EPI_GN_BYTES);
@@ -123,7 +130,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = ((p.m_tiles + MS - 1) / MS) * p.n_tiles;
   const int kc = p.kc0 + p.kc1;
   const int num_kb = p.taps * kc;
 
@@ -163,14 +170,18 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int n_blk = t % p.n_tiles;
-        int m = t / p.n_tiles;
-        const int tx = m % p.tiles_x;
-        m /= p.tiles_x;
-        const int ty = m % p.tiles_y;
-        const int tn = m / p.tiles_y;
-        const int x0 = tx << p.tw_log2;
-        const int y0 = ty << p.th_log2;
-        const int n0 = tn << (7 - p.tw_log2 - p.th_log2);
+        // coordinates of the MS sub-tiles (a sub-tile past m_tiles lies beyond the last image:
+        // its loads are zero fill, its stores are clipped)
+        int xs[MS], ys[MS], ns[MS];
+#pragma unroll
+        for (int u = 0; u < MS; ++u) {
+          int m = (t / p.n_tiles) * MS + u;
+          xs[u] = (m % p.tiles_x) << p.tw_log2;
+          m /= p.tiles_x;
+          ys[u] = (m % p.tiles_y) << p.th_log2;
+          ns[u] = (m / p.tiles_y) << (7 - p.tw_log2 - p.th_log2);
+        }
+        const int x0 = xs[0], y0 = ys[0], n0 = ns[0];
         int kb = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
           const int dy = p.tdy[tap] + p.in_row0;
@@ -178,13 +189,17 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           for (int c = 0; c < kc; ++c, ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
-            uint8_t* sb = sa + A_TILE_BYTES;
+            uint8_t* sb = sa + MS * A_TILE_BYTES;
             if (issuer) {
               mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-              if (c < p.kc0)
-                tma_load_4d(sa, &p.tmA0, &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
-              else
-                tma_load_4d(sa, &p.tmA1, &full_bar[stage], (c - p.kc0) * BK, x0 + dx, y0 + dy, n0);
+#pragma unroll
+              for (int u = 0; u < MS; ++u) {
+                if (c < p.kc0)
+                  tma_load_4d(sa + u * A_TILE_BYTES, &p.tmA0, &full_bar[stage], c * BK, xs[u] + dx, ys[u] + dy, ns[u]);
+                else
+                  tma_load_4d(sa + u * A_TILE_BYTES, &p.tmA1, &full_bar[stage], (c - p.kc0) * BK, xs[u] + dx,
+                              ys[u] + dy, ns[u]);
+              }
               tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * BK, n_blk * p.BN);
             }
             __syncwarp();
@@ -196,10 +211,12 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         for (int rc = 0; rc < p.res_chunks; ++rc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sb = sa + A_TILE_BYTES;
+          uint8_t* sb = sa + MS * A_TILE_BYTES;
           if (issuer) {
             mbar_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
-            tma_load_4d(sa, &p.tmR, &full_bar[stage], n_blk * p.BN + rc * BK, x0, y0, n0);
+#pragma unroll
+            for (int u = 0; u < MS; ++u)
+              tma_load_4d(sa + u * A_TILE_BYTES, &p.tmR, &full_bar[stage], n_blk * p.BN + rc * BK, xs[u], ys[u], ns[u]);
             tma_load_2d(sb, &p.tmI, &full_bar[stage], rc * BK, 0);
           }
           __syncwarp();
@@ -222,19 +239,26 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * MS * p.BN);
         for (int kb = 0; kb < num_kb + p.res_chunks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_base + (uint32_t)(stage * stage_bytes);
           const uint32_t a_lo = umma_desc_lo(sa);
-          const uint32_t b_lo = umma_desc_lo(sa + A_TILE_BYTES);
+          const uint32_t a1_lo = umma_desc_lo(sa + A_TILE_BYTES);
+          const uint32_t b_lo = umma_desc_lo(sa + MS * A_TILE_BYTES);
           if (issuer) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in 16-byte units
               umma_ss_lohi(d_tmem, a_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), desc_hi, idesc,
                            (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            if (MS == 2) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_ss_lohi(d_tmem + (uint32_t)p.BN, a1_lo + (uint32_t)(k * 2), b_lo + (uint32_t)(k * 2), desc_hi,
+                             idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
             umma_commit(&empty_bar[stage]);          // frees the smem slot when MMAs retire
           }
@@ -274,8 +298,11 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     const bool slab_rowadd = (p.rowadd != nullptr) && imgs_per_tile <= 2;
     int tile_iter = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tile_iter) {
-      const int n_blk = t % p.n_tiles;
-      int m = t / p.n_tiles;
+     const int n_blk = t % p.n_tiles;
+#pragma unroll 1
+     for (int sub = 0; sub < MS; ++sub) {
+      const bool last_sub = (sub == MS - 1);
+      int m = (t / p.n_tiles) * MS + sub;
       const int tx = m % p.tiles_x;
       m /= p.tiles_x;
       const int ty = m % p.tiles_y;
@@ -291,7 +318,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       // per-tile slab of (bias + time-embedding row add) in smem: [image-in-tile 0/1][256 cols].
       // Filled while the tile's MMAs are still running; the chunks then read it with
       // broadcast LDS instead of dependent global loads.
-      float* sl = slab + (tile_iter & 1) * 512;
+      float* sl = slab + ((tile_iter * MS + sub) & 1) * 512;
       for (int idx = et; idx < 512; idx += 256) {
         const int i = idx >> 8, c = idx & 255, col = col0 + c;
         float vs = 0.f;
@@ -306,9 +333,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
       const float* ra_row = (p.rowadd && !slab_rowadd && n < p.NIMG)
                                 ? p.rowadd + (long long)n * p.ld_rowadd : nullptr;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      if (sub == 0) mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * MS + sub) * p.BN);
       int c = half * step;
       while (c < p.BN) {
         const int c_group = c;
@@ -412,7 +439,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
           __syncwarp();
         }
-        if (c >= p.BN) {
+        if (c >= p.BN && last_sub) {
           // last TMEM read of this tile is done: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -452,12 +479,13 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
         }
       }
-      if (half * step >= p.BN) {
+      if (half * step >= p.BN && last_sub) {
         // this half owns no chunk of a narrow tile: still release the accumulator
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
+     }   // sub
       if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
     }
@@ -567,7 +595,14 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   if (d->mode == DL_EPI_GEGLU) DL_CHECK_ARG(bn % 64 == 0, "igemm: GEGLU needs bn %% 64 == 0 (got %d)", bn);
   p.BN = bn;
   p.n_tiles = (d->n + bn - 1) / bn;
-  const int stage_bytes = A_TILE_BYTES + bn * BK * 2;
+  // two M sub-tiles per CTA tile for narrow single-N-tile layers that still fill the GPU twice over
+  {
+    static int use_ms = -1;
+    if (use_ms < 0) { const char* e = getenv("DL_IGEMM_MSUB"); use_ms = e ? atoi(e) : 2; }
+    p.msub = (use_ms == 2 && bn <= 128 && (d->n + bn - 1) / bn == 1 && p.m_tiles >= 4 * sms &&
+              (d->mode == DL_EPI_BF16 || d->mode == DL_EPI_F32 || d->mode == DL_EPI_U8_IMAGE)) ? 2 : 1;
+  }
+  const int stage_bytes = p.msub * A_TILE_BYTES + bn * BK * 2;
   const int base_kb = d->taps * ((d->c0 + d->c1) / BK);
   p.epi_nbuf = (base_kb <= 20) ? 4 : 2;
   const int staging_bytes = 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES + EPI_GN_BYTES;
@@ -577,8 +612,8 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   const int num_kb = p.taps * (p.kc0 + p.kc1) + p.res_chunks;
   if (p.stages > num_kb && num_kb >= 2) p.stages = num_kb;
   DL_CHECK_ARG(p.stages >= 2, "igemm: not enough smem for 2 stages");
-  p.acc_bufs = (2 * bn <= 512) ? 2 : 1;
-  int cols = p.acc_bufs * bn;
+  p.acc_bufs = (2 * p.msub * bn <= 512) ? 2 : 1;
+  int cols = p.acc_bufs * p.msub * bn;
   p.tmem_cols = 32;
   while (p.tmem_cols < cols) p.tmem_cols <<= 1;
   p.out = d->out; p.ldo = d->ldo;
@@ -655,14 +690,17 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("igemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_tiles = ((p.m_tiles + p.msub - 1) / p.msub) * p.n_tiles;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  igemm_kernel<<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
+  if (p.msub == 2) igemm_kernel<2><<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
+  else igemm_kernel<1><<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
   return check_launch("igemm");
 }
 

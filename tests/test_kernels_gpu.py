@@ -101,6 +101,7 @@ def test_igemm_linear_epilogues():
     (2, 16, 16, 64, 0, 64), (1, 64, 64, 320, 0, 320), (3, 8, 8, 1280, 1280, 1280),
     (2, 32, 32, 640, 320, 640), (1, 24, 24, 128, 0, 128), (1, 96, 96, 64, 0, 128),
     (1, 128, 128, 256, 0, 128), (2, 12, 12, 64, 0, 64),
+    (2, 256, 256, 64, 0, 128), (1, 593, 128, 64, 0, 128), (1, 600, 128, 64, 64, 64),   # two M sub-tiles per CTA tile
 ])
 def test_igemm_conv3x3(B, H, W, C0, C1, N):
     lib = L()
@@ -375,3 +376,35 @@ def test_igemm_groupnorm_partials(B, H, W, C, N, res):
     lib.groupnorm(out, b, gw, gb, ws, nimg=B, hw=H * W, groups=G, eps=1e-6, silu=True)
     torch.cuda.synchronize()
     assert (a.float() - b.float()).abs().max().item() <= 0.0625
+
+
+def test_igemm_dual_subtile_residual_and_u8():
+    """Narrow-N layers big enough for the two-sub-tile mode (two 128-pixel tiles share a weight
+    tile): fused residual + GroupNorm partials, and the u8 image tail (N = 3), odd tile count."""
+    lib = L()
+    B, H, W, C, N = 1, 593, 128, 64, 128
+    x = bf(rand(B, H, W, C, seed=1))
+    wt = bf(rand(N, C, 3, 3, seed=3, scale=(9 * C) ** -0.5))
+    bias = rand(N, seed=4)
+    res = bf(rand(B, H, W, N, seed=6))
+    w_pack = wt.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+    slots = lib.igemm_tiles_per_image(H, W)
+    part = torch.full((B, slots, 32, 2), float("nan"), device=DEV)
+    lib.igemm(x, w_pack, out, nimg=B, h=H, w=W, taps=9, n=N, bias=bias, residual=res, gn_partial=part, gn_cpg=4)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1) + res.float()
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) < 1e-2
+    assert not torch.isnan(part).any()
+    tot = part.double().sum(1)                                  # [B, 32, 2]
+    o = out.float().view(B, H * W, 32, 4).double()
+    assert torch.allclose(tot[..., 0], o.sum((1, 3)), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(tot[..., 1], (o * o).sum((1, 3)), rtol=1e-4, atol=1e-2)
+    w3 = bf(rand(3, C, 3, 3, seed=8, scale=(9 * C) ** -0.5))
+    img = torch.empty(B, H, W, 3, device=DEV, dtype=torch.uint8)
+    lib.igemm(x, w3.permute(0, 2, 3, 1).reshape(3, 9 * C).contiguous(), img, nimg=B, h=H, w=W, taps=9, n=3,
+              bias=rand(3, seed=9), mode=lib.EPI_U8_IMAGE, ldo=3)
+    r3 = F.conv2d(x.float().permute(0, 3, 1, 2), w3.float(), rand(3, seed=9), padding=1).permute(0, 2, 3, 1)
+    r8 = (r3.bfloat16().float() * 0.5 + 0.5).clamp(0, 1) * 255
+    torch.cuda.synchronize()
+    assert (img.float() - r8).abs().max().item() <= 1.5
