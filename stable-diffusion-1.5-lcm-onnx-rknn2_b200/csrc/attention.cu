@@ -291,7 +291,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 &&
                       threadIdx.x == 64;
       if (tr) p.trace[j * 16 + 4] = clock64();
-      const int hc = p.kt >> 1;                                 // my columns: 64 / 48 / 32
+      const int hc = KT > 0 ? KT / 2 : (p.kt >> 1);            // my columns: 64 / 48 / 32 (compile-time when KT is)
       const int kbase = j * p.kt + ch * hc;
       const bool need_mask = (j * p.kt + p.kt > p.skv);         // only the last tile (warp-uniform)
       // my S columns -> registers with ONE TMEM round trip (loads in flight together); they
