@@ -17,7 +17,7 @@ from __future__ import annotations
 import io
 import json
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 

@@ -260,6 +260,32 @@ def run_b200(args):
                 "step_achieved_tflops": GFLOP_IMAGE * value / world / 1e3,
                 "step_frac": GFLOP_IMAGE * value / world / 1e3 / sustained,
                 "by_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        # the dominant HBM-bound kernel: one-pass GroupNorm(+SiLU) apply of the VAE decoder
+        # (algorithmic 4 B/element: bf16 read once + written once), against the measured copy rate
+        ga = prof.get("groupnorm_apply")
+        if ga and ga["ms"] > 0:
+            gbs = ga["bytes"] / (ga["ms"] / 1e3) / 1e9
+            roof["hbm_kernel"] = {"bound": "hbm", "kernel": "gn_apply_kernel (GroupNorm+SiLU, one pass)",
+                                  "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                  "launches": ga["n"], "ms": round(ga["ms"], 3)}
+
+    # ---- single-request latency (B = 1, one CUDA-graph replay), p50 over 30 replays ----
+    lat_b1 = None
+    if rank == 0:
+        pe1, l1, n1 = syn.synthetic_inputs(1, size, size, nsteps)
+        run1 = lambda: pipe.generate(pe1, l1, n1, nsteps, 1.0, use_graph=True)   # noqa: E731
+        for _ in range(3):
+            run1()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(30):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            run1()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        lat_b1 = statistics.median(ts)
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
@@ -282,6 +308,7 @@ def run_b200(args):
                        "batch_per_gpu": B, "global_batch": B * world, "l2": "flushed between timed iterations",
                        "cuda_graph": True, "parallelism": f"replicas x{world} (no collective)"},
             "p50_latency_ms_per_batch": statistics.median(step_ms),
+            "p50_latency_ms_single_image": lat_b1,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": gr.launches * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

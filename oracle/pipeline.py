@@ -13,7 +13,7 @@ oracle consume bit-identical randomness.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import numpy as np
 import torch

@@ -9,7 +9,7 @@ UNet `StableDiffusionXLPipeline` runs at `backends/cuda_worker.py:532` (config C
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Tuple
 
 import torch
