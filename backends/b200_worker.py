@@ -113,8 +113,8 @@ class B200Worker(PipelineWorker):
 
         self.device = _device_for(worker_id)
         # CUDA_DTYPE keeps its meaning for the *noise stream*: the reference draws latents and
-        # step noise in this dtype (fp16 default, `backends/cuda_worker.py:55-61`).  The kernels
-        # themselves compute in bf16 (fp32 accumulate) regardless.
+        # step noise in this dtype (fp16 default, `backends/cuda_worker.py:55-61`).  fp16 / bf16
+        # compute in bf16 (fp32 accumulate) on the tensor cores; fp32 runs the fp32 precision mode.
         dtype_str = os.environ.get("CUDA_DTYPE", "fp16").lower().strip()
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}.get(dtype_str, torch.float16)
         torch.cuda.set_device(self.device)
@@ -123,8 +123,11 @@ class B200Worker(PipelineWorker):
         vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
         # vae_tiling: the reference switches `pipe.vae.enable_tiling()` on unconditionally
         # (`backends/cuda_worker.py:91`, `:390`)
+        # CUDA_DTYPE=fp32 selects the fp32 precision mode (CUDA-core kernels, parity bar 1e-4);
+        # fp16 / bf16 both run the bf16 tcgen05 path
         self.pipe = LCMPipelineB200(unet_sd, unet_cfg_from_json(ucfg_json), vae_sd,
-                                    vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True)
+                                    vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True,
+                                    precision="fp32" if dtype_str == "fp32" else "bf16")
         self._text = self._make_text_encoder(path)
         # the attributes the reference's worker tests look for on `pipe` (`tests/test_sdxl_worker.py:127-130`)
         towers = getattr(self._text, "models", None) or (getattr(self._text, "model", None),)
@@ -135,7 +138,7 @@ class B200Worker(PipelineWorker):
             self.pipe.text_encoder_2 = None
         self._load_styles({k: tuple(v.shape) for k, v in unet_sd.items()})
         print(f"[{self._tag}] worker {worker_id} loaded: {model_name} on {self.device} "
-              f"(noise dtype={dtype_str}, compute bf16, styles={sorted(self._style_loaded)})")
+              f"(noise dtype={dtype_str}, compute {self.pipe.precision}, styles={sorted(self._style_loaded)})")
 
     # ------------------------------------------------------------------ styles
     def _load_styles(self, unet_shapes):

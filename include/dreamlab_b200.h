@@ -207,6 +207,28 @@ int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidanc
  * [nimg,c,8,8].  h, w multiples of 8.                                                         */
 int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16, void* stream);
 
+/* ---- fp32 precision mode (reference `CUDA_DTYPE=fp32`, `backends/cuda_worker.py:55-61`) --------
+ * The same operators with fp32 activations and weights on the CUDA cores (plain tiled kernels,
+ * accurate expf / erff): they exist for the parity bar of the fp32 pipeline (noise_pred within
+ * 1e-4), not for speed.  Same argument meaning as their bf16 namesakes; dl_igemm_f32 reads the
+ * same descriptor (a0/a1/wgt/residual/out are float; GroupNorm partials and clusters ignored;
+ * channels multiples of 16).                                                                   */
+int dl_igemm_f32(const dl_igemm_desc* desc, void* stream);
+int dl_groupnorm_f32(const float* x0, int c0, const float* x1, int c1, int nimg, int hw, int groups,
+                     float eps, const float* gamma, const float* beta, int apply_silu, float* out,
+                     void* stream);
+int dl_layernorm_f32(const float* x, long long rows, int c, float eps, const float* gamma,
+                     const float* beta, float* out, void* stream);
+int dl_attention_f32(const float* q, long long ldq, const float* k, long long ldk, const float* v,
+                     long long ldv, int dh_stride, float* out, long long ldo, int batch, int sq,
+                     int skv, int heads, int d, float scale, int causal, void* stream);
+int dl_pack_latent_f32(const float* x, long long npix, int cin, int cpad, float scale,
+                       const float* mat, const float* vec, float* out, void* stream);
+int dl_im2col_s2_f32(const float* x, int nimg, int h, int w, int c, float* cols, void* stream);
+int dl_softmax_rows_f32(const float* scores, long long rows, int cols, float* out, void* stream);
+int dl_small_linear_f32(const float* x, int m, int k, const float* w, const float* bias,
+                        const float* add, int n, int silu_in, int silu_out, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

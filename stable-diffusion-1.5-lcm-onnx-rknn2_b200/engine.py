@@ -42,10 +42,13 @@ class _Ctx:
     """Per-forward scratch: device, batch, the GroupNorm workspace and (patch-parallel runs)
     the strip communicator.  comm=None is the single-GPU path."""
 
-    def __init__(self, device, batch, comm=None, gn_fuse=0):
+    def __init__(self, device, batch, comm=None, gn_fuse=0, dt=BF16):
         self.device = device
         self.batch = batch
         self.comm = comm
+        self.dt = dt          # activation dtype: bf16 (tcgen05 path) or fp32 (precision mode, CUDA cores)
+        if dt != BF16:
+            gn_fuse = 0
         # > 0: convs emit GroupNorm partial statistics of their output for norms with this many
         # groups (VAE decoder: 4/8/16 channels per group line up with the epilogue's 32-column
         # chunks); the consumer norm then reads its input once instead of twice
@@ -61,8 +64,8 @@ class _Ctx:
                                            dtype=torch.uint8)
             self.gnx_ws = _gnx_ws[key]
 
-    def empty(self, *shape, dtype=BF16):
-        return torch.empty(*shape, device=self.device, dtype=dtype)
+    def empty(self, *shape, dtype=None):
+        return torch.empty(*shape, device=self.device, dtype=dtype or self.dt)
 
     def pad_rows(self, x):
         """Strip [B,h,W,C] -> Padded copy with exchanged halo rows."""
@@ -94,7 +97,7 @@ def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=li
     if halo:
         H -= 2
     if out is None:
-        out = ctx.empty(B, H, W, n_out, dtype=torch.float32 if mode == lib.EPI_F32 else BF16)
+        out = ctx.empty(B, H, W, n_out, dtype=torch.float32 if mode == lib.EPI_F32 else None)
     part = None
     if feeds_norm and ctx.gn_fuse and mode == lib.EPI_BF16 and not halo:
         part = _gn_request(ctx, B, n_out, lib.igemm_tiles_per_image(H, W))
@@ -114,7 +117,7 @@ def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, ou
     M = x.numel() // x.shape[-1]
     cols = out_cols if out_cols is not None else (n_out // 2 if mode == lib.EPI_GEGLU else n_out)
     if out is None:
-        out = ctx.empty(*lead, cols, dtype=torch.float32 if mode == lib.EPI_F32 else BF16)
+        out = ctx.empty(*lead, cols, dtype=torch.float32 if mode == lib.EPI_F32 else None)
     part = None
     if norm_rows_per_img and norm_rows_per_img % 128 == 0 and mode == lib.EPI_BF16 and M % norm_rows_per_img == 0:
         part = _gn_request(ctx, M // norm_rows_per_img, n_out, norm_rows_per_img // 128)
@@ -266,13 +269,22 @@ def upsample(ctx, x, p: Packed):
 # ------------------------------------------------------------------------------------------------
 # UNet
 # ------------------------------------------------------------------------------------------------
+def _dt_of(precision: str):
+    if precision not in ("bf16", "fp32"):
+        raise RuntimeError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+    return BF16 if precision == "bf16" else torch.float32
+
+
 class UNetB200:
-    def __init__(self, state_dict, cfg, device="cuda:0"):
+    def __init__(self, state_dict, cfg, device="cuda:0", precision="bf16"):
         lib.require_cuda()
         lib.load()
         self.device = torch.device(device)
         self.cfg = cfg
-        self.P = pack_unet(state_dict, cfg, self.device)
+        self.dt = _dt_of(precision)
+        from .weights import pack_dtype
+        with pack_dtype(self.dt):
+            self.P = pack_unet(state_dict, cfg, self.device)
         self.groups = getattr(cfg, "norm_num_groups", 32)
 
     @torch.no_grad()
@@ -280,8 +292,8 @@ class UNetB200:
         """Hoisted cross-attention K/V: per Transformer2DModel, one tensor per block.
         prompt_embeds [B,77,D]."""
         B, T, D = prompt_embeds.shape
-        ctx = _Ctx(self.device, B)
-        pe = prompt_embeds.to(self.device, BF16).contiguous().view(B * T, D)
+        ctx = _Ctx(self.device, B, dt=self.dt)
+        pe = prompt_embeds.to(self.device, self.dt).contiguous().view(B * T, D)
         return [[linear(ctx, pe, q["kv2_w"], q["kv2_b"], 2 * t["heads"] * t["hstride"])
                  for q in t["blocks"]] for t in self.P["transformers"]]
 
@@ -341,7 +353,7 @@ class UNetB200:
         P = self.P
         b0, H, W, Cin = latents_nhwc.shape
         B = b0 * repeat
-        ctx = _Ctx(self.device, B, comm)
+        ctx = _Ctx(self.device, B, comm, dt=self.dt)
         g = self.groups
         ch = self.cfg.block_out_channels
         kv_it = iter(kvs)
@@ -357,7 +369,7 @@ class UNetB200:
             hl = H // comm.world
             r0 = comm.rank * hl
             lo, hi = max(r0 - 1, 0), min(r0 + hl + 1, H)      # strip + halo rows inside the image
-            xp = torch.zeros(B, hl + 2, W, 64, device=self.device, dtype=BF16)
+            xp = torch.zeros(B, hl + 2, W, 64, device=self.device, dtype=self.dt)
             for r in range(repeat):
                 for i in range(b0):
                     lib.pack_latent(latents_nhwc[i, lo:hi], xp[r * b0 + i, lo - (r0 - 1):hi - (r0 - 1)], cin=Cin)
@@ -395,12 +407,15 @@ class UNetB200:
 # VAE decoder
 # ------------------------------------------------------------------------------------------------
 class VAEDecoderB200:
-    def __init__(self, state_dict, cfg, device="cuda:0"):
+    def __init__(self, state_dict, cfg, device="cuda:0", precision="bf16"):
         lib.require_cuda()
         lib.load()
         self.device = torch.device(device)
         self.cfg = cfg
-        self.P = pack_vae_decoder(state_dict, cfg, self.device)
+        self.dt = _dt_of(precision)
+        from .weights import pack_dtype
+        with pack_dtype(self.dt):
+            self.P = pack_vae_decoder(state_dict, cfg, self.device)
         self.groups = cfg.norm_num_groups
         import os
         self.fuse_gn_stats = os.environ.get("DL_VAE_GN_FUSE", "1") not in ("0", "false")
@@ -413,8 +428,8 @@ class VAEDecoderB200:
         hn2 = hn.view(B * S, C)
         qk = linear(ctx, hn2, a["qk_w"], a["qk_b"], 2 * C)                 # [B*S, 2C]
         o = ctx.empty(B * S, C)
-        if S % 64:
-            # ragged tiles of a tiled decode (token count not a multiple of the 64-deep GEMM K
+        if S % 64 or self.dt != BF16:
+            # fp32 precision mode, and ragged tiles of a tiled decode (token count not a multiple of the 64-deep GEMM K
             # chunk, e.g. a 29 x 29 corner tile): the CUDA-core flash kernel takes any length.
             # b_v is folded into the out-proj bias exactly as below (softmax rows sum to 1).
             v = linear(ctx, hn2, a["v_w"], None, C)
@@ -493,7 +508,7 @@ class VAEDecoderB200:
         P = self.P
         B, H, W, Cin = latents_nhwc.shape
         g = self.groups
-        ctx = _Ctx(self.device, B, gn_fuse=g if self.fuse_gn_stats else 0)
+        ctx = _Ctx(self.device, B, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt)
         ch = self.cfg.block_out_channels
         z = ctx.empty(B, H, W, 64)
         lib.pack_latent(latents_nhwc, z, cin=Cin, scale=1.0 / self.cfg.scaling_factor,
@@ -531,7 +546,7 @@ class _StaticGraph:
         ucfg = pipe.unet.cfg
         D = ucfg.cross_attention_dim
         Bc = 2 * B if cfg_scale is not None else B          # CFG: [uncond, cond] context rows
-        self.pe = torch.zeros(Bc, 77, D, device=dev, dtype=BF16)
+        self.pe = torch.zeros(Bc, 77, D, device=dev, dtype=pipe.dt)
         cd = ucfg.time_cond_proj_dim
         self.w_emb = torch.zeros(B, cd, device=dev, dtype=torch.float32) if cd else None
         self.add = None
@@ -566,12 +581,15 @@ class LCMPipelineB200:
     the UNet has no time_cond_proj — `StableDiffusionXLPipeline.__call__` behind reference
     `backends/cuda_worker.py:532`) share this loop."""
 
-    def __init__(self, unet_sd, unet_cfg, vae_sd, vae_cfg, device="cuda:0", vae_tiling: bool = False):
+    def __init__(self, unet_sd, unet_cfg, vae_sd, vae_cfg, device="cuda:0", vae_tiling: bool = False,
+                 precision: str = "bf16"):
         """vae_tiling: `pipe.vae.enable_tiling()` (the reference workers always switch it on,
         `backends/cuda_worker.py:91`): requests larger than the VAE's sample_size decode tiled."""
         self.device = torch.device(device)
-        self.unet = UNetB200(unet_sd, unet_cfg, device)
-        self.vae = VAEDecoderB200(vae_sd, vae_cfg, device)
+        self.precision = precision
+        self.dt = _dt_of(precision)
+        self.unet = UNetB200(unet_sd, unet_cfg, device, precision)
+        self.vae = VAEDecoderB200(vae_sd, vae_cfg, device, precision)
         self.vae_tiling = vae_tiling
         self._graphs = {}
 
@@ -708,7 +726,7 @@ class LCMPipelineB200:
                 g.graph.replay()
                 img, lat = g.img, g.final
             else:
-                pe = pe_all.to(self.device, BF16).contiguous()
+                pe = pe_all.to(self.device, self.dt).contiguous()
                 we = w_emb.to(self.device) if w_emb is not None else None
                 if add is not None:
                     add = (add[0].to(self.device), add[1].to(self.device))

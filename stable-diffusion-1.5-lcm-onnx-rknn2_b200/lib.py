@@ -26,6 +26,8 @@ EXPORTS = [
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
     "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8", "dl_igemm_tiles_per_image",
     "dl_groupnorm_finalize", "dl_embed_tokens", "dl_act_bf16",
+    "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
+    "dl_im2col_s2_f32", "dl_softmax_rows_f32", "dl_small_linear_f32",
 ]
 
 
@@ -112,6 +114,20 @@ def load() -> C.CDLL:
                                                 C.c_void_p]
             lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_igemm_f32.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+            lib.dl_groupnorm_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+            lib.dl_layernorm_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
+            lib.dl_attention_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
+                                             C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+            lib.dl_pack_latent_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_im2col_s2_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            lib.dl_softmax_rows_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+            lib.dl_small_linear_f32.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
             lib.dl_embed_tokens.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_void_p]
             lib.dl_act_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]
@@ -251,9 +267,10 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.bias = _ptr(bias)
     d.rowadd = _ptr(rowadd)
     d.ld_rowadd = rowadd.stride(0) if rowadd is not None else 0
+    f32 = a0.dtype == torch.float32          # fp32 precision mode: CUDA-core kernels, same descriptor
     d.residual = _ptr(residual)
     d.ldr = (residual.stride(-2) if ldr is None else ldr) if residual is not None else 0
-    d.identity = identity_matrix(residual.device).data_ptr() if residual is not None else None
+    d.identity = identity_matrix(residual.device).data_ptr() if (residual is not None and not f32) else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
     d.in_rows, d.in_row0 = in_rows, in_row0
     if gn_partial is not None:         # [nimg, slots, groups, 2] fp32
@@ -267,7 +284,10 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     with _timed("igemm", 2.0 * nimg * h * w * n * taps * (d.c0 + d.c1), nbytes,
                 tag=f"M={nimg * h * w} ({nimg}x{h}x{w}) N={n} K={taps}x{d.c0 + d.c1} mode={mode}"
                     f"{' +res' if residual is not None else ''}"):
-        _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
+        if f32:
+            _check(load().dl_igemm_f32(C.byref(d), _stream()), "igemm_f32")
+        else:
+            _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
     _count()
 
 
@@ -278,6 +298,11 @@ def groupnorm_workspace_bytes(nimg, groups=32):
 def groupnorm(x0, out, gamma, beta, workspace, *, nimg, hw, groups=32, eps=1e-5, silu=True, x1=None):
     c0 = x0.shape[-1]
     c1 = x1.shape[-1] if x1 is not None else 0
+    if x0.dtype == torch.float32:
+        _check(load().dl_groupnorm_f32(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps, gamma.data_ptr(),
+                                       beta.data_ptr(), int(silu), out.data_ptr(), _stream()), "groupnorm_f32")
+        _count()
+        return
     with _timed("groupnorm", 0.0, 4.0 * nimg * hw * (c0 + c1), tag=f"n={nimg} hw={hw} C={c0}+{c1}"):
         _check(load().dl_groupnorm(x0.data_ptr(), c0, _ptr(x1), c1, nimg, hw, groups, eps,
                                    gamma.data_ptr(), beta.data_ptr(), int(silu), out.data_ptr(),
@@ -327,6 +352,11 @@ def groupnorm_apply(x0, out, gamma, beta, stats_all, *, nimg, hw, groups=32, eps
 
 def layernorm(x, out, gamma, beta, eps=1e-5):
     rows = x.numel() // x.shape[-1]
+    if x.dtype == torch.float32:
+        _check(load().dl_layernorm_f32(x.data_ptr(), rows, x.shape[-1], eps, gamma.data_ptr(), beta.data_ptr(),
+                                       out.data_ptr(), _stream()), "layernorm_f32")
+        _count()
+        return
     with _timed("layernorm", 0.0, 4.0 * x.numel()):
         _check(load().dl_layernorm(x.data_ptr(), rows, x.shape[-1], eps, gamma.data_ptr(),
                                    beta.data_ptr(), out.data_ptr(), _stream()), "layernorm")
@@ -335,6 +365,12 @@ def layernorm(x, out, gamma, beta, eps=1e-5):
 
 def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ldv, ldo, scale,
               impl=ATTN_TC, v_ones=False):
+    if q.dtype == torch.float32:
+        _check(load().dl_attention_f32(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
+                                       out.data_ptr(), ldo, batch, sq, skv, heads, d, scale,
+                                       int(impl == ATTN_SIMT_CAUSAL), _stream()), "attention_f32")
+        _count()
+        return
     with _timed("attention", 4.0 * batch * heads * sq * skv * d,
                 tag=f"B={batch} Sq={sq} Skv={skv} h={heads} d={d}"):
         _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
@@ -352,6 +388,12 @@ def timestep_sinusoid(t, out):
 def small_linear(x, w, out, bias=None, add=None, silu_in=False, silu_out=False):
     m, k = x.shape
     n = w.shape[0]
+    if w.dtype == torch.float32:
+        _check(load().dl_small_linear_f32(x.data_ptr(), m, k, w.data_ptr(), _ptr(bias), _ptr(add), n,
+                                          int(silu_in), int(silu_out), out.data_ptr(), _stream()),
+               "small_linear_f32")
+        _count()
+        return
     _check(load().dl_small_linear(x.data_ptr(), m, k, w.data_ptr(), _ptr(bias), _ptr(add), n,
                                   int(silu_in), int(silu_out), out.data_ptr(), _stream()),
            "small_linear")
@@ -366,6 +408,11 @@ def upsample2x(x, out, *, nimg, h, w):
 
 
 def im2col_s2(x, cols, *, nimg, h, w):
+    if x.dtype == torch.float32:
+        _check(load().dl_im2col_s2_f32(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
+               "im2col_s2_f32")
+        _count()
+        return
     with _timed("im2col_s2", 0.0, 2.0 * x.numel() + 2.0 * cols.numel()):
         _check(load().dl_im2col_s2(x.data_ptr(), nimg, h, w, x.shape[-1], cols.data_ptr(), _stream()),
                "im2col_s2")
@@ -381,6 +428,11 @@ def im2col_s2_halo(x, cols, *, nimg, in_rows, in_row0, h, w):
 
 def pack_latent(x, out, *, cin, scale=1.0, mat=None, vec=None):
     npix = x.numel() // cin
+    if out.dtype == torch.float32:
+        _check(load().dl_pack_latent_f32(x.data_ptr(), npix, cin, out.shape[-1], scale, _ptr(mat), _ptr(vec),
+                                         out.data_ptr(), _stream()), "pack_latent_f32")
+        _count()
+        return
     _check(load().dl_pack_latent(x.data_ptr(), npix, cin, out.shape[-1], scale, _ptr(mat),
                                  _ptr(vec), out.data_ptr(), _stream()), "pack_latent")
     _count()
@@ -388,6 +440,11 @@ def pack_latent(x, out, *, cin, scale=1.0, mat=None, vec=None):
 
 def softmax_rows(scores, out):
     rows, cols = scores.shape
+    if out.dtype == torch.float32:
+        _check(load().dl_softmax_rows_f32(scores.data_ptr(), rows, cols, out.data_ptr(), _stream()),
+               "softmax_rows_f32")
+        _count()
+        return
     with _timed("softmax_rows", 0.0, 6.0 * scores.numel()):
         _check(load().dl_softmax_rows(scores.data_ptr(), rows, cols, out.data_ptr(), _stream()),
                "softmax_rows")

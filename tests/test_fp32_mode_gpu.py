@@ -1,0 +1,126 @@
+"""fp32 precision mode (reference `CUDA_DTYPE=fp32`, `backends/cuda_worker.py:55-61`): the parity
+protocol of BASELINE.json in fp32 — per-step noise_pred max-rel-err <= 1e-4 against the fp32
+oracle on the same seed, latents, prompt embeddings and random-init weights; scheduler bit-exact;
+image within one u8 step."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from test_pipeline_gpu import max_rel_err, psnr_u8
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4          # BASELINE.json north_star: max relative error, fp32 mode
+
+
+def test_tiny_pipeline_fp32_parity():
+    from oracle.pipeline import build_random_init, run_pipeline, synthetic_inputs
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from dreamlab_b200.engine import LCMPipelineB200
+    unet, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0", precision="fp32")
+    pe, lat, noise = synthetic_inputs(2, 128, 128, 4, ctx_dim=unet.cfg.cross_attention_dim)
+    rec_o, rec_c = {}, {}
+    ref = run_pipeline(unet, vae, pe, lat, noise, 4, 1.0, record=rec_o, tiling=False)
+    img = pipe.generate(pe, lat, noise, 4, 1.0, record=rec_c)
+    torch.cuda.synchronize()
+    errs = [max_rel_err(c.cpu(), o) for c, o in zip(rec_c["noise_pred"], rec_o["noise_pred"])]
+    d = np.abs(img.cpu().numpy().astype(int) - ref.astype(int))
+    print(f"fp32 mode, tiny: noise_pred max-rel-err per step {['%.2e' % e for e in errs]}  "
+          f"image max |d| {d.max()} PSNR {psnr_u8(img.cpu().numpy(), ref):.1f} dB")
+    assert max(errs) <= FP32_TOL, errs
+    assert d.max() <= 1
+    img2 = pipe.generate(pe, lat, noise, 4, 1.0, use_graph=True).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(img2, img)
+
+
+def test_full_arch_unet_fp32_forward_256():
+    """Full SD1.5-LCM UNet in fp32 mode, one forward at 256x256 (latent 32^2) against the oracle."""
+    from oracle.unet import UNetConfig
+    from oracle.pipeline import build_random_init, synthetic_inputs
+    from oracle.scheduler import guidance_scale_embedding
+    from dreamlab_b200.engine import UNetB200
+    unet, _ = build_random_init(UNetConfig(), None, seed=0)
+    eng = UNetB200(unet.state_dict(), unet.cfg, "cuda:0", precision="fp32")
+    pe, lat, _ = synthetic_inputs(1, 256, 256, 4)
+    w = guidance_scale_embedding(torch.zeros(1), 256)
+    with torch.no_grad():
+        ref = unet(lat, torch.tensor(999), pe, w)
+    kvs = eng.encode_context(pe)
+    temb = eng.time_embeddings([999], 1, w.cuda())[0]
+    x = lat.permute(0, 2, 3, 1).contiguous().cuda()
+    eps = eng.forward(x, temb, kvs).permute(0, 3, 1, 2)
+    torch.cuda.synchronize()
+    e = max_rel_err(eps.cpu(), ref)
+    print(f"fp32 mode, full-arch UNet 256^2: noise_pred max-rel-err {e:.3e}")
+    assert e <= FP32_TOL, e
+
+
+def test_tiny_sdxl_cfg_fp32_parity():
+    """SDXL topology + classifier-free guidance in fp32 mode."""
+    from oracle.pipeline import build_random_init, run_pipeline_sdxl, synthetic_inputs
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from dreamlab_b200.engine import LCMPipelineB200
+    ucfg = UNetConfig.tiny_sdxl()
+    unet, vae = build_random_init(ucfg, VAEConfig.tiny(), seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0", precision="fp32")
+    pe, lat, noise = synthetic_inputs(1, 128, 128, 2, ctx_dim=ucfg.cross_attention_dim)
+    pooled = torch.randn(1, 80, generator=torch.Generator().manual_seed(2))
+    rec_o, rec_c = {}, {}
+    run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, 2, 7.5, 128, 128, record=rec_o, output_type="latent")
+    pipe.generate(pe, lat, noise, 2, 7.5, record=rec_c, pooled_embeds=pooled)
+    torch.cuda.synchronize()
+    raw = [max_rel_err(c.cpu(), o) for c, o in zip(rec_c["noise_pred_raw"], rec_o["noise_pred_raw"])]
+    print(f"fp32 mode, tiny SDXL CFG 7.5: UNet output max-rel-err per step {['%.2e' % e for e in raw]}")
+    assert raw[0] <= FP32_TOL, raw
+    assert max(raw) <= 15 * FP32_TOL, raw      # later steps start from latents carrying the guided (x14) error
+
+
+def test_worker_cuda_dtype_fp32(tmp_path):
+    from dreamlab_b200 import synthetic as S
+    from backends.b200_worker import B200Worker
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from types import SimpleNamespace
+    ucfg = UNetConfig.tiny()
+    ucfg.cross_attention_dim = 768
+    S.write_model_dir(str(tmp_path / "m" / "tiny"), ucfg, VAEConfig.tiny())
+    old = {k: os.environ.get(k) for k in ("MODEL_ROOT", "MODEL", "CUDA_DTYPE")}
+    os.environ.update(MODEL_ROOT=str(tmp_path / "m"), MODEL="tiny", CUDA_DTYPE="fp32")
+    try:
+        w = B200Worker(worker_id=0)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+    assert w.dtype == torch.float32 and w.pipe.precision == "fp32"
+    j = SimpleNamespace(req=SimpleNamespace(prompt="a cat", size="128x128", num_inference_steps=2,
+                                            guidance_scale=1.0, seed=9))
+    a, b = w.run_job(j), w.run_job(j)
+    assert a[0][:4] == b"\x89PNG" and a == b
+
+
+def test_sd15_lcm_512_4step_fp32_vs_committed_golden():
+    """BASELINE config C1 (full SD1.5-LCM arch, 512x512, 4 steps, gs 1.0, B=1) in fp32 mode against
+    the oracle outputs committed in tests/golden/: every step within 1e-4, image within one u8 step."""
+    from oracle.pipeline import build_random_init, synthetic_inputs
+    from dreamlab_b200.engine import LCMPipelineB200
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sd15_lcm_512_4step.npz"))
+    unet, vae = build_random_init(seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0", precision="fp32")
+    pe, lat, noise = synthetic_inputs(1, 512, 512, 4)
+    rec = {}
+    img = pipe.generate(pe, lat, noise, 4, 1.0, record=rec)
+    torch.cuda.synchronize()
+    errs = [max_rel_err(rec["noise_pred"][i].cpu(), torch.from_numpy(g["noise_pred"][i])) for i in range(4)]
+    lerr = [max_rel_err(rec["latents"][i].cpu(), torch.from_numpy(g["latents"][i])) for i in range(4)]
+    d = np.abs(img.cpu().numpy().astype(int) - g["image"].astype(int))
+    print(f"fp32 mode, C1: noise_pred max-rel-err per step {['%.2e' % e for e in errs]}  latents "
+          f"{['%.2e' % e for e in lerr]}  image max |d| {d.max()}  ({(d > 0).mean() * 100:.3f} % of bytes differ)")
+    assert max(errs) <= FP32_TOL, errs
+    assert max(lerr) <= FP32_TOL, lerr
+    assert d.max() <= 1
