@@ -207,6 +207,17 @@ int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidanc
  * [nimg,c,8,8].  h, w multiples of 8.                                                         */
 int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16, void* stream);
 
+/* ---- all-gather over NVLink peer memory (SDXL patch parallel) ---------------
+ * One kernel: store the local message into slot `rank` of every peer's symmetric staging buffer
+ * (peer-mapped pointers stage_ptrs[r], two halves of nranks * slot_bytes each), publish an epoch in
+ * every peer's signal pad (flag_ptrs[r], >= nranks u32, zero-initialised), wait for all ranks and
+ * copy the gathered half to dst [nranks, nbytes].  `state`: 3 zero-initialised u32 in local device
+ * memory (epoch and two CTA counters); epochs advance on the device, so the call is CUDA-graph
+ * safe.  Every rank of the group must issue the same sequence of calls.                          */
+int dl_peer_allgather(const void* src, void* dst, long long nbytes, void* const* stage_ptrs,
+                      void* const* flag_ptrs, int nranks, int rank, long long slot_bytes, void* state,
+                      void* stream);
+
 /* ---- fp32 precision mode (reference `CUDA_DTYPE=fp32`, `backends/cuda_worker.py:55-61`) --------
  * The same operators with fp32 activations and weights on the CUDA cores (plain tiled kernels,
  * accurate expf / erff): they exist for the parity bar of the fp32 pipeline (noise_pred within

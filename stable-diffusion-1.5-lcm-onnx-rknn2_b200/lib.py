@@ -26,7 +26,7 @@ EXPORTS = [
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
     "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8", "dl_igemm_tiles_per_image",
     "dl_groupnorm_finalize", "dl_embed_tokens", "dl_act_bf16",
-    "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
+    "dl_peer_allgather", "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
     "dl_im2col_s2_f32", "dl_softmax_rows_f32", "dl_small_linear_f32",
 ]
 
@@ -114,6 +114,9 @@ def load() -> C.CDLL:
                                                 C.c_void_p]
             lib.dl_lcm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_longlong, C.POINTER(LcmCoeffs), C.c_void_p]
+            lib.dl_peer_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_void_p),
+                                              C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_longlong, C.c_void_p,
+                                              C.c_void_p]
             lib.dl_igemm_f32.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
             lib.dl_groupnorm_f32.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                              C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -469,6 +472,17 @@ def lcm_step(eps, x, noise, x_next, denoised, coeffs):
     k = LcmCoeffs(*[float(v) for v in coeffs])
     _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
                               denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def peer_allgather(src, dst, stage_ptrs, flag_ptrs, rank, slot_bytes, state):
+    """src: contiguous local message; dst: [R, *src.shape]; stage_ptrs / flag_ptrs: per-rank device
+    pointers (ints) of the symmetric staging buffers and signal pads."""
+    R = len(stage_ptrs)
+    sp = (C.c_void_p * R)(*stage_ptrs)
+    fp = (C.c_void_p * R)(*flag_ptrs)
+    _check(load().dl_peer_allgather(src.data_ptr(), dst.data_ptr(), src.numel() * src.element_size(), sp, fp, R,
+                                    rank, slot_bytes, state.data_ptr(), _stream()), "peer_allgather")
     _count()
 
 

@@ -92,6 +92,47 @@ class DistComm(StripComm):
         return out.view((self.world,) + tuple(x.shape))
 
 
+class PeerComm(StripComm):
+    """All-gathers as ONE kernel of ours over NVLink peer memory (`dl_peer_allgather`, csrc/peer.cu):
+    stores into every peer's symmetric staging buffer, epoch flags in the peers' signal pads, no
+    NCCL call and no pack / unpack kernels.  The buffers come from torch's symmetric-memory
+    allocator (plumbing: it only maps the same allocation into every rank of the group)."""
+
+    def __init__(self, group=None, slot_bytes: int = 16 << 20):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.slot_bytes = int(slot_bytes)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._stage = symm_mem.empty(2 * self.world * self.slot_bytes, dtype=torch.uint8, device=dev)
+        self._hdl = symm_mem.rendezvous(self._stage, self.group)
+        self._stage_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+        # our own epoch flags (one u32 per peer) in a second symmetric allocation: the handle's
+        # signal pads stay reserved for torch's barrier
+        self._flags = symm_mem.empty(64, dtype=torch.int32, device=dev)
+        self._flags.zero_()
+        self._fhdl = symm_mem.rendezvous(self._flags, self.group)
+        self._flag_ptrs = [int(p) for p in self._fhdl.buffer_ptrs]
+        self._state = torch.zeros(4, device=dev, dtype=torch.int32)
+        torch.cuda.synchronize(dev)
+        self._fhdl.barrier()                      # every rank's flags are zero before the first call
+        torch.cuda.synchronize(dev)
+
+    def all_gather(self, x):
+        from . import lib
+        x = x.contiguous()
+        out = torch.empty((self.world,) + tuple(x.shape), device=x.device, dtype=x.dtype)
+        lib.peer_allgather(x, out, self._stage_ptrs, self._flag_ptrs, self.rank, self.slot_bytes, self._state)
+        return out
+
+    def halo_exchange(self, t):
+        """Rows 1 and h of t [B, h+2, W, C] go to the neighbours' rows h+1 / 0 — through the same
+        gather kernel (both boundary rows of every rank; neighbours pick theirs)."""
+        super().halo_exchange(t)
+
+
 class _ThreadHub:
     def __init__(self, world: int):
         self.world = world
@@ -304,18 +345,25 @@ class PatchParallelDenoiser:
             return self.pipe.vae.decode(lat)
 
 
-def dist_denoiser(pipe, cfg: bool = True) -> "PatchParallelDenoiser":
+def dist_denoiser(pipe, cfg: bool = True, peer: bool = False) -> "PatchParallelDenoiser":
     """PatchParallelDenoiser over the default torch.distributed world: builds the two strip
-    groups of the CFG halves (every rank must call this: `new_group` is collective)."""
+    groups of the CFG halves (every rank must call this: `new_group` is collective).
+    peer=True: exchanges run as `dl_peer_allgather` kernels over NVLink peer memory instead of
+    NCCL all-gathers."""
     import torch.distributed as dist
-    world = DistComm()
-    groups = {}
+    make = PeerComm if peer else DistComm
+    world = make()
+    groups, comms = {}, {}
     if cfg and world.world % 2 == 0 and world.world > 2:
         topo = Topology(world.world, world.rank, True)
         for c in range(2):
             groups[c] = dist.new_group(topo.strip_ranks(c))
+        if peer:                                  # rendezvous is collective inside its group
+            comms[topo.cfg_index] = PeerComm(groups[topo.cfg_index])
 
     def factory(topo: Topology):
-        return DistComm(groups[topo.cfg_index])
+        if topo.cfg_index in comms:
+            return comms[topo.cfg_index]
+        return make(groups[topo.cfg_index])
 
     return PatchParallelDenoiser(pipe, world, factory)

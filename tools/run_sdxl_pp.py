@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny SDXL topology (debug)")
+    ap.add_argument("--peer", action="store_true", help="exchanges as dl_peer_allgather kernels (NVLink peer memory)")
+    ap.add_argument("--both", action="store_true", help="time NCCL and peer-memory exchanges in one process")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -61,9 +63,10 @@ def main():
     pe, lat, noise = syn.synthetic_inputs(1, a.size, a.size, a.steps, ctx_dim=ucfg.cross_attention_dim)
     pooled = torch.randn(1, pdim, generator=torch.Generator().manual_seed(2))
     pe, lat, noise, pooled = pe.to(dev), lat.to(dev), noise.to(dev), pooled.to(dev)
-    den = pp.dist_denoiser(pipe) if world > 1 else pp.PatchParallelDenoiser(pipe, pp.SingleComm())
+    den = pp.dist_denoiser(pipe, peer=a.peer) if world > 1 else pp.PatchParallelDenoiser(pipe, pp.SingleComm())
     out = {"config": f"SDXL-base arch (random-init) {a.size}x{a.size}, {a.steps} LCM steps, CFG {a.gs}, "
-                     f"1 image over {world} GPU(s)", "n_gpus": world, "load_s": round(load_s, 1)}
+                     f"1 image over {world} GPU(s)", "n_gpus": world, "load_s": round(load_s, 1),
+           "exchange": "dl_peer_allgather (NVLink peer memory)" if a.peer else "ncclAllGather"}
 
     def timed(fn, iters):
         ts = []
@@ -94,6 +97,18 @@ def main():
             key = "noise_pred_raw" if a.gs > 1 else "noise_pred"
             out["check_max_rel_err_vs_unsharded"] = [
                 float((x - y).abs().max() / y.abs().max()) for x, y in zip(rec[key], rec1[key])]
+    if a.both and world > 1:
+        # second denoiser on the same weights with the peer-memory exchanges: parity + timing
+        den_p = pp.dist_denoiser(pipe, peer=True)
+        rec_p = {}
+        den_p.denoise(pe, pooled, lat, noise, min(a.steps, 2), a.gs, record=rec_p)
+        rec_n = {}
+        den.denoise(pe, pooled, lat, noise, min(a.steps, 2), a.gs, record=rec_n)
+        torch.cuda.synchronize()
+        out["peer_vs_nccl_bit_identical"] = all(torch.equal(x, y) for x, y in zip(rec_p["noise_pred"], rec_n["noise_pred"]))
+        den_p.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=not a.no_graph)
+        torch.cuda.synchronize()
+        log("peer capture done")
     use_graph = not a.no_graph
     log(f"warm-up / capture (graph={use_graph})")
     try:
@@ -113,6 +128,10 @@ def main():
     if world > 1:
         ms_e = timed(lambda: den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=False), 1)
         out["ms_per_image_denoise_eager"] = round(ms_e, 2)
+    if a.both and world > 1:
+        ms_p = timed(lambda: den_p.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph), a.iters)
+        out["ms_per_image_denoise_peer_exchange"] = round(ms_p, 2)
+        out["ms_per_unet_step_peer_exchange"] = round(ms_p / a.steps, 3)
     log("sharded timing done")
     if rank == 0:
         # un-sharded reference timing of the same loop on one GPU (graph replay)
