@@ -124,3 +124,54 @@ def test_sd15_lcm_512_4step_fp32_vs_committed_golden():
     assert max(errs) <= FP32_TOL, errs
     assert max(lerr) <= FP32_TOL, lerr
     assert d.max() <= 1
+
+
+def _bf16_vs_fp32(unet_cfg, vae_cfg, B, size, steps, gs, sdxl=False, seed=0):
+    """Both precisions of the engine on the same random-init weights and inputs (no CPU oracle:
+    sizes the oracle cannot finish in test time).  The fp32 mode is itself pinned to the oracle
+    at 2e-6..7e-6 above, so it stands in for it here."""
+    from dreamlab_b200 import synthetic as syn
+    from dreamlab_b200.engine import LCMPipelineB200
+    usd = syn.random_state_dict(syn.unet_shapes(unet_cfg), seed)
+    vsd = syn.random_state_dict(syn.vae_decoder_shapes(vae_cfg), seed + 1)
+    pe, lat, noise = syn.synthetic_inputs(B, size, size, steps, ctx_dim=unet_cfg.cross_attention_dim)
+    kw = {}
+    if sdxl:
+        pdim = unet_cfg.projection_class_embeddings_input_dim - 6 * unet_cfg.addition_time_embed_dim
+        kw["pooled_embeds"] = torch.randn(B, pdim, generator=torch.Generator().manual_seed(2))
+    recs, imgs = [], []
+    for prec in ("fp32", "bf16"):
+        pipe = LCMPipelineB200(usd, unet_cfg, vsd, vae_cfg, "cuda:0", precision=prec)
+        rec = {}
+        imgs.append(pipe.generate(pe, lat, noise, steps, gs, record=rec, **kw).cpu().numpy())
+        torch.cuda.synchronize()
+        recs.append(rec)
+        del pipe
+        torch.cuda.empty_cache()
+    key = "noise_pred_raw" if gs > 1.0 else "noise_pred"
+    errs = [max_rel_err(b, a) for a, b in zip(recs[0][key], recs[1][key])]
+    return errs, psnr_u8(imgs[1], imgs[0])
+
+
+def test_c2_full_batch_bf16_vs_fp32_mode():
+    """BASELINE config C2 at its FULL size (SD1.5-LCM arch, 512x512, 4 steps, batch 16): the bf16
+    tensor-core path against the fp32 mode, every image of the batch."""
+    from dreamlab_b200 import synthetic as syn
+    from test_pipeline_gpu import NOISE_PRED_TOL, PSNR_MIN_DB
+    errs, p = _bf16_vs_fp32(syn.sd15_lcm_unet_cfg(), syn.sd_vae_cfg(), 16, 512, 4, 1.0)
+    print(f"C2 (B=16, 512^2, 4 steps) bf16 vs fp32 mode: noise_pred max-rel-err per step "
+          f"{['%.2e' % e for e in errs]}  image PSNR {p:.1f} dB")
+    assert max(errs) <= NOISE_PRED_TOL, errs
+    assert p >= PSNR_MIN_DB, p
+
+
+def test_c5_geometry_sdxl_1024_bf16_vs_fp32_mode():
+    """BASELINE config C5 geometry at its FULL size (SDXL-base arch, 1024x1024, CFG 7.5; 2 of the 30
+    steps): S = 4096 / 1024 self-attention at head dim 64, 10-deep transformers, 128^2 latents."""
+    from dreamlab_b200 import synthetic as syn
+    from test_pipeline_gpu import PSNR_MIN_DB, assert_unet_outputs
+    errs, p = _bf16_vs_fp32(syn.sdxl_unet_cfg(), syn.sdxl_vae_cfg(), 1, 1024, 2, 7.5, sdxl=True)
+    print(f"C5 geometry (SDXL 1024^2, CFG 7.5, 2 steps) bf16 vs fp32 mode: UNet output max-rel-err per step "
+          f"{['%.2e' % e for e in errs]}  image PSNR {p:.1f} dB")
+    assert_unet_outputs(errs, 7.5)
+    assert p >= PSNR_MIN_DB, p
