@@ -408,3 +408,17 @@ def test_igemm_dual_subtile_residual_and_u8():
     r8 = (r3.bfloat16().float() * 0.5 + 0.5).clamp(0, 1) * 255
     torch.cuda.synchronize()
     assert (img.float() - r8).abs().max().item() <= 1.5
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 4096), (33, 256), (16, 192), (8, 4100), (5, 1023)])
+def test_softmax_rows(rows, cols):
+    """fp32 scores -> bf16 probabilities (VAE mid-block attention): register-resident variant
+    (cols <= 4096, multiple of 4) and the generic one."""
+    lib = L()
+    s = rand(rows, cols, seed=1, scale=4.0)
+    out = torch.empty(rows, cols, device=DEV, dtype=torch.bfloat16)
+    lib.softmax_rows(s, out)
+    ref = torch.softmax(s.float(), dim=-1)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 4e-3 * ref.max().item() + 1e-6
+    assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=2e-2)
