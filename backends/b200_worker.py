@@ -294,6 +294,7 @@ class B200SDXLWorker(B200Worker):
     when guidance_scale > 1 (all jobs of one batch must then share the scale), SDXL VAE."""
     _tag = "b200-sdxl"
     _env_what = "SDXL CUDA worker"
+    batch_same_guidance = True        # CFG runs one guidance scale per (doubled) batch: the pool groups by it
 
     def _make_text_encoder(self, path):
         ucfg = self.pipe.unet.cfg

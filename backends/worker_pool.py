@@ -114,10 +114,13 @@ def _auto_num_workers() -> int:
     return n if isinstance(n, int) and n > 0 else 1
 
 
-def _batch_key(job):
-    """Generation jobs that may share one batched pass: same size, step count and style."""
+def _batch_key(job, same_guidance: bool = False):
+    """Generation jobs that may share one batched pass: same size, step count and style (and,
+    for workers that run classifier-free guidance on a doubled batch, the same guidance scale)."""
     req = getattr(job, "req", None)
     try:
+        if same_guidance:
+            return _batch_key(job) + (float(req.guidance_scale),)
         sl = getattr(req, "style_lora", None)
         style = (getattr(sl, "style", None), int(getattr(sl, "level", 0) or 0)) if sl else (None, 0)
         if not style[0] or style[1] <= 0:
@@ -213,13 +216,14 @@ class WorkerPool:
         if not (isinstance(first, GenerationJob) and hasattr(worker, "run_batch")
                 and not isinstance(getattr(worker, "run_batch"), type(None))):
             return batch
-        key = _batch_key(first)
+        same_gs = bool(getattr(type(worker), "batch_same_guidance", False))
+        key = _batch_key(first, same_gs)
         if key is None or self.max_batch <= 1:
             return batch
         with self.q.mutex:                      # peek under the queue's own lock: FIFO prefix only
             while len(batch) < self.max_batch and self.q.queue:
                 nxt = self.q.queue[0]
-                if isinstance(nxt, GenerationJob) and type(nxt) is type(first) and _batch_key(nxt) == key:
+                if isinstance(nxt, GenerationJob) and type(nxt) is type(first) and _batch_key(nxt, same_gs) == key:
                     batch.append(self.q.queue.popleft())
                     self.q.not_full.notify()
                 else:

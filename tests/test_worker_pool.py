@@ -208,3 +208,23 @@ def test_deferred_png_encoding_overlaps_the_next_gpu_pass(pool_factory):
     with pytest.raises(ValueError, match="encode failed"):
         fb.result(timeout=5)
     assert pool.submit_job(GenerationJob(req=req("c"))).result(timeout=5) == (b"png-c", 0)
+
+
+def test_cfg_workers_batch_by_guidance_scale(pool_factory):
+    """A worker that runs classifier-free guidance on a doubled batch (B200SDXLWorker) needs one
+    guidance scale per pass: the pool then splits the FIFO prefix where the scale changes."""
+    class CfgWorker(FakeWorker):
+        batch_same_guidance = True
+
+    w = CfgWorker(0, delay=0.2)
+    pool = pool_factory(worker_factory=lambda worker_id: w, num_workers=1, max_batch=16)
+    blocker = pool.submit_job(GenerationJob(req=req("warm")))
+    time.sleep(0.05)                                   # the worker is busy: the next six queue up
+    futs = []
+    for i, gs in enumerate([7.5, 7.5, 7.5, 5.0, 5.0, 7.5]):
+        r = req(f"p{i}")
+        r.guidance_scale = gs
+        futs.append(pool.submit_job(GenerationJob(req=r)))
+    blocker.result(timeout=5)
+    assert [f.result(timeout=5)[0] for f in futs] == [f"png-p{i}".encode() for i in range(6)]
+    assert w.batches == [1, 3, 2, 1]
