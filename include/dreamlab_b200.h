@@ -81,6 +81,10 @@ typedef struct dl_igemm_desc {
   int gn_rows_per_img;       /*   channels per group 4/8/16/32.  Token-row GEMMs (nimg=1,h=1) give the
                                 rows per image (multiple of 128); 0 for NHWC convs.  The records feed
                                 dl_groupnorm_finalize: the consumer norm then reads its input once.   */
+  void* peer_out[7];         /* all-gather fused into the GEMM (SDXL patch parallel, §8e X2): every output  */
+  int n_peer_out;            /*   tile is ALSO TMA-stored into these peer-mapped buffers (same layout and
+                                strides as `out`, which already points at this rank's row block); the caller
+                                follows the launch with a dl_peer_allgather(nbytes = 0) barrier             */
   int in_rows;               /* halo-padded row strips (SDXL patch parallel): a0/a1 */
   int in_row0;               /*   hold in_rows >= h rows per image and output row y reads input rows
                                 y + dy + in_row0; 0/0 = dense (in_rows = h)                    */
@@ -213,7 +217,9 @@ int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f
  * every peer's signal pad (flag_ptrs[r], >= nranks u32, zero-initialised), wait for all ranks and
  * copy the gathered half to dst [nranks, nbytes].  `state`: 3 zero-initialised u32 in local device
  * memory (epoch and two CTA counters); epochs advance on the device, so the call is CUDA-graph
- * safe.  Every rank of the group must issue the same sequence of calls.                          */
+ * safe.  Every rank of the group must issue the same sequence of calls.  nbytes = 0 (src / dst
+ * may be NULL) is a pure barrier: "every rank's earlier kernels — e.g. a dl_igemm with peer_out —
+ * have completed and their peer writes are visible".                                            */
 int dl_peer_allgather(const void* src, void* dst, long long nbytes, void* const* stage_ptrs,
                       void* const* flag_ptrs, int nranks, int rank, long long slot_bytes, void* state,
                       void* stream);

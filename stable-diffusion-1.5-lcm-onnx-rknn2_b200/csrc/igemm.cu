@@ -45,6 +45,8 @@ constexpr int EPI_GN_BYTES = 2 * 4 * 4 * 16 * 4;
 struct IgemmParams {
   CUtensorMap tmA0, tmA1, tmB;
   CUtensorMap tmOut;     // bf16 output, box {32, tw, th, tn}, 64B swizzle (TMA store)
+  CUtensorMap tmOutPeer[7];   // the same tile stored into peer GPUs' buffers as well (all-gather fused
+  int n_peer_out;             // into the GEMM: NVLink writes straight from the epilogue's staging smem)
   CUtensorMap tmR;       // residual as an extra A source (box like tmA0)
   CUtensorMap tmI;       // 256x256 bf16 identity as its B operand (box {64, BN})
   int res_chunks;        // ceil(BN/64) when a residual is fused, else 0
@@ -474,6 +476,8 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
               const int cc = col0 + c_group + gg * 2 * step;
               const int out_col = (p.mode == DL_EPI_GEGLU) ? (cc >> 1) : cc;
               tma_store_4d(&p.tmOut, my_staging + gg * EPI_BUF_BYTES, out_col, x0, y0, n0);
+              for (int q = 0; q < p.n_peer_out; ++q)
+                tma_store_4d(&p.tmOutPeer[q], my_staging + gg * EPI_BUF_BYTES, out_col, x0, y0, n0);
             }
             bulk_commit_group();
           }
@@ -672,6 +676,14 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
     const uint64_t strides[3] = {xs, ys, is};
     const uint32_t box[4] = {32, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (make_tmap_bf16(&p.tmOut, d->out, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    DL_CHECK_ARG(d->n_peer_out >= 0 && d->n_peer_out <= 7, "igemm: at most 7 peer outputs");
+    p.n_peer_out = d->n_peer_out;
+    for (int q = 0; q < d->n_peer_out; ++q) {
+      DL_CHECK_ARG(d->peer_out[q] != nullptr, "igemm: null peer output");
+      if (make_tmap_bf16(&p.tmOutPeer[q], d->peer_out[q], 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+    }
+  } else {
+    DL_CHECK_ARG(d->n_peer_out == 0, "igemm: peer outputs need a bf16 output mode");
   }
   if (d->residual) {
     const uint64_t dims[4] = {(uint64_t)d->n, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->nimg};

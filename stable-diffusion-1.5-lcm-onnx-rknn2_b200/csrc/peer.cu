@@ -91,9 +91,9 @@ extern "C" int dl_peer_allgather(const void* src, void* dst, long long nbytes, v
                                  void* const* flag_ptrs, int nranks, int rank, long long slot_bytes,
                                  void* state, void* stream_) {
   using namespace dl;
-  DL_CHECK_ARG(src && dst && stage_ptrs && flag_ptrs && state, "peer_allgather: null pointer");
+  DL_CHECK_ARG(stage_ptrs && flag_ptrs && state && (nbytes == 0 || (src && dst)), "peer_allgather: null pointer");
   DL_CHECK_ARG(nranks >= 1 && nranks <= PG_MAX_RANKS && rank >= 0 && rank < nranks, "peer_allgather: bad ranks");
-  DL_CHECK_ARG(nbytes > 0 && nbytes % 16 == 0 && nbytes <= slot_bytes && slot_bytes % 16 == 0,
+  DL_CHECK_ARG(nbytes >= 0 && nbytes % 16 == 0 && nbytes <= slot_bytes && slot_bytes % 16 == 0,
                "peer_allgather: message of %lld bytes (slot %lld) must be a multiple of 16 and fit a slot", nbytes,
                slot_bytes);
   PeerGatherParams p;

@@ -196,8 +196,16 @@ def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
         # row strips: queries stay local, keys/values of every strip are all-gathered
         # (SURVEY.md §8e exchange X2); key order = rank order = image row order
         qs = linear(ctx, n1, q["qkv_w"][:hs], None, hs)
-        kvl = linear(ctx, n1, q["qkv_w"][hs:], q["qkv_b"][hs:], 2 * hs)
-        kvf = ctx.comm.gather_rows(kvl.view(B, S, 2 * hs))            # [B, R*S, 2hs]
+        if hasattr(ctx.comm, "gather_linear") and S % 128 == 0 and ctx.dt == BF16:
+            # gather fused into the K/V projection: its epilogue TMA-stores every tile into the
+            # peers' K/V buffers as well (NVLink writes overlap the GEMM), a flag barrier follows
+            def kv_proj(out_view, peer_ptrs):
+                lib.igemm(n1, q["qkv_w"][hs:], out_view, nimg=B, h=1, w=S, taps=1, n=2 * hs, bias=q["qkv_b"][hs:],
+                          ldo=2 * hs, out_strides=(2 * hs, S * 2 * hs, out_view.stride(0)), peer_outs=peer_ptrs)
+            kvf = ctx.comm.gather_linear(kv_proj, B, S, 2 * hs)
+        else:
+            kvl = linear(ctx, n1, q["qkv_w"][hs:], q["qkv_b"][hs:], 2 * hs)
+            kvf = ctx.comm.gather_rows(kvl.view(B, S, 2 * hs))            # [B, R*S, 2hs]
         skv_all = kvf.shape[1]
         kvf = kvf.view(B * skv_all, 2 * hs)
         lib.attention(qs, kvf, kvf[:, hs:], a, batch=B, sq=S, skv=skv_all, heads=heads, d=d,

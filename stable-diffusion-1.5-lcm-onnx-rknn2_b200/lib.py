@@ -44,6 +44,7 @@ class IgemmDesc(C.Structure):
         ("mode", C.c_int), ("alpha", C.c_float), ("bn", C.c_int),
         ("gn_partial", C.c_void_p), ("gn_cpg", C.c_int), ("gn_slots", C.c_int), ("gn_slot0", C.c_int),
         ("gn_rows_per_img", C.c_int),
+        ("peer_out", C.c_void_p * 7), ("n_peer_out", C.c_int),
         ("in_rows", C.c_int), ("in_row0", C.c_int),
     ]
 
@@ -249,7 +250,7 @@ def require_cuda():
 def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
           a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
           mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None, in_rows=0, in_row0=0,
-          gn_partial=None, gn_cpg=0, gn_slot0=0, gn_rows_per_img=0):
+          gn_partial=None, gn_cpg=0, gn_slot0=0, gn_rows_per_img=0, peer_outs=None):
     """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
     nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
     d = IgemmDesc()
@@ -276,6 +277,10 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
     d.identity = identity_matrix(residual.device).data_ptr() if (residual is not None and not f32) else None
     d.mode, d.alpha, d.bn = mode, alpha, bn
     d.in_rows, d.in_row0 = in_rows, in_row0
+    if peer_outs:                      # device pointers (ints) of the same view in the peers' buffers
+        for i, ptr in enumerate(peer_outs):
+            d.peer_out[i] = ptr
+        d.n_peer_out = len(peer_outs)
     if gn_partial is not None:         # [nimg, slots, groups, 2] fp32
         d.gn_partial, d.gn_cpg, d.gn_slots = gn_partial.data_ptr(), gn_cpg, gn_partial.shape[1]
         d.gn_slot0, d.gn_rows_per_img = gn_slot0, gn_rows_per_img
@@ -472,6 +477,16 @@ def lcm_step(eps, x, noise, x_next, denoised, coeffs):
     k = LcmCoeffs(*[float(v) for v in coeffs])
     _check(load().dl_lcm_step(eps.data_ptr(), x.data_ptr(), _ptr(noise), x_next.data_ptr(),
                               denoised.data_ptr(), x.numel(), C.byref(k), _stream()), "lcm_step")
+    _count()
+
+
+def peer_barrier(stage_ptrs, flag_ptrs, rank, slot_bytes, state):
+    """dl_peer_allgather with an empty message: all ranks' earlier work (and its peer writes) is done."""
+    R = len(stage_ptrs)
+    sp = (C.c_void_p * R)(*stage_ptrs)
+    fp = (C.c_void_p * R)(*flag_ptrs)
+    _check(load().dl_peer_allgather(None, None, 0, sp, fp, R, rank, slot_bytes, state.data_ptr(), _stream()),
+           "peer_barrier")
     _count()
 
 

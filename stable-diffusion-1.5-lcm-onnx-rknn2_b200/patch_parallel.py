@@ -132,6 +132,40 @@ class PeerComm(StripComm):
         gather kernel (both boundary rows of every rank; neighbours pick theirs)."""
         super().halo_exchange(t)
 
+    # ---- all-gather fused into the producing GEMM ----------------------------------------------
+    def _fused_setup(self, nbytes: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        if getattr(self, "_fbuf_bytes", 0) >= nbytes:
+            return
+        # (re)allocation is collective and happens on the first call of a geometry, never under capture
+        self._fbuf_bytes = max(int(nbytes), 32 << 20)
+        dev = self._state.device
+        self._fbuf = symm_mem.empty(2 * self._fbuf_bytes, dtype=torch.uint8, device=dev)
+        self._fbuf_hdl = symm_mem.rendezvous(self._fbuf, self.group)
+        self._fbuf_ptrs = [int(p) for p in self._fbuf_hdl.buffer_ptrs]
+        self._fcalls = 0
+
+    def gather_linear(self, linear_fn, B: int, rows: int, cols: int):
+        """[B, R*rows, cols] bf16 = all-gather over the group of every rank's [B, rows, cols] GEMM
+        output, with the gather fused into the GEMM: `linear_fn(out_view, peer_ptrs)` must launch
+        the igemm whose epilogue TMA-stores each tile into `out_view` (this rank's row block of the
+        local buffer) and into the same view of every peer's buffer.  A flag-only barrier kernel
+        then orders the peers' NVLink writes before the consumer.  Halves of the symmetric buffer
+        alternate per call (callers issue an even number of calls per captured graph)."""
+        from . import lib
+        R, esz = self.world, 2
+        nbytes = B * R * rows * cols * esz
+        self._fused_setup(nbytes)
+        half = (self._fcalls & 1) * self._fbuf_bytes
+        self._fcalls += 1
+        full = self._fbuf[half:half + nbytes].view(torch.bfloat16).view(B, R * rows, cols)
+        mine = full[:, self.rank * rows:(self.rank + 1) * rows]
+        off = half + self.rank * rows * cols * esz                 # byte offset of my row block
+        peers = [self._fbuf_ptrs[r] + off for r in range(R) if r != self.rank]
+        linear_fn(mine, peers)
+        lib.peer_barrier(self._stage_ptrs, self._flag_ptrs, self.rank, self.slot_bytes, self._state)
+        return full
+
 
 class _ThreadHub:
     def __init__(self, world: int):
@@ -318,8 +352,12 @@ class PatchParallelDenoiser:
                 torch.cuda.current_stream(dev).wait_stream(s)
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
+                f0 = getattr(comm, "_fcalls", 0)
                 with torch.cuda.graph(graph):
                     st["out"] = self._loop(*args())
+                if (getattr(comm, "_fcalls", 0) - f0) % 2:
+                    raise RuntimeError("patch parallel: a captured loop must issue an even number of fused "
+                                       "gathers (the peer buffers alternate halves per call)")
                 st["graph"] = graph
                 g = self._graphs[key] = st
             g["pe"].copy_(pe)

@@ -37,6 +37,25 @@ up = 0.0 if rank == 0 else float(rank - 1)
 dn = 0.0 if rank == world - 1 else float(rank + 1)
 ok2 = float(t[:, 0].float().mean()) == up and float(t[:, 5].float().mean()) == dn
 log(f"halo exchange: {ok2}")
+# all-gather fused into a GEMM (peer TMA stores from the epilogue) vs GEMM + gather
+from dreamlab_b200 import lib
+Bq, S, Cin, N = 2, 256, 128, 192
+xa = torch.randn(Bq * S, Cin, device=dev, generator=g).bfloat16()
+wa = (torch.randn(N, Cin, device=dev, generator=torch.Generator(device=dev).manual_seed(7)) * 0.1).bfloat16()
+ok4 = True
+for rep in range(4):
+    def proj(out_view, peer_ptrs):
+        lib.igemm(xa, wa, out_view, nimg=Bq, h=1, w=S, taps=1, n=N, ldo=N,
+                  out_strides=(N, S * N, out_view.stride(0)), peer_outs=peer_ptrs)
+    fused = pc.gather_linear(proj, Bq, S, N).clone()
+    loc = torch.empty(Bq * S, N, device=dev, dtype=torch.bfloat16)
+    lib.igemm(xa, wa, loc, nimg=1, h=1, w=Bq * S, taps=1, n=N, ldo=N)
+    ref = nc.gather_rows(loc.view(Bq, S, N))
+    torch.cuda.synchronize()
+    ok4 = ok4 and torch.equal(fused, ref)
+    xa = torch.randn(Bq * S, Cin, device=dev, generator=g).bfloat16()
+log(f"fused GEMM + gather: {ok4}")
+ok = ok and ok4
 # CUDA graph: odd number of calls per replay, replayed several times with fresh inputs
 xs = [torch.zeros(4096, device=dev), torch.zeros(64, device=dev), torch.zeros(262144, device=dev)]
 s = torch.cuda.Stream()
