@@ -394,14 +394,21 @@ extern "C" int dl_small_linear(const float* x, int m, int k, const void* w, cons
   DL_CHECK_ARG(k % 8 == 0, "small_linear: k=%d must be a multiple of 8", k);
   DL_CHECK_ARG(m >= 1 && m <= 64, "small_linear: m=%d must be in [1,64]", m);
   const int threads = 256;
-  constexpr int NR = 4;
-  const int blocks = (((n + NR - 1) / NR) * 32 + threads - 1) / threads;
+  // wide outputs (the fused time_emb_proj matrix): 4 columns per warp share the x chunk; narrow
+  // ones (time MLP): one column per warp so that the few hundred outputs still fill the SMs
+  const int nr = n >= 8192 ? 4 : 1;
+  const int blocks = (((n + nr - 1) / nr) * 32 + threads - 1) / threads;
   const __nv_bfloat16* wb = reinterpret_cast<const __nv_bfloat16*>(w);
   for (int m0 = 0; m0 < m; m0 += 16) {
     const int mm = (m - m0) < 16 ? (m - m0) : 16;
-    small_linear_kernel<16, NR><<<blocks, threads, 0, STREAM>>>(
-        x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
-        silu_out, out + (size_t)m0 * n);
+    if (nr == 4)
+      small_linear_kernel<16, 4><<<blocks, threads, 0, STREAM>>>(
+          x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
+          silu_out, out + (size_t)m0 * n);
+    else
+      small_linear_kernel<16, 1><<<blocks, threads, 0, STREAM>>>(
+          x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
+          silu_out, out + (size_t)m0 * n);
   }
   return check_launch("small_linear");
 }

@@ -342,9 +342,11 @@ class UNetB200:
             e1 = torch.empty(batch, ch0 * 4, device=self.device, dtype=torch.float32)
             lib.small_linear(x, P["t1_w"], e1, bias=P["t1_b"], silu_out=True)
             emb = torch.empty_like(e1)
-            lib.small_linear(e1, P["t2_w"], emb, bias=P["t2_b"], add=aug_emb)
+            # `emb` is only ever consumed as SiLU(emb) (ResnetBlock2D.time_emb_proj): apply it once
+            # here instead of once per output column of the 20160-wide projection
+            lib.small_linear(e1, P["t2_w"], emb, bias=P["t2_b"], add=aug_emb, silu_out=True)
             temb = torch.empty(batch, P["temb_total"], device=self.device, dtype=torch.float32)
-            lib.small_linear(emb, P["temb_w"], temb, bias=P["temb_b"], silu_in=True)
+            lib.small_linear(emb, P["temb_w"], temb, bias=P["temb_b"])
             out.append(temb)
         return out
 
