@@ -363,6 +363,9 @@ class UNetB200:
         P = self.P
         b0, H, W, Cin = latents_nhwc.shape
         B = b0 * repeat
+        if comm is not None and self.dt != BF16:
+            raise RuntimeError("patch parallel runs on the bf16 path only (the split GroupNorm kernels have no "
+                               "fp32 variant); the fp32 precision mode is a one-GPU parity mode")
         ctx = _Ctx(self.device, B, comm, dt=self.dt)
         g = self.groups
         ch = self.cfg.block_out_channels
@@ -436,6 +439,8 @@ class VAEDecoderB200:
         S = H * W
         hn = groupnorm(ctx, x, a["norm_w"], a["norm_b"], eps=1e-6, silu=False, groups=self.groups)
         hn2 = hn.view(B * S, C)
+        if ctx.comm is not None:
+            return self._mid_attention_strips(ctx, x, hn2, a)
         qk = linear(ctx, hn2, a["qk_w"], a["qk_b"], 2 * C)                 # [B*S, 2C]
         o = ctx.empty(B * S, C)
         if S % 64 or self.dt != BF16:
@@ -464,6 +469,39 @@ class VAEDecoderB200:
         if hasattr(out, "_gn"):
             res._gn = out._gn
         return res
+
+    def _mid_attention_strips(self, ctx, x, hn2, a: Packed):
+        """Row strips (VAE row): the queries of this rank's S tokens attend to the
+        keys / values of all R*S tokens.  ONE exchange: the normalised tokens are all-gathered
+        (rank order = image row order) and every rank projects K and V^T from them itself — the
+        two projections are 2*R*S*C^2 MACs, far cheaper than a second and third gather."""
+        B, H, W, C = x.shape
+        S = H * W
+        comm = ctx.comm
+        hn_all = comm.gather_rows(hn2.view(B, S, C))                        # [B, R*S, C]
+        Sa = hn_all.shape[1]
+        hn_all = hn_all.reshape(B * Sa, C)
+        scale = 1.0 / math.sqrt(C)
+        q = linear(ctx, hn2, a["qk_w"][:C], a["qk_b"][:C], C)               # [B*S, C]
+        k = linear(ctx, hn_all, a["qk_w"][C:], a["qk_b"][C:], C)            # [B*Sa, C]
+        o = ctx.empty(B * S, C)
+        if Sa % 64:                       # ragged key count: the CUDA-core flash kernel takes any length
+            v = linear(ctx, hn_all, a["v_w"], None, C)
+            lib.attention(q, k, v, o, batch=B, sq=S, skv=Sa, heads=1, d=C, dh_stride=C,
+                          ldq=C, ldk=C, ldv=C, ldo=C, scale=scale, impl=lib.ATTN_SIMT)
+        else:
+            scores = ctx.empty(S, Sa, dtype=torch.float32)
+            probs = ctx.empty(S, Sa)
+            vt = ctx.empty(C, Sa)
+            for b in range(B):
+                rows, keys = slice(b * S, (b + 1) * S), slice(b * Sa, (b + 1) * Sa)
+                lib.igemm(a["v_w"], hn_all[keys], vt, nimg=1, h=1, w=C, taps=1, n=Sa, a0_stride=C, ldo=Sa)
+                lib.igemm(q[rows], k[keys], scores, nimg=1, h=1, w=S, taps=1, n=Sa, c0=C, a0_stride=C,
+                          mode=lib.EPI_F32, alpha=scale, ldo=Sa)
+                lib.softmax_rows(scores, probs)
+                lib.igemm(probs, vt, o[rows], nimg=1, h=1, w=S, taps=1, n=C, a0_stride=Sa, ldo=C)
+        out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C))
+        return out.view(B, H, W, C)
 
     @torch.no_grad()
     def decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
@@ -511,19 +549,44 @@ class VAEDecoderB200:
         return out_u8
 
     @torch.no_grad()
+    def decode_strips(self, latents_nhwc: torch.Tensor, comm, f32_out: bool = False) -> torch.Tensor:
+        """One image decoded by all ranks of `comm` (a patch_parallel.StripComm), SURVEY.md §8e
+        "VAE decode in C5": rank r owns latent rows [r*H/R, (r+1)*H/R) and therefore 8x as many
+        pixel rows at the output.  Same kernels as the one-GPU decode; exchanges: one halo row to
+        each neighbour in front of every 3x3 conv (the upsample convs included), the per-(image,
+        group) GroupNorm records, the mid-block attention tokens (`_mid_attention_strips`), and at
+        the end the pixel rows (3 bytes / pixel).  latents: the FULL fp32 NHWC latent, identical on
+        every rank (as `PatchParallelDenoiser.denoise` leaves it).  -> the full u8 (or fp32)
+        image [B,8H,8W,3] on every rank."""
+        B, H, W, _ = latents_nhwc.shape
+        R = comm.world
+        if self.dt != BF16:
+            raise RuntimeError("strip decode runs on the bf16 path only (the split GroupNorm kernels have no "
+                               "fp32 variant); the fp32 precision mode is a one-GPU parity mode")
+        if H % R:
+            raise RuntimeError(f"strip decode: {H} latent rows do not split into {R} strips")
+        hl = H // R
+        mine = latents_nhwc[:, comm.rank * hl:(comm.rank + 1) * hl].contiguous()
+        strip = self._decode(mine, f32_out=f32_out, comm=comm)                # [B, 8*hl, 8W, 3]
+        return comm.gather_rows(strip)
+
+    @torch.no_grad()
     def _decode(self, latents_nhwc: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
-                f32_out: bool = False) -> torch.Tensor:
+                f32_out: bool = False, comm=None) -> torch.Tensor:
         """One untiled decode.  Fuses `/ scaling_factor`, post_quant_conv and (u8 output) the
-        VaeImageProcessor denormalise; f32_out returns the decoder output fp32 [B,8h,8w,3]."""
+        VaeImageProcessor denormalise; f32_out returns the decoder output fp32 [B,8h,8w,3].
+        comm: latents_nhwc is this rank's row strip (see `decode_strips`), so is the result."""
         P = self.P
         B, H, W, Cin = latents_nhwc.shape
         g = self.groups
-        ctx = _Ctx(self.device, B, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt)
+        ctx = _Ctx(self.device, B, comm=comm, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt)
         ch = self.cfg.block_out_channels
         z = ctx.empty(B, H, W, 64)
         lib.pack_latent(latents_nhwc, z, cin=Cin, scale=1.0 / self.cfg.scaling_factor,
                         mat=P["pq_w"], vec=P["pq_b"])
         # `/ scaling_factor` is computed as a multiply by the fp32 reciprocal
+        if comm is not None:
+            z = ctx.pad_rows(z)
         h = conv3x3(ctx, z, P["conv_in_w"], P["conv_in_b"], ch[-1], feeds_norm=True)
         h = resnet(ctx, h, P["mid_res"][0], eps=1e-6, groups=g)
         h = self._mid_attention(ctx, h, P["mid_attn"])
@@ -533,8 +596,9 @@ class VAEDecoderB200:
                 h = resnet(ctx, h, r, eps=1e-6, groups=g)
             if blk["up"] is not None:
                 h = upsample(ctx, h, blk["up"])
-        hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-6, silu=True, groups=g)
-        Bo, Ho, Wo, _ = hn.shape
+        hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-6, silu=True, groups=g,
+                       halo=comm is not None)
+        Bo, Ho, Wo, _ = h.shape
         if f32_out:
             img = torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.float32)
             conv3x3(ctx, hn, P["conv_out_w"], P["conv_out_b"], 3, mode=lib.EPI_F32, out=img, ldo=3)

@@ -16,7 +16,8 @@ sharded: the world of N ranks is `cfg_ways x strips`:
 
 Every rank keeps the full latent (64 KB): after the per-step all-gather of the strip outputs all
 ranks run the same CFG combine + `LCMScheduler.step` kernels on identical inputs, so latents stay
-bit-identical across ranks without a broadcast.  The VAE decode runs on rank 0.
+bit-identical across ranks without a broadcast.  The VAE decode runs on rank 0, or (`vae_strips`)
+as row strips over all N ranks with the same three exchanges (`VAEDecoderB200.decode_strips`).
 
 Communicators: `DistComm` = torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests);
 `ThreadComm` = N virtual ranks as threads of one process on one device (test double that lets
@@ -373,10 +374,17 @@ class PatchParallelDenoiser:
 
     @torch.no_grad()
     def generate(self, prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps: int,
-                 guidance_scale: float, record: dict = None, decode_rank: int = 0, use_graph: bool = False):
-        """-> u8 images [B,H,W,3] on `decode_rank` (None elsewhere)."""
+                 guidance_scale: float, record: dict = None, decode_rank: int = 0, use_graph: bool = False,
+                 vae_strips: bool = False):
+        """-> u8 images [B,H,W,3] on `decode_rank` (None elsewhere).  vae_strips: the decode is
+        sharded too — every rank of the WORLD (there is no CFG batch in the decoder, so all
+        cfg_ways x strips ranks form one strip group) decodes H/N latent rows
+        (`VAEDecoderB200.decode_strips`) and every rank returns the full image."""
         lat = self.denoise(prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps,
                            guidance_scale, record, use_graph=use_graph)
+        if vae_strips and self.world.world > 1:
+            with torch.cuda.device(self.pipe.device):
+                return self.pipe.vae.decode_strips(lat, self.world)
         if self.world.rank != decode_rank:
             return None
         with torch.cuda.device(self.pipe.device):

@@ -157,3 +157,77 @@ def test_halo_conv_matches_dense_rows():
             assert torch.equal(out, ref), (r0, hl)
         else:
             assert torch.allclose(out.float(), ref.float(), rtol=2e-2, atol=2e-2), (r0, hl)
+
+
+def _decode_world(dec, x, world, f32_out=False):
+    """-> per-rank result of `decode_strips` over `world` thread ranks sharing cuda:0."""
+    from dreamlab_b200.patch_parallel import SingleComm, ThreadComm
+    if world == 1:
+        return [dec.decode_strips(x, SingleComm(), f32_out=f32_out)]
+    comms = ThreadComm.make(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            out[rank] = dec.decode_strips(x, comms[rank], f32_out=f32_out)
+            torch.cuda.synchronize()
+        except BaseException:             # noqa: BLE001
+            import traceback
+            errs.append(traceback.format_exc())
+            comms[0].hub.barrier.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(300) for t in ts]
+    assert not errs, errs[0]
+    return out
+
+
+@pytest.mark.parametrize("world,h,w,B", [(1, 16, 16, 1), (2, 16, 16, 2), (4, 16, 16, 1), (2, 32, 24, 1),
+                                         (4, 32, 32, 1), (8, 32, 16, 1)])
+def test_vae_strip_decode_matches_unsharded_and_oracle(world, h, w, B):
+    """SURVEY.md §8e "VAE decode in C5": the decoder over row strips — halo rows in front of every
+    3x3 conv (upsample convs included), split GroupNorm, mid-block attention over the gathered
+    tokens, pixel-row gather — against the one-GPU decode of the same kernels (GroupNorm merge /
+    key order differ, then bf16 rounding) and against the fp32 oracle at the pipeline's PSNR bar.
+    (4, 16, 16): 64 query tokens per rank; (8, 32, 16): 4 latent rows x 16 = 64 tokens per rank and 512 keys."""
+    from oracle.pipeline import build_random_init, denormalize_to_u8
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from dreamlab_b200.engine import VAEDecoderB200
+    from test_pipeline_gpu import PSNR_MIN_DB, psnr_u8
+    _, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    dec = VAEDecoderB200(vae.state_dict(), vae.cfg, "cuda:0")
+    lat = torch.randn(B, 4, h, w, generator=torch.Generator().manual_seed(7)) * 0.18215 * 3
+    with torch.no_grad():
+        ref = denormalize_to_u8(vae(lat / vae.cfg.scaling_factor, tiling=False))
+    x = lat.permute(0, 2, 3, 1).contiguous().cuda()
+    one = dec.decode(x)
+    torch.cuda.synchronize()
+    outs = _decode_world(dec, x, world)
+    for r, img in enumerate(outs):
+        assert img.shape == (B, 8 * h, 8 * w, 3) and img.dtype == torch.uint8
+        assert torch.equal(img, outs[0]), r                  # every rank holds the same gathered image
+    got = outs[0].cpu().numpy()
+    p_one, p_ref = psnr_u8(got, one.cpu().numpy()), psnr_u8(got, ref)
+    dmax = int((outs[0].int() - one.int()).abs().max())
+    print(f"VAE strips world={world} {h}x{w} B={B}: vs one-GPU decode PSNR {p_one:.1f} dB (max |d| {dmax}), "
+          f"vs oracle {p_ref:.1f} dB (one-GPU vs oracle {psnr_u8(one.cpu().numpy(), ref):.1f} dB)")
+    assert p_ref >= PSNR_MIN_DB, p_ref
+    assert p_one >= 45.0, p_one
+
+
+def test_strips_refuse_fp32_mode():
+    """The split GroupNorm kernels exist for bf16 only: the fp32 precision mode (a one-GPU parity
+    mode) must refuse a strip communicator loudly instead of computing garbage."""
+    from oracle.pipeline import build_random_init
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from dreamlab_b200.engine import VAEDecoderB200
+    from dreamlab_b200.patch_parallel import SingleComm
+    _, vae = build_random_init(UNetConfig.tiny(), VAEConfig.tiny(), seed=0)
+    dec = VAEDecoderB200(vae.state_dict(), vae.cfg, "cuda:0", precision="fp32")
+    x = torch.zeros(1, 16, 16, 4, device="cuda")
+    with pytest.raises(RuntimeError, match="bf16 path only"):
+        dec.decode_strips(x, SingleComm())

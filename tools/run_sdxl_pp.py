@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="tiny SDXL topology (debug)")
     ap.add_argument("--peer", action="store_true", help="exchanges as dl_peer_allgather kernels (NVLink peer memory)")
     ap.add_argument("--both", action="store_true", help="time NCCL and peer-memory exchanges in one process")
+    ap.add_argument("--vae-strips", action="store_true",
+                    help="also time the VAE decode as row strips over all ranks vs on one GPU, and compare the images")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -133,6 +135,19 @@ def main():
         out["ms_per_image_denoise_peer_exchange"] = round(ms_p, 2)
         out["ms_per_unet_step_peer_exchange"] = round(ms_p / a.steps, 3)
     log("sharded timing done")
+    if a.vae_strips:
+        # VAE decode of the final latent: one GPU vs row strips over the world
+        latf = den.denoise(pe, pooled, lat, noise, a.steps, a.gs, use_graph=use_graph).clone()
+        one = pipe.vae.decode(latf)
+        ms_1 = timed(lambda: pipe.vae.decode(latf), a.iters)
+        out["ms_vae_decode_1gpu"] = round(ms_1, 2)
+        if world > 1:
+            sh = pipe.vae.decode_strips(latf, den.world)
+            torch.cuda.synchronize()
+            diff = (sh.int() - one.int()).abs()
+            out["vae_strips_max_abs_diff_u8"] = int(diff.max())
+            out["vae_strips_frac_bytes_differing"] = float((diff > 0).float().mean())
+            out["ms_vae_decode_strips"] = round(timed(lambda: pipe.vae.decode_strips(latf, den.world), a.iters), 2)
     if rank == 0:
         # un-sharded reference timing of the same loop on one GPU (graph replay)
         g1 = lambda: pipe.generate(pe, lat, noise, a.steps, a.gs, pooled_embeds=pooled, use_graph=True)  # noqa: E731
