@@ -57,7 +57,10 @@ struct AttnParams {
 // several cycles: with KS/KT known the issue paths are straight runs of UMMAs with folded
 // descriptor offsets instead of 12 / 8 predicated slots with runtime address math (measured
 // ~660 / ~330 cycles per tile for the S / PV issue before).
-template <bool kOnes, bool kBf16Exp, int KS, int KT>
+// kPoly: of every 8 score pairs, this many take their exponentials from `poly_exp2` (FMA / ALU
+// pipes) instead of MUFU.EX2 — the exp pass of the d = 40 / 64 / 80 heads is bound by the 16-lane XU
+// pipe (one MUFU per score), not by the tensor core (opt-in: DL_ATTN_POLY).
+template <bool kOnes, bool kBf16Exp, int KS, int KT, int kPoly = 0>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -369,7 +372,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           const float x0 = fmaf(__uint_as_float(u0), p.scale_log2, -m_new);
           const float x1 = fmaf(__uint_as_float(u1), p.scale_log2, -m_new);
           __nv_bfloat162 pb;
-          if (kBf16Exp) {
+          if (kPoly > 0 && (i & 7) >= 8 - kPoly) {
+            pb = __floats2bfloat162_rn(poly_exp2(x0), poly_exp2(x1));
+          } else if (kBf16Exp) {
             // two exponentials per MUFU op; P is rounded to bf16 for the PV MMA anyway, and the
             // denominator comes from the same P through V's ones column
             const __nv_bfloat162 xb = __floats2bfloat162_rn(x0, x1);
@@ -590,6 +595,10 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
     DL_ATTN_ATTR(true, true, 4, 128);
     DL_ATTN_ATTR(true, true, 5, 128);
     DL_ATTN_ATTR(false, false, 0, 0);
+    DL_ATTN_ATTR(true, true, 3, 128, 2);
+    DL_ATTN_ATTR(true, true, 3, 128, 3);
+    DL_ATTN_ATTR(true, true, 4, 128, 2);
+    DL_ATTN_ATTR(true, true, 5, 128, 2);
 #undef DL_ATTN_ATTR
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
@@ -597,8 +606,23 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   dim3 grid((sq + AT_TILE - 1) / AT_TILE, heads, batch);
   static int generic = -1;
   if (generic < 0) { const char* e = getenv("DL_ATTN_GENERIC"); generic = e ? atoi(e) : 0; }
+  // exponentials partly on the FMA pipe (see kPoly): 0 = all MUFU, 2 / 3 = 25 % / 37.5 % polynomial.
+  // Measured on B200 (B = 16, S = 4096, d = 40): 981 us all-MUFU, 942 us at 25 %, 975 us at 37.5 %;
+  // d = 80 (S = 1024) unchanged.  Default: 25 % for head dim 40 only; DL_ATTN_POLY=0 switches it
+  // off, =2 / =3 apply it to head dims 64 / 80 as well.
+  static int poly = -2;
+  if (poly == -2) { const char* e = getenv("DL_ATTN_POLY"); poly = e ? atoi(e) : -1; }
+  const bool long_keys = skv >= 256;           // short key lists (cross attention) are not exp-bound
   if (p.l_col < 0) {
     attn_tc_kernel<false, false, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 3 && !generic && poly == 3 && long_keys) {
+    attn_tc_kernel<true, true, 3, 128, 3><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 3 && !generic && (poly >= 2 || poly == -1) && long_keys) {
+    attn_tc_kernel<true, true, 3, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 4 && !generic && poly >= 2 && long_keys) {
+    attn_tc_kernel<true, true, 4, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
+  } else if (p.kt == 128 && p.ksteps == 5 && !generic && poly >= 2 && long_keys) {
+    attn_tc_kernel<true, true, 5, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 3 && !generic) {       // SD1.5 head dim 40
     attn_tc_kernel<true, true, 3, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 4 && !generic) {       // SDXL head dim 64

@@ -329,6 +329,20 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x WITHOUT the MUFU pipe (16 lanes / clk / SM, and `ex2.approx.*x2` is lowered to two MUFU ops on
+// sm_100a, so the packed form saves no XU cycles): Cody-Waite split x = n + f with |f| <= 0.5 by
+// the 1.5 * 2^23 rounding constant, degree-3 minimax polynomial of 2^f (max rel err 7.7e-5, far
+// below the bf16 rounding of P), n added into the exponent field as an integer.  ~8 FMA / ALU
+// pipe instructions.  x <= -125 (masked keys: -inf) returns ~2^-125, which rounds away in P.
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;                     // low mantissa bits of r hold round(x)
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(0.05508873611688614f, f, 0.242604061961174f);
+  p = fmaf(p, f, 0.6932762265205383f);
+  p = fmaf(p, f, 0.9999289512634277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
 // silu(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: ONE MUFU op (tanh.approx, rel err 2^-11, below
 // bf16 output rounding).  exp + reciprocal (2 MUFU + a precise divide) made GroupNorm+SiLU
 // MUFU-/ALU-bound instead of HBM-bound.
