@@ -375,8 +375,9 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
           if (kPoly > 0 && (i & 7) >= 8 - kPoly) {
             pb = __floats2bfloat162_rn(poly_exp2(x0), poly_exp2(x1));
           } else if (kBf16Exp) {
-            // two exponentials per MUFU op; P is rounded to bf16 for the PV MMA anyway, and the
-            // denominator comes from the same P through V's ones column
+            // packed exp: bf16 results without a conversion (still one MUFU per value in SASS); P is
+            // rounded to bf16 for the PV MMA anyway, and the denominator comes from the same P through
+            // V's ones column
             const __nv_bfloat162 xb = __floats2bfloat162_rn(x0, x1);
             const uint32_t e = ex2_bf16x2(*reinterpret_cast<const uint32_t*>(&xb));
             pb = *reinterpret_cast<const __nv_bfloat162*>(&e);

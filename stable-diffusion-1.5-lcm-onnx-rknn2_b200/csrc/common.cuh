@@ -318,7 +318,8 @@ __device__ __forceinline__ void tmem_st_wait() {
 }
 
 // ---- small numeric helpers ----
-// two exp2 per MUFU instruction: packed bf16 in, packed bf16 out
+// packed bf16 in, packed bf16 out: saves the fp32 -> bf16 conversion of the results (in sm_100a SASS it is
+// still two MUFU.EX2.BF16, one per half, + a PRMT — not two exponentials per XU op)
 __device__ __forceinline__ uint32_t ex2_bf16x2(uint32_t packed) {
   uint32_t r;
   asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(packed));
