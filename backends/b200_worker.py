@@ -322,10 +322,28 @@ def _encoders():
     return _ENCODERS
 
 
+def _png_level():
+    """B200_PNG_COMPRESS_LEVEL (0-9): zlib level of the PNG encoder.  Unset = PIL's default (6), i.e.
+    exactly the reference's `img.save(buf, format="PNG")` (`backends/cuda_worker.py:234-239`).  The pixels
+    are the same at every level; level 1 encodes a 512x512 image in ~45 ms instead of 70-100 ms per core,
+    which matters once one GPU produces > 130 images/s."""
+    v = os.environ.get("B200_PNG_COMPRESS_LEVEL", "").strip()
+    if not v:
+        return None
+    lvl = int(v)
+    if not 0 <= lvl <= 9:
+        raise RuntimeError(f"B200_PNG_COMPRESS_LEVEL must be 0..9, got {v!r}")
+    return lvl
+
+
 def _encode_png(arr) -> bytes:
     from PIL import Image
     buf = io.BytesIO()
-    Image.fromarray(arr).save(buf, format="PNG")
+    lvl = _png_level()
+    if lvl is None:
+        Image.fromarray(arr).save(buf, format="PNG")
+    else:
+        Image.fromarray(arr).save(buf, format="PNG", compress_level=lvl)
     return buf.getvalue()
 
 

@@ -111,3 +111,25 @@ def test_b200_worker_contract_errors_without_loading():
     with patch.dict(os.environ, {"MODEL_ROOT": "/models"}, clear=True):
         with pytest.raises(RuntimeError, match="MODEL is required"):
             B200Worker(worker_id=0)
+
+
+def test_png_compress_level_knob(monkeypatch):
+    """B200_PNG_COMPRESS_LEVEL: unset = the reference's exact PIL call; any level decodes to the
+    same pixels; a bad value fails loudly."""
+    import io
+    import numpy as np
+    from PIL import Image
+    from backends.b200_worker import _encode_png
+    arr = np.random.default_rng(0).integers(0, 256, (64, 48, 3), dtype=np.uint8)
+    monkeypatch.delenv("B200_PNG_COMPRESS_LEVEL", raising=False)
+    ref = io.BytesIO()
+    Image.fromarray(arr).save(ref, format="PNG")
+    assert _encode_png(arr) == ref.getvalue()
+    for lvl in ("0", "1", "9"):
+        monkeypatch.setenv("B200_PNG_COMPRESS_LEVEL", lvl)
+        png = _encode_png(arr)
+        assert png[:8] == b"\x89PNG\r\n\x1a\n"
+        assert np.array_equal(np.asarray(Image.open(io.BytesIO(png))), arr)
+    monkeypatch.setenv("B200_PNG_COMPRESS_LEVEL", "12")
+    with pytest.raises(RuntimeError, match="0..9"):
+        _encode_png(arr)
