@@ -24,6 +24,11 @@ namespace dl {
 int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                      long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                      int skv, int heads, int d, float scale, int causal, cudaStream_t stream);
+// attention_pp.cu: two query tiles per CTA, one softmax thread per row (long keys, head dim <= 56);
+// -1 = shape not covered
+int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                   int dh_stride, void* out, long long ldo, int batch, int sq, int skv, int heads, int d,
+                   float scale, int v_ones, cudaStream_t stream);
 
 constexpr int AT_THREADS = 320;               // TMA warp, MMA warp, 8 softmax warps
 constexpr int AT_TILE = 128;                 // queries per CTA and keys per KV tile
@@ -526,6 +531,11 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   const int full_budget = 227 * 1024 - 3072;
   static int force_mode = -1;
   if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
+  if (force_mode == 0 && g_attn_trace == nullptr) {
+    const int rc = attn_pp_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d, scale,
+                                  v_ones, stream);
+    if (rc >= 0) return rc;
+  }
   // Configuration search:
   //  1. (DL_ATTN_MODE=3 only; measured 13 % slower on B200) two CTAs per SM with a double-buffered
   //     S: the key tile shrinks to 96 or 64 so that 2*kt + dv <= 256;

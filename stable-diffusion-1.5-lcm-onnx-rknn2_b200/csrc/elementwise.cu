@@ -359,12 +359,15 @@ __global__ void latent_pool8_kernel(const float* __restrict__ lat, int nimg, int
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nimg * c * 64) return;
   const int ox = i % 8, oy = (i / 8) % 8, ch = (i / 64) % c, n = i / (64 * c);
-  const int bh = h / 8, bw = w / 8;
+  // torch.nn.functional.adaptive_avg_pool2d bins: [floor(i*H/8), ceil((i+1)*H/8)) — equal blocks when
+  // H, W are multiples of 8 (reference `backends/cuda_worker.py:299`), overlapping bins otherwise
+  const int y0 = (oy * h) / 8, y1 = ((oy + 1) * h + 7) / 8;
+  const int x0 = (ox * w) / 8, x1 = ((ox + 1) * w + 7) / 8;
   float s = 0.f;
-  for (int y = 0; y < bh; ++y)
-    for (int x = 0; x < bw; ++x)
-      s += lat[(((long long)n * h + oy * bh + y) * w + ox * bw + x) * c + ch];
-  out[i] = __float2half_rn(s / (float)(bh * bw));
+  for (int y = y0; y < y1; ++y)
+    for (int x = x0; x < x1; ++x)
+      s += lat[(((long long)n * h + y) * w + x) * c + ch];
+  out[i] = __float2half_rn(s / (float)((y1 - y0) * (x1 - x0)));
 }
 
 static inline unsigned grid_for(long long total, int threads) {
@@ -577,7 +580,7 @@ extern "C" int dl_cfg_combine(const float* eps_uncond, const float* eps_text, fl
 
 extern "C" int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16,
                                void* stream_) {
-  DL_CHECK_ARG(lat && out_f16 && h % 8 == 0 && w % 8 == 0, "latent_pool8: h, w must be multiples of 8");
+  DL_CHECK_ARG(lat && out_f16 && h > 0 && w > 0 && nimg > 0 && c > 0, "latent_pool8: bad args");
   const int total = nimg * c * 64;
   latent_pool8_kernel<<<(total + 127) / 128, 128, 0, STREAM>>>(lat, nimg, h, w, c,
                                                                 reinterpret_cast<__half*>(out_f16));

@@ -211,13 +211,14 @@ def test_layernorm(rows, C):
 
 
 # ------------------------------------------------------------------ attention
-def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0, v_ones=False):
+def _attn_case(lib, B, Sq, Skv, heads, d, impl, seed=0, v_ones=False, qscale=1.0):
     d16 = (d + 15) // 16 * 16
     hs = (d + 1 + 15) // 16 * 16 if v_ones else d16      # zero-padded per-head stride
     q = torch.zeros(B * Sq, heads * hs, device=DEV, dtype=torch.bfloat16)
     k = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
     v = torch.zeros(B * Skv, heads * hs, device=DEV, dtype=torch.bfloat16)
     qr, kr, vr = (bf(rand(B, n, heads, d, seed=seed + i)) for i, n in enumerate((Sq, Skv, Skv)))
+    qr = bf(qr.float() * qscale)          # > 1: peaked rows, the running max moves and O is rescaled
     q.view(B, Sq, heads, hs)[..., :d] = qr
     k.view(B, Skv, heads, hs)[..., :d] = kr
     v.view(B, Skv, heads, hs)[..., :d] = vr
@@ -251,6 +252,31 @@ def test_attention_tc(B, Sq, Skv, heads, d):
     assert e < 2e-2, f"rel err {e}"
     e1 = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True)     # denominator on the tensor core
     assert e1 < 2e-2, f"rel err (v_ones) {e1}"
+
+
+@pytest.mark.parametrize("B,Sq,Skv,heads,d", [
+    (1, 512, 512, 2, 40), (2, 1024, 1024, 3, 40), (1, 300, 600, 2, 40), (1, 4096, 4096, 1, 40),
+    (1, 768, 1000, 2, 56), (1, 512, 640, 2, 48), (2, 9216, 9216, 1, 40),
+])
+@pytest.mark.parametrize("poly", ["0", "3"])
+def test_attention_pp_two_query_tiles(B, Sq, Skv, heads, d, poly):
+    """attention_pp.cu (256 queries per CTA, one softmax thread per row, P in its own TMEM columns):
+    ragged key tiles, query counts that are not a multiple of 256, both K-step variants, all-MUFU and
+    3/8-polynomial exponentials; and the same inputs through the older kernel agree with it."""
+    import subprocess, sys, os
+    e1 = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True)
+    assert e1 < 2e-2, f"rel err {e1}"
+    e2 = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True, qscale=6.0, seed=7)
+    assert e2 < 2e-2, f"rel err (peaked rows) {e2}"
+    if poly == "0":
+        # the env knobs are read once per process: check the all-MUFU variant in a child
+        code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_kernels_gpu as t; "
+                "e = t._attn_case(t.L(), %d, %d, %d, %d, %d, 0, v_ones=True); assert e < 2e-2, e; print(e)"
+                % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+                   B, Sq, Skv, heads, d))
+        env = dict(os.environ, DL_ATTN_PP_POLY="0")
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
 
 
 # ------------------------------------------------------------------ elementwise / scheduler
