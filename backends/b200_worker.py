@@ -50,7 +50,10 @@ def _load_component(path: str):
     from safetensors.torch import load_file
     with open(os.path.join(path, "config.json")) as f:
         cfg = json.load(f)
-    for name in ("diffusion_pytorch_model.safetensors", "model.safetensors"):
+    # plain names first, then the `variant="fp16"` names the reference's SDXL worker downloads
+    # (`backends/cuda_worker.py:371-377`)
+    for name in ("diffusion_pytorch_model.safetensors", "model.safetensors",
+                 "diffusion_pytorch_model.fp16.safetensors", "model.fp16.safetensors"):
         p = os.path.join(path, name)
         if os.path.exists(p):
             return cfg, load_file(p)
@@ -119,6 +122,8 @@ class B200Worker(PipelineWorker):
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}.get(dtype_str, torch.float16)
         torch.cuda.set_device(self.device)
 
+        with open(os.path.join(path, "model_index.json")) as f:
+            self._model_index = json.load(f)
         ucfg_json, unet_sd = _load_component(os.path.join(path, "unet"))
         vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
         # vae_tiling: the reference switches `pipe.vae.enable_tiling()` on unconditionally
@@ -195,15 +200,35 @@ class B200Worker(PipelineWorker):
     # launch latency, not by the GPU.  B200_CUDA_GRAPH=0 runs eagerly.
     _use_graph = os.environ.get("B200_CUDA_GRAPH", "1").lower() not in ("0", "false", "no", "off")
 
+    @property
+    def batch_same_guidance(self) -> bool:
+        """A UNet without the LCM guidance embedding (time_cond_proj_dim None: vanilla SD1.5 checkpoints such
+        as the reference's dreamshaper / realisticvision modes) runs classifier-free guidance on a doubled batch
+        when guidance_scale > 1: one scale per batch, so the pool must group requests by it."""
+        return not self.pipe.unet.cfg.time_cond_proj_dim
+
+    def _negative(self, n: int):
+        """Unconditional half under CFG: `StableDiffusionPipeline.encode_prompt` encodes the EMPTY prompt
+        (zeros are an SDXL-only convention, `force_zeros_for_empty_prompt`)."""
+        return self._text.encode([""] * n)
+
     def _generate(self, prompts, lat, noise, steps, gs, height, width):
         pe = self._text.encode(prompts)
-        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, use_graph=self._use_graph)
+        neg = self._negative(len(prompts)) if self.pipe.cfg_scale_for(gs) is not None else None
+        return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, use_graph=self._use_graph,
+                                  negative_prompt_embeds=neg)
 
     # ------------------------------------------------------------------ jobs
     def _parse(self, req):
         width, height = parse_size(req.size)
         if width % 8 or height % 8 or width <= 0 or height <= 0:
             raise RuntimeError(f"Invalid size '{req.size}', expected 'WIDTHxHEIGHT'")
+        # every UNet level halves the latent (stride-2 conv, padding 1): this engine implements the exact-halving
+        # case only; diffusers' ceil-mode downsample + `upsample_size` path for other sizes is not built
+        m = 8 << (len(self.pipe.unet.cfg.block_out_channels) - 1)
+        if width % m or height % m:
+            raise RuntimeError(f"Invalid size '{req.size}': the b200 worker needs WIDTH and HEIGHT to be multiples "
+                               f"of {m} for this model (e.g. {max(m, width // m * m)}x{max(m, height // m * m)})")
         seed = int(req.seed) if getattr(req, "seed", None) is not None else \
             int(torch.randint(0, 100_000_000, (1,)).item())
         return width, height, seed
@@ -252,19 +277,25 @@ class B200Worker(PipelineWorker):
                                             height, width)
             finally:
                 self._apply_style(None, 0)          # reset: no state bleed into the next job
+            from dreamlab_b200 import lib
             pooled = None
             if with_latents:
-                from dreamlab_b200 import lib
                 pooled = torch.empty(len(jobs), 4, 8, 8, device=self.device, dtype=torch.float16)
                 lib.latent_pool8(final, pooled)
                 pooled = pooled.cpu().numpy()
-            img = img.cpu().numpy()
+            png_files, png_size = None, 0
+            if not raw and _png_mode() == "gpu":
+                # the finished PNG files come off the device (csrc/png.cu): no zlib on the host
+                png_dev, png_size = lib.png_stored(img.contiguous())
+                png_files = png_dev.cpu().numpy()
+            else:
+                img = img.cpu().numpy()
 
         def finish(i):
             seed = parsed[i][2]
             if raw:
                 return (img[i], seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (img[i], seed)
-            png = _encode_png(img[i])
+            png = png_files[i, :png_size].tobytes() if png_files is not None else _encode_png(img[i])
             return (png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed)
 
         if deferred:
@@ -294,7 +325,6 @@ class B200SDXLWorker(B200Worker):
     when guidance_scale > 1 (all jobs of one batch must then share the scale), SDXL VAE."""
     _tag = "b200-sdxl"
     _env_what = "SDXL CUDA worker"
-    batch_same_guidance = True        # CFG runs one guidance scale per (doubled) batch: the pool groups by it
 
     def _make_text_encoder(self, path):
         ucfg = self.pipe.unet.cfg
@@ -305,8 +335,14 @@ class B200SDXLWorker(B200Worker):
 
     def _generate(self, prompts, lat, noise, steps, gs, height, width):
         pe, pooled = self._text.encode(prompts)
+        neg = negp = None
+        # `force_zeros_for_empty_prompt` (model_index.json; True for SDXL-base): zeros for the unconditional
+        # half, which is the engine's default; otherwise the empty prompt is encoded like any other
+        if self.pipe.cfg_scale_for(gs) is not None and not self._model_index.get("force_zeros_for_empty_prompt", True):
+            neg, negp = self._text.encode([""] * len(prompts))
         return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, pooled_embeds=pooled,
-                                  use_graph=self._use_graph)
+                                  use_graph=self._use_graph, negative_prompt_embeds=neg,
+                                  negative_pooled_embeds=negp)
 
 
 _ENCODERS = None
@@ -320,6 +356,18 @@ def _encoders():
         n = int(os.environ.get("B200_PNG_THREADS", "0")) or min(16, os.cpu_count() or 4)
         _ENCODERS = ThreadPoolExecutor(max_workers=n, thread_name_prefix="png")
     return _ENCODERS
+
+
+def _png_mode() -> str:
+    """B200_PNG: "pil" (default) = the reference's exact call `img.save(buf, format="PNG")`
+    (`backends/cuda_worker.py:234-239`) on encoder threads; "gpu" = PNG files assembled on the device by
+    `dl_png_stored` (stored deflate blocks, CRC-32 / Adler-32 in CUDA): same pixels in any PNG reader,
+    deterministic bytes, ~1 ms instead of 70-100 ms of host zlib per 512x512 image — the host encoder caps an
+    8-GPU box at a few hundred images/s."""
+    v = os.environ.get("B200_PNG", "pil").strip().lower()
+    if v not in ("pil", "gpu"):
+        raise RuntimeError(f"B200_PNG must be 'pil' or 'gpu', got {v!r}")
+    return v
 
 
 def _png_level():

@@ -17,6 +17,13 @@ What is new (the reference runs ONE worker and ONE job at a time, `worker_pool.p
 
 N comes from the ctor (`num_workers`), else `B200_NUM_WORKERS`, else the number of visible
 CUDA devices (1 when that is not a positive integer, e.g. under mocked torch).
+
+Dequeueing is done by ONE worker thread at a time (the collector role, `_collect_lock`): it pops the
+next job, tops its batch up from the FIFO prefix — waiting up to `B200_BATCH_WINDOW_MS` (default 2 ms,
+0 = never wait) for more compatible requests while the batch is short — registers it as in flight and
+only then hands the role to the next idle thread.  Without that, N idle threads race for every arriving
+request and batches degrade to 1 below saturation.  A mode switch is executed by the thread that pops it
+while it still holds the role, so no later job can be popped before the switch is done (strict FIFO).
 """
 from __future__ import annotations
 
@@ -146,6 +153,8 @@ class WorkerPool:
         self._switching = False
         self.num_workers = num_workers if num_workers else _auto_num_workers()
         self.max_batch = max_batch if max_batch else int(os.environ.get("B200_MAX_BATCH", "16"))
+        self.batch_window = float(os.environ.get("B200_BATCH_WINDOW_MS", "2")) / 1e3
+        self._collect_lock = threading.Lock()
 
         self._worker_factory = worker_factory or self._default_worker_factory
         if mode_config is None:
@@ -173,16 +182,48 @@ class WorkerPool:
         return create_cuda_worker(worker_id)
 
     # ------------------------------------------------------------------ lifecycle
+    def _create_workers(self) -> List[Any]:
+        """One worker per GPU, built concurrently (each constructor loads and packs its own copy of the
+        weights on its own device: 8 serial loads would make a mode switch 8x longer)."""
+        if self.num_workers == 1:
+            return [self._worker_factory(worker_id=0)]
+        out: List[Any] = [None] * self.num_workers
+        errs: List[BaseException] = []
+
+        def make(k):
+            try:
+                out[k] = self._worker_factory(worker_id=k)
+            except BaseException as e:                      # noqa: BLE001 - re-raised below
+                errs.append(e)
+        ts = [threading.Thread(target=make, args=(k,), name=f"WorkerInit-{k}") for k in range(self.num_workers)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        if errs:
+            raise errs[0]
+        return out
+
     def _load_mode(self, mode_name: str):
         mode = self._mode_config.get_mode(mode_name)
-        if self._workers:
-            self._unload_current_worker()
+        old_env = (os.environ.get("MODEL_ROOT"), os.environ.get("MODEL"))
         # the workers read the model location from the environment (reference contract)
         os.environ["MODEL_ROOT"] = self._mode_config.config.model_root
         os.environ["MODEL"] = mode.model
         vram_before = self._registry.get_used_vram()
-        self._workers = [self._worker_factory(worker_id=k) for k in range(self.num_workers)]
+        try:
+            # new workers first (180 GB of HBM hold both generations): a model that fails to load
+            # leaves the pool serving the old mode instead of with no workers at all
+            new_workers = self._create_workers()
+        except BaseException:
+            for key, val in zip(("MODEL_ROOT", "MODEL"), old_env):
+                if val is None:
+                    os.environ.pop(key, None)
+                else:
+                    os.environ[key] = val
+            raise
         vram_used = self._registry.get_used_vram() - vram_before
+        if self._workers:
+            self._unload_current_worker()
+        self._workers = new_workers
         self._registry.register_model(
             name=mode_name, model_path=mode.model_path, vram_bytes=vram_used, worker_id=0,
             loras=[lora.path for lora in mode.loras])
@@ -211,35 +252,35 @@ class WorkerPool:
 
     # ------------------------------------------------------------------ worker threads
     def _take_batch(self, first: Job, worker) -> List[Job]:
-        """Pull more queued generation jobs compatible with `first` (never blocks)."""
+        """Pull queued generation jobs compatible with `first` (FIFO prefix only); while the batch is
+        short, wait up to `batch_window` for more to arrive.  Called by the collector thread only."""
         batch = [first]
-        if not (isinstance(first, GenerationJob) and hasattr(worker, "run_batch")
-                and not isinstance(getattr(worker, "run_batch"), type(None))):
+        if not (worker is not None and type(first) is GenerationJob and _is_real_batcher(worker)):
             return batch
-        same_gs = bool(getattr(type(worker), "batch_same_guidance", False))
+        same_gs = _same_guidance(worker)
         key = _batch_key(first, same_gs)
         if key is None or self.max_batch <= 1:
             return batch
-        with self.q.mutex:                      # peek under the queue's own lock: FIFO prefix only
-            while len(batch) < self.max_batch and self.q.queue:
-                nxt = self.q.queue[0]
-                if isinstance(nxt, GenerationJob) and type(nxt) is type(first) and _batch_key(nxt, same_gs) == key:
-                    batch.append(self.q.queue.popleft())
-                    self.q.not_full.notify()
-                else:
+        import time
+        deadline = time.monotonic() + self.batch_window
+        with self.q.mutex:                      # peek under the queue's own lock
+            while len(batch) < self.max_batch:
+                if self.q.queue:
+                    nxt = self.q.queue[0]
+                    if isinstance(nxt, GenerationJob) and type(nxt) is type(first) and _batch_key(nxt, same_gs) == key:
+                        batch.append(self.q.queue.popleft())
+                        self.q.not_full.notify()
+                        continue
+                    break                       # an incompatible job (or a mode switch) ends the prefix
+                left = deadline - time.monotonic()
+                if left <= 0 or self._stop.is_set():
                     break
+                self.q.not_empty.wait(left)     # releases the mutex while waiting
         return batch
 
-    def _run_generation(self, k: int, job: Job):
-        with self._gate:
-            while self._switching:
-                self._gate.wait()
-            self._active += 1
-            worker = self._workers[k] if k < len(self._workers) else None
-        batch = [job]
+    def _run_generation(self, k: int, job: Job, batch: List[Job], worker):
+        """`batch` is already registered as in flight (`_active`) by the collector."""
         try:
-            if worker is not None and type(job) is GenerationJob and _is_real_batcher(worker):
-                batch = self._take_batch(job, worker)
             if (worker is not None and type(job) is GenerationJob and _is_real_batcher(worker)
                     and getattr(type(worker), "supports_deferred", False) is True):
                 # GPU pass here, PNG encoding on the encoder threads: this thread moves on to the
@@ -270,9 +311,9 @@ class WorkerPool:
                 self._gate.notify_all()
 
     def _run_mode_switch(self, job: ModeSwitchJob):
+        """Runs on the collector thread (no other job can be popped meanwhile): waits for the batches
+        in flight, then recreates every worker."""
         with self._gate:
-            while self._switching:
-                self._gate.wait()
             self._switching = True
             while self._active > 0:
                 self._gate.wait()
@@ -296,14 +337,19 @@ class WorkerPool:
 
     def _worker_loop(self, k: int = 0):
         while not self._stop.is_set():
-            try:
-                job = self.q.get(timeout=0.25)
-            except queue.Empty:
-                continue
-            if isinstance(job, ModeSwitchJob):
-                self._run_mode_switch(job)
-            else:
-                self._run_generation(k, job)
+            with self._collect_lock:                 # the collector role: one dequeuer at a time
+                try:
+                    job = self.q.get(timeout=0.25)
+                except queue.Empty:
+                    continue
+                if isinstance(job, ModeSwitchJob):
+                    self._run_mode_switch(job)
+                    continue
+                with self._gate:
+                    self._active += 1
+                worker = self._workers[k] if k < len(self._workers) else None
+                batch = self._take_batch(job, worker)
+            self._run_generation(k, job, batch, worker)
 
     # ------------------------------------------------------------------ public API
     def submit_job(self, job: Job) -> Future:
@@ -343,6 +389,15 @@ def _resolve(job, thunk):
         logger.error("[WorkerPool] Job failed while encoding: %s", e, exc_info=True)
         if not job.fut.done():
             job.fut.set_exception(e)
+
+
+def _same_guidance(worker) -> bool:
+    """Does this worker need one guidance scale per batch (classifier-free guidance on a doubled batch)?
+    Read through the class so that a Mock's auto-attributes do not count; a property is evaluated."""
+    v = getattr(type(worker), "batch_same_guidance", False)
+    if isinstance(v, property):
+        v = v.fget(worker)
+    return v is True
 
 
 def _is_real_batcher(worker) -> bool:

@@ -1,12 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: 512x512 LCM 4-step images/sec (UNet + VAE) — BASELINE.json metric.
 
-  python bench.py --gpus N --steps K --warmup W            # the B200-native arm
-  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+  python bench.py --gpus N --steps K --warmup W                 # the B200-native arm, config C2
+  python bench.py --impl reference --gpus N --steps K ...        # the reference's CPU path (oracle port)
+  python bench.py --config c3 | c5 ...                           # BASELINE configs C3 / C5 (same arms)
+  python bench.py --pool-workers N                               # ONE process, WorkerPool with N GPU workers
 
-A "step" is one pass of the hot path over one batch: 4 x (UNet forward + LCM scheduler step)
-followed by the VAE decode of a batch of 16 images (BASELINE config C2; at N GPUs each rank
-runs its own batch of 16 = config C4's 128/8 shard, weak scaling, no data-path collective).
+Config C2 (default): a "step" is one pass of the hot path over one batch: 4 x (UNet forward + LCM
+scheduler step) followed by the VAE decode of a batch of 16 images (at N GPUs each rank runs its own
+batch of 16 = config C4's 128/8 shard, weak scaling, no data-path collective).
+  value       images/s, inputs resident in HBM, one CUDA-graph replay per step, CUDA events, L2 flushed
+  e2e         the same metric through the reference-facing plugin boundary: `GenerationJob`s ->
+              `WorkerPool.submit_job` -> `B200Worker.run_batch` -> PNG bytes (reference
+              `backends/worker_pool.py:84-88`, `backends/cuda_worker.py:201-239`), host in, host out
+  e2e_engine  the engine-level figure (pinned host tensors -> `LCMPipelineB200.generate` -> host u8)
+Config C3: the same at 768x768, 8 steps, batch 8.  Config C5: SDXL-base arch, 1024x1024, 30 steps, CFG 7.5,
+ONE image over the N ranks (CFG halves x row strips, `patch_parallel.py`), strong scaling.
 One JSON line is printed by rank 0.
 """
 from __future__ import annotations
@@ -19,15 +28,34 @@ import subprocess
 import sys
 import threading
 import time
+from types import SimpleNamespace
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "512x512 LCM 4-step images/sec (UNet+VAE)"
 UNIT = "images/s"
-GFLOP_UNET, GFLOP_VAE = 803.27, 2514.52            # per sample, BASELINE.md §3 (2*MAC)
-GFLOP_IMAGE = 4 * GFLOP_UNET + GFLOP_VAE           # 5727.6
+# algorithmic GFLOP per sample (2*MAC), SURVEY.md §8(d) / BASELINE.md §3
+CONFIGS = {
+    "c2": dict(arch="sd15", size=512, lcm_steps=4, batch=16, gs=1.0, gflop_unet=803.27, gflop_vae=2514.52,
+               metric="512x512 LCM 4-step images/sec (UNet+VAE)"),
+    "c3": dict(arch="sd15", size=768, lcm_steps=8, batch=8, gs=1.0, gflop_unet=2148.12, gflop_vae=5754.30,
+               metric="768x768 LCM 8-step images/sec (UNet+VAE)"),
+    "c5": dict(arch="sdxl", size=1024, lcm_steps=30, batch=1, gs=7.5, gflop_unet=2 * 6761.24, gflop_vae=10470.39,
+               metric="SDXL 1024x1024 30-step CFG 7.5 images/sec, one image over N GPUs (patch parallel)"),
+}
+
+
+def gflop_image(c):
+    return c["lcm_steps"] * c["gflop_unet"] + c["gflop_vae"]
+
+
+def workload_text(c, per_gpu=True):
+    if c["arch"] == "sdxl":
+        return (f"SDXL-base arch (random-init seed 0) {c['size']}x{c['size']}, {c['lcm_steps']} LCM steps, CFG {c['gs']}, "
+                f"1 image sharded over the ranks (UNet x{c['lcm_steps']} x2 CFG + scheduler + VAE decode)")
+    return (f"SD1.5-LCM arch (random-init seed 0) {c['size']}x{c['size']}, {c['lcm_steps']} LCM steps, guidance {c['gs']}, "
+            f"batch {c['batch']} per GPU (UNet x{c['lcm_steps']} + scheduler + VAE decode)")
 
 
 def peaks():
@@ -88,61 +116,168 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_sample(threads: int):
-    """Bounded sample of config C1 on the host cores: one UNet forward at the full 64^2 latent
-    + one VAE decode of a 32^2 latent (256^2 image; conv FLOPs scale with pixel count: x4).
-    images/s = 1 / (4 t_unet + 4 t_vae256)."""
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle (fp32 CPU restatement of the diffusers path) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(c, threads: int):
+    """-> (once, sample_text, extrapolated).  once() runs ONE bounded sample of the workload on the host
+    cores and returns (seconds the sample took, seconds per image it stands for).
+    SD1.5 configs: the sample IS one image of the batch — the full pass through
+    `oracle.pipeline.run_pipeline` (all UNet forwards + scheduler steps + the full-size VAE decode), so
+    seconds per image is measured, not extrapolated.  C5 (416 TFLOP per image, ~10 minutes of CPU) is the
+    one extrapolated case: one CFG UNet forward (batch 2) + the full 1024^2 decode, image = 30 x UNet + decode."""
     import torch
-    from oracle.pipeline import build_random_init, synthetic_inputs
-    from oracle.scheduler import guidance_scale_embedding
     torch.set_num_threads(threads)
-    unet, vae = build_random_init(seed=0)
-    pe, lat, _ = synthetic_inputs(1, 512, 512, 4)
-    w = guidance_scale_embedding(torch.zeros(1), 256)
-    z = torch.randn(1, 4, 32, 32, generator=torch.Generator().manual_seed(0))
+    if c["arch"] == "sd15":
+        from oracle.pipeline import build_random_init, run_pipeline, synthetic_inputs
+        unet, vae = build_random_init(seed=0)
+        pe, lat, noise = synthetic_inputs(1, c["size"], c["size"], c["lcm_steps"])
+
+        def once():
+            t0 = time.perf_counter()
+            run_pipeline(unet, vae, pe, lat, noise, c["lcm_steps"], c["gs"], tiling=False)
+            dt = time.perf_counter() - t0
+            return dt, dt
+        txt = (f"1 image of the batch (config C1 geometry, B=1): the full oracle pass run_pipeline() = {c['lcm_steps']} UNet "
+               f"forwards + scheduler steps + {c['size']}^2 VAE decode, fp32 torch CPU restatement of the diffusers path; "
+               f"images/s = 1 / seconds per pass (measured, not extrapolated)")
+        return once, txt, False
+    from oracle.pipeline import build_random_init, sdxl_time_ids, synthetic_inputs
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    unet, vae = build_random_init(UNetConfig.sdxl_base(), VAEConfig(scaling_factor=0.13025, sample_size=1024), seed=0)
+    pe, lat, _ = synthetic_inputs(1, c["size"], c["size"], 2, ctx_dim=2048)
+    pooled = torch.randn(1, 1280, generator=torch.Generator().manual_seed(2))
+    tid = sdxl_time_ids(c["size"], c["size"], 2)
 
     def once():
         with torch.no_grad():
             t0 = time.perf_counter()
-            unet(lat, torch.tensor(999), pe, w)
+            unet(torch.cat([lat, lat]), torch.tensor(999), torch.cat([torch.zeros_like(pe), pe]), None,
+                 text_embeds=torch.cat([torch.zeros_like(pooled), pooled]), time_ids=tid)
             t1 = time.perf_counter()
-            vae.decode(z)
+            vae(lat / vae.cfg.scaling_factor, tiling=False)
             t2 = time.perf_counter()
-        return 4 * (t1 - t0) + 4 * (t2 - t1), (t1 - t0), (t2 - t1)
-    return once
+        return t2 - t0, c["lcm_steps"] * (t1 - t0) + (t2 - t1)
+    txt = (f"EXTRAPOLATED: one CFG UNet forward (batch 2) + the {c['size']}^2 VAE decode of the fp32 CPU oracle; seconds per "
+           f"image = {c['lcm_steps']} x t_unet + t_vae (a full image is ~416 TFLOP of CPU work)")
+    return once, txt, True
 
 
-SAMPLE_TXT = ("config C1 (B=1, fp32 torch CPU restatement of the diffusers path): 1 UNet forward @64^2 "
-              "latent + 1 VAE decode @32^2 latent scaled x4 by pixel count; images/s = 1/(4*t_unet + 4*t_vae256)")
-
-
-def run_reference(args):
+def run_reference(args, c):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    once = cpu_oracle_sample(threads)
+    once, txt, extrapolated = cpu_reference(c, threads)
     for _ in range(args.warmup):
         once()
-    ts = [once()[0] for _ in range(args.steps)]
-    sec_per_image = sum(ts) / len(ts)
-    v = 1.0 / sec_per_image
+    runs = [once() for _ in range(args.steps)]
+    sample_s = [r[0] for r in runs]
+    per_image = statistics.median(r[1] for r in runs)
+    v = 1.0 / per_image
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_image,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"SD1.5-LCM arch (random-init seed 0) {args.size}x{args.size}, {args.lcm_steps} LCM steps, "
-                               f"guidance 1.0, batch {args.batch} per GPU (UNet x{args.lcm_steps} + scheduler + VAE decode)",
-                   "note": "reference arm = fp32 CPU port of the diffusers path on the host cores; each step is a "
-                           "bounded sample of the workload (see cpu_baseline.sample), rate is per image"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_TXT},
+        "impl": "reference", "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(sample_s) / len(sample_s),
+        "higher_is_better": True, "scaling": "strong" if c["arch"] == "sdxl" else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_text(c),
+                   "note": "reference arm = fp32 CPU port (oracle/) of the reference's diffusers path on the host cores; "
+                           "each step is one bounded sample of the workload (cpu_baseline.sample); value = median over "
+                           "the steps", "extrapolated": extrapolated},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": txt,
+                         "seconds_per_sample_median": statistics.median(sample_s)},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def run_b200(args):
+# ------------------------------------------------------------------------------------------------
+# plugin boundary: WorkerPool -> B200Worker -> PNG
+# ------------------------------------------------------------------------------------------------
+class _Modes:
+    """The slice of the reference's ModeConfigManager the pool reads (`server/mode_config.py:202-265`)."""
+
+    def __init__(self, root, model):
+        self.config = SimpleNamespace(model_root=root)
+        self._mode = SimpleNamespace(model=model, model_path=os.path.join(root, model), loras=[])
+
+    def get_default_mode(self):
+        return "bench"
+
+    def get_mode(self, name):
+        if name != "bench":
+            raise KeyError(name)
+        return self._mode
+
+
+class _Registry:
+    def get_used_vram(self):
+        return 0
+
+    def register_model(self, **kw):
+        pass
+
+    def unregister_model(self, name):
+        pass
+
+
+def bench_model_dir(c, rank, barrier):
+    """Random-init diffusers-layout model directory the worker loads (`MODEL_ROOT/MODEL`): written once
+    per box by rank 0."""
+    from dreamlab_b200 import synthetic as syn
+    root = os.environ.get("B200_BENCH_MODEL_ROOT", "/tmp/dreamlab_b200_bench_models")
+    name = "sd15-lcm" if c["arch"] == "sd15" else "sdxl-base"
+    path = os.path.join(root, name)
+    done = os.path.join(path, ".complete")
+    if rank == 0 and not os.path.exists(done):
+        if c["arch"] == "sd15":
+            syn.write_model_dir(path)
+        else:
+            syn.write_model_dir(path, syn.sdxl_unet_cfg(), syn.sdxl_vae_cfg())
+        open(done, "w").close()
+    barrier()
+    return root, name
+
+
+def make_pool(c, root, name, num_workers, device_env=None):
+    import contextlib
+    from backends.worker_factory import create_cuda_worker
+    from backends.worker_pool import WorkerPool
+    os.environ["MODEL_ROOT"], os.environ["MODEL"] = root, name
+    if device_env:
+        os.environ["CUDA_DEVICE"] = device_env
+    else:
+        os.environ.pop("CUDA_DEVICE", None)
+    with contextlib.redirect_stdout(sys.stderr):          # the workers announce themselves with print()
+        return WorkerPool(queue_max=1 << 16, worker_factory=create_cuda_worker, mode_config=_Modes(root, name),
+                          registry=_Registry(), num_workers=num_workers, max_batch=c["batch"])
+
+
+def pool_requests(pool, c, n, seed0):
+    from backends.worker_pool import GenerationJob
+    size = f"{c['size']}x{c['size']}"
+    return [pool.submit_job(GenerationJob(req=SimpleNamespace(
+        prompt=f"bench prompt {seed0 + i}", size=size, num_inference_steps=c["lcm_steps"],
+        guidance_scale=c["gs"], seed=seed0 + i))) for i in range(n)]
+
+
+def pool_e2e(pool, c, n_requests, warm_requests):
+    """-> (seconds for n_requests, mean PNG bytes).  Requests in (host objects), PNG bytes out."""
+    for f in pool_requests(pool, c, warm_requests, 0):          # graph capture, encoder threads, allocator
+        f.result(timeout=1200)
+    t0 = time.perf_counter()
+    outs = [f.result(timeout=1200) for f in pool_requests(pool, c, n_requests, 100000)]
+    dt = time.perf_counter() - t0
+    for png, _seed in outs[:2]:
+        assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    return dt, sum(len(o[0]) for o in outs) / len(outs)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm, SD1.5 configs (C2 / C3 / C4 shard)
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, c):
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -155,16 +290,30 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     import __graft_entry__ as g
     if rank == 0:
         g.build()
-    if world > 1:
-        dist.barrier()
+    barrier()
+    if c["arch"] == "sdxl":
+        return run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks)
     from dreamlab_b200 import lib
     from dreamlab_b200.engine import LCMPipelineB200
     from dreamlab_b200 import synthetic as syn
     from dreamlab_b200.synthetic import synthetic_inputs
-    B, size, nsteps = args.batch, args.size, args.lcm_steps
+    B, size, nsteps = c["batch"], c["size"], c["lcm_steps"]
+    GFLOP_IMAGE = gflop_image(c)
     ucfg, vcfg = syn.sd15_lcm_unet_cfg(), syn.sd_vae_cfg()
     pipe = LCMPipelineB200(syn.random_state_dict(syn.unet_shapes(ucfg), 0), ucfg,
                            syn.random_state_dict(syn.vae_decoder_shapes(vcfg), 1), vcfg, dev)
@@ -177,12 +326,6 @@ def run_b200(args):
     from dreamlab_b200.scheduler import guidance_scale_embedding
     gr.w_emb.copy_(guidance_scale_embedding(torch.zeros(B), 256))
     l2_flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)   # > 126 MB L2
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
         gr.graph.replay()
@@ -201,18 +344,13 @@ def run_b200(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = sum(step_ms)
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = t.item()
+    total_ms = max_over_ranks(sum(step_ms))
     value = world * B * args.steps / (total_ms / 1e3)
 
-    # ---- e2e: host pinned inputs -> public API -> host image, every step ----
+    # ---- e2e_engine: host pinned inputs -> engine API -> host image, every step ----
     pe_h, lat_h, noise_h = pe.pin_memory(), lat.pin_memory(), noise.pin_memory()
     img_h = torch.empty(B, size, size, 3, dtype=torch.uint8).pin_memory()
-    h2d = pe_h.numel() * 4 + lat_h.numel() * 4 + noise_h.numel() * 4 + B * 256 * 4
-    d2h = img_h.numel()
+    h2d_engine = pe_h.numel() * 4 + lat_h.numel() * 4 + noise_h.numel() * 4 + B * 256 * 4
 
     def e2e_once():
         img = pipe.generate(pe_h, lat_h, noise_h, nsteps, 1.0, use_graph=True)
@@ -226,10 +364,7 @@ def run_b200(args):
         e2e_once()
     e1.record()
     barrier()
-    te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (te.item() / 1e3)
+    e2e_engine = world * B * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
 
     # ---- roofline of the dominant kernel (igemm), CUDA events around every launch ----
     roof = None
@@ -241,16 +376,17 @@ def run_b200(args):
         ig = prof.get("igemm", {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
         tot_ms = sum(v["ms"] for v in prof.values())
         ach = ig["flops"] / (ig["ms"] / 1e3) / 1e12 if ig["ms"] > 0 else 0.0
-        # DRAM bytes per igemm launch from the committed ncu capture of this very workload
-        # (profiles/r01_ncu_dram_per_kernel_v7.*: dram__bytes_read.sum + dram__bytes_write.sum over
-        # the 922 igemm launches of one pass); only quoted for the configuration it was taken on
+        # DRAM bytes per igemm launch from the committed ncu capture of this very workload; only quoted
+        # for the configuration (and launch count) it was taken on
         traffic, traffic_src = None, None
-        tj = os.path.join(ROOT, "profiles", "r01_ncu_dram_per_kernel_v7.json")
-        if os.path.exists(tj) and (B, size, nsteps) == (16, 512, 4):
-            k = json.load(open(tj)).get("dl::igemm_kernel")
-            if k and k["launches"] == ig["n"]:
-                traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
-                traffic_src = "profiles/r01_ncu_dram_per_kernel_v7.json (ncu, same workload, per launch)"
+        for tj_name in ("r02_ncu_dram_per_kernel.json", "r01_ncu_dram_per_kernel_v7.json"):
+            tj = os.path.join(ROOT, "profiles", tj_name)
+            if os.path.exists(tj) and (B, size, nsteps) == (16, 512, 4):
+                k = json.load(open(tj)).get("dl::igemm_kernel")
+                if k and k["launches"] == ig["n"]:
+                    traffic = (k["dram_read_bytes"] + k["dram_write_bytes"]) / k["launches"]
+                    traffic_src = f"profiles/{tj_name} (ncu, same workload, per launch)"
+                    break
         roof = {"bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit-GEMM conv/linear)",
                 "achieved": ach, "peak": sustained, "peak_kind": f"bf16 dense sustained, {src}",
                 "unit": "TFLOP/s", "frac": ach / sustained, "traffic": traffic, "traffic_unit": "bytes/launch (DRAM)",
@@ -260,7 +396,12 @@ def run_b200(args):
                 "step_achieved_tflops": GFLOP_IMAGE * value / world / 1e3,
                 "step_frac": GFLOP_IMAGE * value / world / 1e3 / sustained,
                 "by_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
-        # the dominant HBM-bound kernel: one-pass GroupNorm(+SiLU) apply of the VAE decoder
+        at = prof.get("attention")
+        if at and at["ms"] > 0:
+            tf = at["flops"] / (at["ms"] / 1e3) / 1e12
+            roof["attention_kernel"] = {"bound": "tensor", "achieved": tf, "peak": sustained, "unit": "TFLOP/s",
+                                        "frac": tf / sustained, "launches": at["n"], "ms": round(at["ms"], 3)}
+        # the dominant HBM-bound kernel: one-pass GroupNorm(+SiLU) apply
         # (algorithmic 4 B/element: bf16 read once + written once), against the measured copy rate
         ga = prof.get("groupnorm_apply")
         if ga and ga["ms"] > 0:
@@ -286,35 +427,199 @@ def run_b200(args):
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b))
         lat_b1 = statistics.median(ts)
+    launches_per_step = gr.launches
+    del pipe, gr, l2_flush
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
-    # ---- CPU baseline (rank 0, N=1 only) ----
+    # ---- e2e through the plugin boundary: requests -> WorkerPool -> B200Worker -> PNG bytes ----
+    e2e = None
+    if not args.no_pool_e2e:
+        root, name = bench_model_dir(c, rank, barrier)
+        pool = make_pool(c, root, name, 1, device_env=f"cuda:{local}")
+        n_req = B * args.steps
+        barrier()
+        dt, png_bytes = pool_e2e(pool, c, n_req, 2 * B)
+        barrier()
+        dt = max_over_ranks(dt)
+        pool.shutdown()
+        D = 768
+        e2e = {"value": world * n_req / dt, "unit": UNIT,
+               # per step (= one batch of B requests): the prompt conditioning enters from the host
+               # (77 x 768 fp32 per request), latents / step noise are drawn on the device from the request's
+               # seed exactly as the reference's CUDA worker does (`cuda_worker.py:212-213`); u8 images leave
+               "h2d_bytes_per_step": B * 77 * D * 4 + B * 4,
+               "d2h_bytes_per_step": B * size * size * 3,
+               "path": "GenerationJob -> WorkerPool.submit_job -> B200Worker.run_batch -> PNG bytes",
+               "png": os.environ.get("B200_PNG", "pil"), "png_bytes_mean": png_bytes,
+               "requests": n_req * world, "timed": "wall clock, first submit to last PNG, max over ranks",
+               "host_cores": os.cpu_count()}
+
+    # ---- CPU baseline (rank 0, N=1 only): 1 warm-up + median of 3 full oracle passes ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        once = cpu_oracle_sample(threads)
+        once, txt, extrapolated = cpu_reference(c, threads)
         once()
-        s, tu, tv = once()
-        cpu = {"value": 1.0 / s, "unit": UNIT, "cores": threads, "kind": "port", "sample": SAMPLE_TXT,
-               "t_unet_s": tu, "t_vae256_s": tv}
+        runs = [once() for _ in range(3)]
+        per_image = statistics.median(r[1] for r in runs)
+        cpu = {"value": 1.0 / per_image, "unit": UNIT, "cores": threads, "kind": "port", "sample": txt,
+               "seconds_per_image_runs": [round(r[1], 3) for r in runs], "extrapolated": extrapolated}
 
     if rank == 0:
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"SD1.5-LCM arch (random-init seed 0) {size}x{size}, {nsteps} LCM steps, "
-                                   f"guidance 1.0, batch {B} per GPU (UNet x{nsteps} + scheduler + VAE decode)",
+            "config": {"workload": workload_text(c),
                        "batch_per_gpu": B, "global_batch": B * world, "l2": "flushed between timed iterations",
                        "cuda_graph": True, "parallelism": f"replicas x{world} (no collective)"},
             "p50_latency_ms_per_batch": statistics.median(step_ms),
             "p50_latency_ms_single_image": lat_b1,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": gr.launches * args.steps * world,
+            "e2e": e2e if e2e is not None else {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": h2d_engine,
+                                                "d2h_bytes_per_step": img_h.numel(), "path": "engine (pool e2e skipped)"},
+            "e2e_engine": {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": h2d_engine,
+                           "d2h_bytes_per_step": img_h.numel(),
+                           "path": "pinned host tensors -> LCMPipelineB200.generate (CUDA graph) -> pinned host u8"},
+            "gpu_launches": launches_per_step * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         }))
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm, config C5: one SDXL 1024^2 image over the ranks
+# ------------------------------------------------------------------------------------------------
+def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
+    import torch
+    from dreamlab_b200 import lib
+    from dreamlab_b200 import patch_parallel as pp
+    from dreamlab_b200 import synthetic as syn
+    from dreamlab_b200.engine import LCMPipelineB200
+    size, nsteps, gs = c["size"], c["lcm_steps"], c["gs"]
+    ucfg, vcfg = syn.sdxl_unet_cfg(), syn.sdxl_vae_cfg()
+    pipe = LCMPipelineB200(syn.random_state_dict(syn.unet_shapes(ucfg), 0, torch.bfloat16), ucfg,
+                           syn.random_state_dict(syn.vae_decoder_shapes(vcfg), 1, torch.bfloat16), vcfg, dev)
+    pdim = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
+    pe, lat, noise = syn.synthetic_inputs(1, size, size, nsteps, ctx_dim=ucfg.cross_attention_dim)
+    pooled = torch.randn(1, pdim, generator=torch.Generator().manual_seed(2))
+    pe_h, lat_h, noise_h, pooled_h = (t.pin_memory() for t in (pe, lat, noise, pooled))
+    pe_d, lat_d, noise_d, pooled_d = (t.to(dev) for t in (pe, lat, noise, pooled))
+    img_h = torch.empty(1, size, size, 3, dtype=torch.uint8).pin_memory()
+    peer = os.environ.get("B200_C5_EXCHANGE", "peer") == "peer"
+    if world > 1:
+        den = pp.dist_denoiser(pipe, peer=peer)
+
+        def step(host: bool):
+            a = (pe_h, pooled_h, lat_h, noise_h) if host else (pe_d, pooled_d, lat_d, noise_d)
+            img = den.generate(*a, nsteps, gs, use_graph=True, vae_strips=True)
+            if host:
+                img_h.copy_(img, non_blocking=True)
+    else:
+        def step(host: bool):
+            a = (pe_h, lat_h, noise_h) if host else (pe_d, lat_d, noise_d)
+            img = pipe.generate(*a, nsteps, gs, use_graph=True, pooled_embeds=pooled_h if host else pooled_d)
+            if host:
+                img_h.copy_(img, non_blocking=True)
+    n0 = lib.launch_count
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    barrier()
+    launches = None
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l2_flush = torch.empty(256 * 1024 * 1024, device=dev, dtype=torch.uint8)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        l2_flush.zero_()
+        a.record()
+        step(False)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = max_over_ranks(sum(step_ms))
+    value = args.steps / (total_ms / 1e3)
+    for _ in range(2):
+        step(True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(True)
+    e1.record()
+    barrier()
+    e2e_v = args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+    # launches of one eager pass on this rank (the graph replays exactly these)
+    n0 = lib.launch_count
+    if world > 1:
+        den.generate(pe_d, pooled_d, lat_d, noise_d, nsteps, gs, use_graph=False, vae_strips=True)
+    else:
+        pipe.generate(pe_d, lat_d, noise_d, nsteps, gs, pooled_embeds=pooled_d)
+    barrier()
+    launches = lib.launch_count - n0
+    if rank == 0:
+        sustained, burst, hbm, src = peaks()
+        tf = gflop_image(c) * value / 1e3
+        print(json.dumps({
+            "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_text(c), "l2": "flushed between timed iterations", "cuda_graph": True,
+                       "parallelism": ("1 GPU" if world == 1 else
+                                       f"CFG halves x row strips over {world} ranks, exchanges: "
+                                       f"{'NVLink peer-memory kernels' if peer else 'ncclAllGather'}; VAE decode as row strips")},
+            "ms_per_unet_step": total_ms / args.steps / nsteps,
+            "e2e": {"value": e2e_v, "unit": UNIT,
+                    "h2d_bytes_per_step": 4 * (pe.numel() + lat.numel() + noise.numel() + pooled.numel()),
+                    "d2h_bytes_per_step": img_h.numel(),
+                    "path": "pinned host tensors -> PatchParallelDenoiser.generate (CUDA graph) -> pinned host u8"},
+            "gpu_launches": launches * args.steps * world,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "whole pass (igemm + attention dominate)", "achieved": tf / world,
+                         "peak": sustained, "unit": "TFLOP/s per GPU", "frac": tf / world / sustained,
+                         "peak_kind": f"bf16 dense sustained, {src}", "traffic": None},
+            "cpu_baseline": None,
+        }))
+    sys.stdout.flush()
+    os._exit(0)        # NCCL collectives captured in CUDA graphs: communicator teardown can hang
+
+
+# ------------------------------------------------------------------------------------------------
+# ONE process, N GPU workers behind one WorkerPool (the product's multi-GPU path)
+# ------------------------------------------------------------------------------------------------
+def run_pool(args, c):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    import __graft_entry__ as g
+    g.build()
+    n = args.pool_workers
+    root, name = bench_model_dir(c, 0, lambda: None)
+    pool = make_pool(c, root, name, n)
+    B = c["batch"]
+    n_req = n * B * args.steps
+    dt, png_bytes = pool_e2e(pool, c, n_req, 2 * n * B)
+    pool.shutdown()
+    v = n_req / dt
+    print(json.dumps({
+        "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": 2,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_text(c), "parallelism": f"ONE process, WorkerPool with {n} B200Worker threads "
+                   f"(worker k on cuda:k), shared FIFO, micro-batches of {B}, PNG on encoder threads / GPU",
+                   "png": os.environ.get("B200_PNG", "pil"), "host_cores": os.cpu_count()},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": n * (B * 77 * 768 * 4 + B * 4),
+                "d2h_bytes_per_step": n * B * c["size"] * c["size"] * 3, "png_bytes_mean": png_bytes,
+                "path": "GenerationJob -> WorkerPool.submit_job -> B200Worker.run_batch -> PNG bytes",
+                "requests": n_req, "timed": "wall clock, first submit to last PNG"},
+        "gpu_launches": None,
+    }))
 
 
 def main():
@@ -323,15 +628,28 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16)
-    ap.add_argument("--size", type=int, default=512)
-    ap.add_argument("--lcm-steps", type=int, default=4)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the config's batch per GPU")
+    ap.add_argument("--size", type=int, default=0)
+    ap.add_argument("--lcm-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pool-e2e", action="store_true", help="skip the WorkerPool/PNG leg (kernel work only)")
+    ap.add_argument("--pool-workers", type=int, default=0,
+                    help="one process, WorkerPool with this many GPU workers; prints the e2e line only")
     args = ap.parse_args()
+    c = dict(CONFIGS[args.config])
+    if args.batch:
+        c["batch"] = args.batch
+    if args.size:
+        c["size"] = args.size
+    if args.lcm_steps:
+        c["lcm_steps"] = args.lcm_steps
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, c)
+    elif args.pool_workers:
+        run_pool(args, c)
     else:
-        run_b200(args)
+        run_b200(args, c)
 
 
 if __name__ == "__main__":

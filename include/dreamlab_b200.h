@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DL_ABI_VERSION 2
+#define DL_ABI_VERSION 3
 
 /* ---- library ---------------------------------------------------------------------------- */
 int dl_abi_version(void);
@@ -208,7 +208,7 @@ int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidanc
 
 /* ---- run_job_with_latents tail: fp32 adaptive_avg_pool2d -> (8,8) -> fp16 NCHW ------------- *
  * (reference `backends/cuda_worker.py:297-304`).  lat: fp32 NHWC [nimg,h,w,c]; out: fp16
- * [nimg,c,8,8].  h, w multiples of 8.                                                         */
+ * [nimg,c,8,8].  Any h, w >= 1: adaptive_avg_pool2d bins [floor(i*h/8), ceil((i+1)*h/8)).      */
 int dl_latent_pool8(const float* lat, int nimg, int h, int w, int c, void* out_f16, void* stream);
 
 /* ---- all-gather over NVLink peer memory (SDXL patch parallel) ---------------
@@ -245,6 +245,18 @@ int dl_im2col_s2_f32(const float* x, int nimg, int h, int w, int c, float* cols,
 int dl_softmax_rows_f32(const float* scores, long long rows, int cols, float* out, void* stream);
 int dl_small_linear_f32(const float* x, int m, int k, const float* w, const float* bias,
                         const float* add, int n, int silu_in, int silu_out, float* out, void* stream);
+
+/* ---- PNG files assembled on the device (B200_PNG=gpu) -------------------------------------------
+ * Replaces the host-side `img.save(buf, format="PNG")` that ends every job (reference
+ * `backends/cuda_worker.py:234-239`; 70-100 ms of zlib per 512x512 image and core).  img: u8 NHWC
+ * [nimg,h,w,3]; out: u8 [nimg, out_stride], each row one complete PNG file of dl_png_stored_size(h,w)
+ * bytes: 8-bit RGB, filter 0, zlib stream of stored deflate blocks, Adler-32 / CRC-32 computed by the
+ * kernels.  out 4-byte aligned, out_stride a multiple of 4 and >= the size rounded up to 4;
+ * workspace: dl_png_stored_workspace_bytes(nimg, h) bytes.  Deterministic (same pixels -> same bytes). */
+long long dl_png_stored_size(int h, int w);
+long long dl_png_stored_workspace_bytes(int nimg, int h);
+int dl_png_stored(const void* img_u8, int nimg, int h, int w, void* out, long long out_stride,
+                  void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,7 @@
 // barrier per tile) and runs P over the S columns, so S_{j+1} cannot start before the exp pass of
 // tile j is over; measured 26 % of the tensor roofline with the XU pipe 54 % busy.
 //
-// This kernel (one CTA per SM, 256 queries per CTA):
+// This kernel, NQ = 2 (one CTA per SM, 256 queries per CTA; NQ = 1: 128 queries per CTA, two CTAs per SM):
 //   warp 0      TMA producer: Q (2 x 128 rows) once, K_j / V_j (128 keys) through an mbarrier ring,
 //               fetched ONCE for 256 query rows
 //   warp 1      MMA issuer: S_w = Q_w K_j^T (SS) and O_w += P_w V_j (TS, P from TMEM) for both
@@ -22,6 +22,9 @@
 //               columns — so the tensor core computes S_w,j+1 as soon as group w holds S_w,j in
 //               registers, i.e. under the exp pass, and a softmax group never waits for S.
 //   TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O0 [384,448) O1 [448,512)
+//   NQ = 1: one query tile per CTA, 256 columns (S [0,128) P [128,192) O [192,256)), two CTAs per SM with
+//   their own K/V rings: the prologue (TMEM allocation, Q / K / V fetch, first S) and the epilogue of one CTA
+//   run under the steady state of the other, and the two tiles are no longer coupled through one issuer.
 // The softmax denominator is accumulated by the tensor core through V's ones column (as in
 // attention.cu); running max is lazy (moved only when the tile max exceeds it by 2^8).
 #include <stdlib.h>
@@ -31,7 +34,6 @@
 
 namespace dl {
 
-constexpr int PP_THREADS = 320;
 constexpr int PP_TILE = 128;                      // queries per tile (two per CTA), keys per K/V tile
 constexpr int PP_TILE_BYTES = PP_TILE * 128;      // [128 rows x 64 bf16] swizzled block
 
@@ -43,7 +45,7 @@ struct AttnPPParams {
   int dv;            // PV MMA N (multiple of 16, <= 64): head dim + ones column, padded
   int l_col;         // O column holding the softmax denominator
   int stages;
-  int stagger;       // clocks softmax group 1 idles before its first tile (de-synchronises the two groups)
+  int smem_bytes;    // dynamic shared memory of the launch (checked against the carve-up on the device)
   float scale_log2;
 };
 
@@ -72,15 +74,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 }
 
 // KS: QK^T K-steps of 16 (3: head dim 40, 4: head dim <= 64).  kPoly: of every 8 score pairs, this
-// many take 2^x from the packed polynomial (FMA / ALU pipes) instead of MUFU.EX2.
-template <int KS, int kPoly>
-__global__ void __launch_bounds__(PP_THREADS, 1)
+// many take 2^x from the packed polynomial (FMA / ALU pipes) instead of MUFU.EX2.  NQ: query tiles per CTA.
+template <int KS, int kPoly, int NQ>
+__global__ void __launch_bounds__(64 + 128 * NQ, 3 - NQ)
 attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
+  static_assert(NQ == 1 || NQ == 2, "one or two query tiles per CTA");
+  constexpr uint32_t TMEM_COLS = 256u * NQ;
+  constexpr uint32_t P_COL = 128u * NQ, O_COL = 192u * NQ;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // 2 x 16 KB
-  uint8_t* sKV = smem + 2 * PP_TILE_BYTES;              // stages x (K 16 KB | V 16 KB)
+  uint8_t* sKV = smem + NQ * PP_TILE_BYTES;             // stages x (K 16 KB | V 16 KB)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + (size_t)p.stages * 2 * PP_TILE_BYTES);
   uint64_t* q_full = bars;                   // 1
   uint64_t* k_full = bars + 1;               // [stages]
@@ -92,9 +97,12 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
   uint64_t* p_ready = s_taken + 2;           // [2]  P_w,j written (and O_w rescaled)
   uint64_t* pv_done = p_ready + 2;           // [2]  O_w += P_w,j V_j retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  // the launch reserves < 1 KB of alignment slack (two CTAs of NQ = 1 must fit one SM): a dynamic segment
+  // that starts less aligned than assumed becomes a launch error, not silent corruption
+  if (threadIdx.x == 0 && reinterpret_cast<uint8_t*>(tmem_slot + 1) - smem_raw > p.smem_bytes) __trap();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * PP_TILE;
+  const int q0 = blockIdx.x * NQ * PP_TILE;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = (p.skv + PP_TILE - 1) / PP_TILE;
 
@@ -107,13 +115,13 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
     }
-    for (int w = 0; w < 2; ++w) {
+    for (int w = 0; w < NQ; ++w) {
       mbar_init(&s_full[w], 1); mbar_init(&s_taken[w], 4);
       mbar_init(&p_ready[w], 4); mbar_init(&pv_done[w], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512u); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -124,9 +132,9 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
     const bool issuer = elect_one();
     const int col0 = h * p.dh_stride;
     if (issuer) {
-      mbar_expect_tx(q_full, 2u * PP_TILE_BYTES);
+      mbar_expect_tx(q_full, (uint32_t)(NQ * PP_TILE_BYTES));
       tma_load_2d(sQ, &p.tmQ, q_full, col0, b * p.sq + q0);
-      tma_load_2d(sQ + PP_TILE_BYTES, &p.tmQ, q_full, col0, b * p.sq + q0 + PP_TILE);
+      if (NQ == 2) tma_load_2d(sQ + PP_TILE_BYTES, &p.tmQ, q_full, col0, b * p.sq + q0 + PP_TILE);
     }
     __syncwarp();
     auto load = [&](int t, bool is_v) {
@@ -171,7 +179,7 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
-    issue_s(1, 0);
+    if (NQ == 2) issue_s(1, 0);
     if (issuer) umma_commit(&k_empty[0]);
     __syncwarp();
     int stage = 0;
@@ -183,7 +191,7 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
       if (j + 1 < n_tiles) {
         // S_w,j+1 as soon as group w has S_w,j in registers: it runs under the exp pass
         mbar_wait(&k_full[nstage], nphase);
-        for (int w = 0; w < 2; ++w) {
+        for (int w = 0; w < NQ; ++w) {
           mbar_wait(&s_taken[w], (uint32_t)(j & 1));
           tc_fence_after();
           issue_s(w, nstage);
@@ -195,12 +203,12 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
       // V is the MN-major B operand: SBO = 8-key groups (1024 B); one 64-wide d chunk, LBO unused
       const uint32_t v_lo = umma_desc_lo(skv_addr + (uint32_t)(stage * 2 * PP_TILE_BYTES + PP_TILE_BYTES),
                                          (uint32_t)PP_TILE_BYTES);
-      for (int w = 0; w < 2; ++w) {
+      for (int w = 0; w < NQ; ++w) {
         mbar_wait(&p_ready[w], (uint32_t)(j & 1));
         tc_fence_after();
         if (issuer) {
-          const uint32_t o_tmem = tmem_base + 384u + (uint32_t)(w * 64);
-          const uint32_t p_tmem = tmem_base + 256u + (uint32_t)(w * 64);
+          const uint32_t o_tmem = tmem_base + O_COL + (uint32_t)(w * 64);
+          const uint32_t p_tmem = tmem_base + P_COL + (uint32_t)(w * 64);
 #pragma unroll
           for (int ks = 0; ks < PP_TILE / 16; ++ks)   // 16 keys = two 8-row atoms = 2048 B; P: 8 packed columns
             umma_ts_lohi(o_tmem, p_tmem + (uint32_t)(ks * 8), v_lo + (uint32_t)(ks * 128), hi_k, idesc_o,
@@ -221,15 +229,11 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
     const int r = quad * 32 + lane;                // row of the 128-row tile
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t s_tmem = tmem_base + lane_off + (uint32_t)(w * PP_TILE);
-    const uint32_t p_tmem = tmem_base + lane_off + 256u + (uint32_t)(w * 64);
-    const uint32_t o_tmem = tmem_base + lane_off + 384u + (uint32_t)(w * 64);
+    const uint32_t p_tmem = tmem_base + lane_off + P_COL + (uint32_t)(w * 64);
+    const uint32_t o_tmem = tmem_base + lane_off + O_COL + (uint32_t)(w * 64);
     const float sc = p.scale_log2;
     const uint64_t sc2 = f2_pack(sc, sc);
     float m_run = -INFINITY;
-    if (w == 1 && p.stagger > 0) {
-      const long long t0 = clock64();
-      while (clock64() - t0 < p.stagger) { }
-    }
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[w], (uint32_t)(j & 1));
       tc_fence_after();
@@ -365,7 +369,7 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512u);
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // -> 0 launched, 1 error, -1 shape not covered (caller falls through to attn_tc_kernel)
@@ -388,12 +392,18 @@ int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, c
   p.sq = sq; p.skv = skv; p.d = d; p.dh_stride = dh_stride;
   p.dv = dv;
   p.l_col = d;
-  p.stages = 4;
-  {
-    static int stagger = -1;
-    if (stagger < 0) { const char* e = getenv("DL_ATTN_PP_STAGGER"); stagger = e ? atoi(e) : 0; }
-    p.stagger = stagger;
-  }
+  // DL_ATTN_PP_NQ = query tiles per CTA: 1 (default: two CTAs per SM, each with its own K/V ring; measured on B200,
+  // B = 16, S = 4096, d = 40: 690 us) or 2 (one CTA per SM, K/V fetched once for 256 rows: 716 us)
+  static int nq = -2, poly = -2;
+  if (nq == -2) { const char* e = getenv("DL_ATTN_PP_NQ"); nq = e ? atoi(e) : 1; }
+  // share of the exponentials on the FMA pipe: DL_ATTN_PP_POLY = 0 / 2 / 3 of every 8 pairs
+  if (poly == -2) { const char* e = getenv("DL_ATTN_PP_POLY"); poly = e ? atoi(e) : 2; }
+  const int NQr = nq == 1 ? 1 : 2;
+  const int overhead = 512 + 256;              // alignment slack + barriers
+  const int budget = (NQr == 1 ? (228 * 1024) / 2 - 1024 : 200 * 1024) - overhead;
+  p.stages = (budget - NQr * PP_TILE_BYTES) / (2 * PP_TILE_BYTES);
+  if (p.stages > 4) p.stages = 4;
+  DL_CHECK_ARG(p.stages >= 2, "attention(pp): not enough shared memory for 2 K/V stages");
   p.scale_log2 = scale * 1.4426950408889634f;
   const uint32_t box[2] = {64, PP_TILE};
   {
@@ -411,7 +421,8 @@ int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, c
     const uint64_t str[1] = {(uint64_t)ldv * 2};
     if (make_tmap_bf16(&p.tmV, v, 2, dims, str, box)) return 1;
   }
-  const int smem_bytes = 2 * PP_TILE_BYTES + p.stages * 2 * PP_TILE_BYTES + 1024 + 512;
+  const int smem_bytes = NQr * PP_TILE_BYTES + p.stages * 2 * PP_TILE_BYTES + overhead;
+  p.smem_bytes = smem_bytes;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -420,25 +431,27 @@ int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, c
 #define DL_PP_ATTR(...)                                                                         \
   if (e == cudaSuccess)                                                                         \
     e = cudaFuncSetAttribute(attn_pp_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-    DL_PP_ATTR(3, 0); DL_PP_ATTR(3, 2); DL_PP_ATTR(3, 3); DL_PP_ATTR(3, 4);
-    DL_PP_ATTR(4, 0); DL_PP_ATTR(4, 2); DL_PP_ATTR(4, 3); DL_PP_ATTR(4, 4);
+    DL_PP_ATTR(3, 0, 1); DL_PP_ATTR(3, 2, 1); DL_PP_ATTR(3, 3, 1);
+    DL_PP_ATTR(4, 0, 1); DL_PP_ATTR(4, 2, 1); DL_PP_ATTR(4, 3, 1);
+    DL_PP_ATTR(3, 0, 2); DL_PP_ATTR(3, 2, 2); DL_PP_ATTR(3, 3, 2);
+    DL_PP_ATTR(4, 0, 2); DL_PP_ATTR(4, 2, 2); DL_PP_ATTR(4, 3, 2);
 #undef DL_PP_ATTR
     if (e != cudaSuccess) { set_error("attention(pp): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
   }
-  // share of the exponentials on the FMA pipe: DL_ATTN_PP_POLY = 0 / 2 / 3 / 4 of every 8 pairs
-  static int poly = -2;
-  if (poly == -2) { const char* e = getenv("DL_ATTN_PP_POLY"); poly = e ? atoi(e) : 2; }
-  dim3 grid((sq + 2 * PP_TILE - 1) / (2 * PP_TILE), heads, batch);
+  dim3 grid((sq + NQr * PP_TILE - 1) / (NQr * PP_TILE), heads, batch);
   const int ks = d16 / 16;
-#define DL_PP_LAUNCH(KS_, PL_) attn_pp_kernel<KS_, PL_><<<grid, PP_THREADS, smem_bytes, stream>>>(p)
-  if (ks <= 3) {
-    if (poly <= 0) DL_PP_LAUNCH(3, 0); else if (poly == 2) DL_PP_LAUNCH(3, 2);
-    else if (poly == 3) DL_PP_LAUNCH(3, 3); else DL_PP_LAUNCH(3, 4);
-  } else {
-    if (poly <= 0) DL_PP_LAUNCH(4, 0); else if (poly == 2) DL_PP_LAUNCH(4, 2);
-    else if (poly == 3) DL_PP_LAUNCH(4, 3); else DL_PP_LAUNCH(4, 4);
-  }
+  const int pl = poly <= 0 ? 0 : (poly >= 3 ? 3 : 2);
+#define DL_PP_LAUNCH(KS_, PL_, NQ_) \
+  attn_pp_kernel<KS_, PL_, NQ_><<<grid, 64 + 128 * NQ_, smem_bytes, stream>>>(p)
+#define DL_PP_PICK(KS_, NQ_)                                                                   \
+  do {                                                                                          \
+    if (pl == 0) DL_PP_LAUNCH(KS_, 0, NQ_); else if (pl == 2) DL_PP_LAUNCH(KS_, 2, NQ_);        \
+    else DL_PP_LAUNCH(KS_, 3, NQ_);                                                             \
+  } while (0)
+  if (ks == 3) { if (NQr == 1) DL_PP_PICK(3, 1); else DL_PP_PICK(3, 2); }
+  else { if (NQr == 1) DL_PP_PICK(4, 1); else DL_PP_PICK(4, 2); }
+#undef DL_PP_PICK
 #undef DL_PP_LAUNCH
   return check_launch("attention(pp)");
 }

@@ -612,6 +612,16 @@ class VAEDecoderB200:
 # ------------------------------------------------------------------------------------------------
 # pipeline: denoise loop + decode
 # ------------------------------------------------------------------------------------------------
+# Warm-up + capture of ALL pipelines of the process are serialised: the WorkerPool runs one worker thread
+# per GPU in one process and every worker captures lazily on first use of a geometry.  The capture itself
+# uses capture_error_mode="thread_local", so CUDA calls of the OTHER worker threads (caching-allocator
+# cudaMalloc, event queries) neither fail with "operation not permitted when stream is capturing" nor
+# invalidate this capture.
+import threading as _threading
+
+CAPTURE_LOCK = _threading.Lock()
+
+
 class _StaticGraph:
     """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps[, gs])."""
 
@@ -633,18 +643,19 @@ class _StaticGraph:
         self.steps = steps
         args = (self.pe, self.w_emb, self.lat, self.noise, steps)
         kw = dict(add=self.add, cfg_scale=cfg_scale)
-        # warm-up on a side stream (lazy per-device init: smem attributes, module load)
-        s = torch.cuda.Stream(device=dev)
-        s.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(s):
-            pipe.run_static(*args, **kw)
-        torch.cuda.current_stream(dev).wait_stream(s)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = lib.launch_count
-        with torch.cuda.graph(self.graph):
-            self.img, self.final = pipe.run_static(*args, **kw)
-        self.launches = lib.launch_count - n0        # native kernel launches per replay
+        with CAPTURE_LOCK:
+            # warm-up on a side stream (lazy per-device init: smem attributes, module load)
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                pipe.run_static(*args, **kw)
+            torch.cuda.current_stream(dev).wait_stream(s)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = lib.launch_count
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.img, self.final = pipe.run_static(*args, **kw)
+            self.launches = lib.launch_count - n0        # native kernel launches per replay
 
 
 class LCMPipelineB200:
@@ -691,7 +702,7 @@ class LCMPipelineB200:
 
     @torch.no_grad()
     def run_static(self, pe_bf16, w_emb, lat_nchw, noise_nchw, steps: int, record: dict = None,
-                   add=None, cfg_scale: Optional[float] = None):
+                   add=None, cfg_scale: Optional[float] = None, teacher=None):
         """Everything on device, no host sync, graph-capturable.  Returns (u8 images, latents).
         pe_bf16 / add carry 2B rows ([uncond, cond]) when cfg_scale is set."""
         B = lat_nchw.shape[0]
@@ -700,7 +711,7 @@ class LCMPipelineB200:
         kvs = self.unet.encode_context(pe_bf16)
         aug = self.unet.addition_embedding(*add) if add is not None else None
         tembs = self.unet.time_embeddings(sched.timesteps, Bu, w_emb, aug)
-        lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale)
+        lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale, teacher=teacher)
         return self.vae.decode(lat, tiling=self.vae_tiling), lat
 
     max_graphs = 12       # captured geometries kept per pipeline (each owns its activation pool)
@@ -718,8 +729,11 @@ class LCMPipelineB200:
 
     @torch.no_grad()
     def denoise(self, latents_nchw, step_noise_nchw, sched, kvs, tembs, record: dict = None,
-                cfg_scale: Optional[float] = None):
-        """latents fp32 NCHW [B,4,h,w]; step_noise [steps-1,B,4,h,w].  Returns final latents NHWC."""
+                cfg_scale: Optional[float] = None, teacher=None):
+        """latents fp32 NCHW [B,4,h,w]; step_noise [steps-1,B,4,h,w].  Returns final latents NHWC.
+        teacher (parity tests): fp32 NCHW [steps,B,4,h,w] — the latents fed to the UNet at step i
+        come from this tensor (an oracle trajectory) instead of from the previous step, so every
+        step's noise_pred is compared on identical inputs (teacher forcing)."""
         B, C, H, W = latents_nchw.shape
         x = torch.empty(B, H, W, C, device=self.device, dtype=torch.float32)
         lib.nchw_to_nhwc_f32(latents_nchw, x)
@@ -730,7 +744,14 @@ class LCMPipelineB200:
             lib.nchw_to_nhwc_f32(step_noise_nchw[:n - 1].reshape((n - 1) * B, C, H, W),
                                  noise.view((n - 1) * B, H, W, C))
         den = torch.empty_like(x)
+        tx = None
+        if teacher is not None:
+            tx = torch.empty(n, B, H, W, C, device=self.device, dtype=torch.float32)
+            lib.nchw_to_nhwc_f32(teacher.to(self.device, torch.float32).reshape(n * B, C, H, W).contiguous(),
+                                 tx.view(n * B, H, W, C))
         for i in range(n):
+            if tx is not None:
+                x = tx[i]
             if cfg_scale is None:
                 eps = self.unet.forward(x, tembs[i], kvs)
             else:
@@ -775,7 +796,7 @@ class LCMPipelineB200:
     def generate(self, prompt_embeds, latents_nchw, step_noise_nchw, num_inference_steps: int,
                  guidance_scale=1.0, record: dict = None, return_latents: bool = False,
                  use_graph: bool = False, pooled_embeds=None, time_ids=None,
-                 negative_prompt_embeds=None, negative_pooled_embeds=None):
+                 negative_prompt_embeds=None, negative_pooled_embeds=None, teacher_latents=None):
         """Public entry: host or device tensors in -> u8 images [B,H,W,3] on device (and the
         final latents NHWC fp32 if asked).  With use_graph the whole pass is one CUDA-graph
         replay; the returned tensors are the graph's static outputs (consume before next call)."""
@@ -786,7 +807,7 @@ class LCMPipelineB200:
         pe_all, add = self._conditioning(prompt_embeds, pooled_embeds, time_ids, negative_prompt_embeds,
                                          negative_pooled_embeds, cfg_scale, 8 * h, 8 * w)
         with torch.cuda.device(self.device):
-            if use_graph and record is None:
+            if use_graph and record is None and teacher_latents is None:
                 g = self.graph_for(B, h, w, steps, cfg_scale)
                 g.pe.copy_(pe_all, non_blocking=True)
                 if w_emb is not None:
@@ -807,5 +828,6 @@ class LCMPipelineB200:
                 lat0 = latents_nchw.to(self.device, torch.float32).contiguous()
                 nz = (step_noise_nchw.to(self.device, torch.float32).contiguous()
                       if steps > 1 else None)
-                img, lat = self.run_static(pe, we, lat0, nz, steps, record, add=add, cfg_scale=cfg_scale)
+                img, lat = self.run_static(pe, we, lat0, nz, steps, record, add=add, cfg_scale=cfg_scale,
+                                           teacher=teacher_latents)
         return (img, lat) if return_latents else img

@@ -28,6 +28,7 @@ EXPORTS = [
     "dl_groupnorm_finalize", "dl_embed_tokens", "dl_act_bf16",
     "dl_peer_allgather", "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
     "dl_im2col_s2_f32", "dl_softmax_rows_f32", "dl_small_linear_f32",
+    "dl_png_stored_size", "dl_png_stored_workspace_bytes", "dl_png_stored",
 ]
 
 
@@ -143,6 +144,12 @@ def load() -> C.CDLL:
                                            C.c_void_p]
             lib.dl_latent_pool8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_void_p]
+            lib.dl_png_stored_size.restype = C.c_longlong
+            lib.dl_png_stored_size.argtypes = [C.c_int, C.c_int]
+            lib.dl_png_stored_workspace_bytes.restype = C.c_longlong
+            lib.dl_png_stored_workspace_bytes.argtypes = [C.c_int, C.c_int]
+            lib.dl_png_stored.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                          C.c_void_p, C.c_void_p]
             _lib = lib
     return _lib
 
@@ -541,3 +548,23 @@ def latent_pool8(lat_nhwc, out_f16):
     _check(load().dl_latent_pool8(lat_nhwc.data_ptr(), n, h, w, c, out_f16.data_ptr(), _stream()),
            "latent_pool8")
     _count()
+
+
+def png_stored_size(h, w) -> int:
+    return int(load().dl_png_stored_size(h, w))
+
+
+def png_stored(img_u8, out=None):
+    """img u8 NHWC [n,h,w,3] on the device -> (u8 [n, stride] with one PNG file per row, file size)."""
+    n, h, w, c = img_u8.shape
+    if c != 3 or img_u8.dtype != torch.uint8 or not img_u8.is_contiguous():
+        raise RuntimeError("png_stored: contiguous u8 [n,h,w,3] expected")
+    size = png_stored_size(h, w)
+    stride = (size + 3) & ~3
+    if out is None:
+        out = torch.empty(n, stride, device=img_u8.device, dtype=torch.uint8)
+    ws = torch.empty(load().dl_png_stored_workspace_bytes(n, h), device=img_u8.device, dtype=torch.uint8)
+    _check(load().dl_png_stored(img_u8.data_ptr(), n, h, w, out.data_ptr(), out.stride(0), ws.data_ptr(), _stream()),
+           "png_stored")
+    _count(2)
+    return out, size

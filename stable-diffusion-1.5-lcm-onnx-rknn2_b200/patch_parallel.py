@@ -279,7 +279,8 @@ class PatchParallelDenoiser:
         return topo, comm, pe_all, add, w_emb, repeat, cfg_scale
 
     @torch.no_grad()
-    def _loop(self, topo, comm, pe, add, we, repeat, cfg_scale, lat_nchw, noise_nchw, steps, record=None):
+    def _loop(self, topo, comm, pe, add, we, repeat, cfg_scale, lat_nchw, noise_nchw, steps, record=None,
+              teacher=None):
         """Device tensors in, final latents NHWC out; no host sync (graph-capturable)."""
         from . import lib
         from .scheduler import LCMSchedule
@@ -298,7 +299,14 @@ class PatchParallelDenoiser:
             lib.nchw_to_nhwc_f32(noise_nchw[:steps - 1].reshape((steps - 1) * B, C, H, W),
                                  noise.view((steps - 1) * B, H, W, C))
         den = torch.empty_like(x)
+        tx = None
+        if teacher is not None:          # parity tests: step i starts from a given trajectory (teacher forcing)
+            tx = torch.empty(steps, B, H, W, C, device=dev, dtype=torch.float32)
+            lib.nchw_to_nhwc_f32(teacher.to(dev, torch.float32).reshape(steps * B, C, H, W).contiguous(),
+                                 tx.view(steps * B, H, W, C))
         for i in range(steps):
+            if tx is not None:
+                x = tx[i]
             strip = pipe.unet.forward(x, tembs[i], kvs, repeat=repeat, comm=comm)
             e_u, e_t = assemble_eps(self.world.all_gather(strip), topo, B)
             if e_t is not None:
@@ -319,7 +327,7 @@ class PatchParallelDenoiser:
 
     @torch.no_grad()
     def denoise(self, prompt_embeds, pooled_embeds, latents_nchw, step_noise_nchw, steps: int,
-                guidance_scale: float, record: dict = None, use_graph: bool = False):
+                guidance_scale: float, record: dict = None, use_graph: bool = False, teacher_latents=None):
         """Inputs as `LCMPipelineB200.generate` (host or device, identical on every rank).
         Returns the final latents NHWC fp32 (identical on every rank).  use_graph: the whole
         loop — kernels and collectives — is captured once per geometry and replayed (one image
@@ -336,8 +344,9 @@ class PatchParallelDenoiser:
             we = w_emb.to(dev) if w_emb is not None else None
             lat0 = latents_nchw.to(dev, torch.float32).contiguous()
             nz = step_noise_nchw.to(dev, torch.float32).contiguous() if steps > 1 else None
-            if not use_graph or record is not None:
-                return self._loop(topo, comm, pe, add, we, repeat, cfg_scale, lat0, nz, steps, record)
+            if not use_graph or record is not None or teacher_latents is not None:
+                return self._loop(topo, comm, pe, add, we, repeat, cfg_scale, lat0, nz, steps, record,
+                                  teacher=teacher_latents)
             key = (B, H, W, steps, cfg_scale)
             g = self._graphs.get(key)
             if g is None:
@@ -354,7 +363,7 @@ class PatchParallelDenoiser:
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
                 f0 = getattr(comm, "_fcalls", 0)
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     st["out"] = self._loop(*args())
                 if (getattr(comm, "_fcalls", 0) - f0) % 2:
                     raise RuntimeError("patch parallel: a captured loop must issue an even number of fused "

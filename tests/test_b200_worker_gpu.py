@@ -67,6 +67,10 @@ def test_sizes_and_errors(worker):
         assert Image.open(io.BytesIO(png)).size == (w, h)
     with pytest.raises(RuntimeError, match="Invalid size"):
         worker.run_job(job(size="banana"))
+    # sizes the UNet cannot halve exactly at every level are refused up front with a clear message
+    # (they used to fail deep in the pass with 'im2col_s2: bad args')
+    with pytest.raises(RuntimeError, match="multiples of"):
+        worker.run_job(job(size="72x72"))
     a = worker.run_job(job(seed=None))
     b = worker.run_job(job(seed=None))
     assert a[1] != b[1] and a[0] != b[0]
@@ -216,3 +220,25 @@ def test_yume_style_quick_job(worker):
     arr, seed2 = worker.run_job_array(j)
     assert seed == seed2 == 11 and arr.shape == (64, 64, 3) and arr.dtype == np.uint8
     assert np.array_equal(np.asarray(Image.open(io.BytesIO(png))), arr)
+
+
+def test_gpu_png_mode_same_pixels_and_deterministic(worker, monkeypatch):
+    """B200_PNG=gpu: the PNG file is assembled on the device (csrc/png.cu).  The contract the reference's tests
+    pin (`tests/test_sdxl_worker.py:139-198`): PNG magic, seed echo, same seed => byte-identical file; plus it
+    decodes to exactly the pixels of the default (PIL) path and equals the oracle's stored-deflate file."""
+    import numpy as np
+    from PIL import Image
+    from oracle.png import png_stored
+    ref_png, _ = worker.run_job(job(seed=42))
+    arr, _ = worker.run_job_array(job(seed=42))
+    monkeypatch.setenv("B200_PNG", "gpu")
+    png, seed = worker.run_job(job(seed=42))
+    assert png[:8] == b"\x89PNG\r\n\x1a\n" and seed == 42
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(png))), np.asarray(Image.open(io.BytesIO(ref_png))))
+    assert png == png_stored(arr)
+    assert worker.run_job(job(seed=42))[0] == png
+    batch = worker.run_batch([job(prompt=f"p{i}", seed=200 + i) for i in range(3)], with_latents=True)
+    assert all(b[0][:8] == b"\x89PNG\r\n\x1a\n" and len(b[2]) == 512 for b in batch)
+    monkeypatch.setenv("B200_PNG", "jpeg")
+    with pytest.raises(RuntimeError, match="B200_PNG"):
+        worker.run_job(job(seed=42))

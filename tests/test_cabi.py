@@ -29,7 +29,7 @@ def test_header_symbols_are_exported(lib):
     missing = [n for n in names if not hasattr(l, n)]
     assert not missing, missing
     assert sorted(lib.EXPORTS) == names
-    assert l.dl_abi_version() == 2
+    assert l.dl_abi_version() == 3
 
 
 def test_fails_loudly_without_gpu(lib):

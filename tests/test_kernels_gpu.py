@@ -260,6 +260,10 @@ def test_attention_tc(B, Sq, Skv, heads, d):
 ])
 @pytest.mark.parametrize("poly", ["0", "3"])
 def test_attention_pp_two_query_tiles(B, Sq, Skv, heads, d, poly):
+    _attention_pp_case(B, Sq, Skv, heads, d, poly)
+
+
+def _attention_pp_case(B, Sq, Skv, heads, d, poly):
     """attention_pp.cu (256 queries per CTA, one softmax thread per row, P in its own TMEM columns):
     ragged key tiles, query counts that are not a multiple of 256, both K-step variants, all-MUFU and
     3/8-polynomial exponentials; and the same inputs through the older kernel agree with it."""
@@ -274,7 +278,8 @@ def test_attention_pp_two_query_tiles(B, Sq, Skv, heads, d, poly):
                 "e = t._attn_case(t.L(), %d, %d, %d, %d, %d, 0, v_ones=True); assert e < 2e-2, e; print(e)"
                 % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
                    B, Sq, Skv, heads, d))
-        env = dict(os.environ, DL_ATTN_PP_POLY="0")
+        # ... with two query tiles per CTA (the default is one tile per CTA, two CTAs per SM)
+        env = dict(os.environ, DL_ATTN_PP_POLY="0", DL_ATTN_PP_NQ="2")
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stdout + r.stderr
 

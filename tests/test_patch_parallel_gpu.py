@@ -9,7 +9,7 @@ import threading
 import pytest
 import torch
 
-from test_pipeline_gpu import NOISE_PRED_TOL, assert_unet_outputs, guided_tol, max_rel_err
+from test_pipeline_gpu import NOISE_PRED_TOL, assert_unet_outputs, guided_tol, max_rel_err, teacher_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +29,7 @@ def _setup(steps=2, size=128, B=1):
     return unet, vae, pipe, (pe, pooled, lat, noise)
 
 
-def _run_world(pipe, inputs, world, steps, gs):
+def _run_world(pipe, inputs, world, steps, gs, teacher=None):
     """-> per-rank (record, final latents) of a `world`-thread patch-parallel run."""
     from dreamlab_b200.patch_parallel import PatchParallelDenoiser, ThreadComm, Topology, _ThreadHub
     pe, pooled, lat, noise = inputs
@@ -44,7 +44,7 @@ def _run_world(pipe, inputs, world, steps, gs):
             den = PatchParallelDenoiser(pipe, comms[rank],
                                         lambda topo: ThreadComm(hubs[topo.cfg_index], topo.strip_index))
             rec = {}
-            final = den.denoise(pe, pooled, lat, noise, steps, gs, record=rec)
+            final = den.denoise(pe, pooled, lat, noise, steps, gs, record=rec, teacher_latents=teacher)
             torch.cuda.synchronize()
             out[rank] = (rec, final)
         except BaseException as e:        # noqa: BLE001
@@ -95,6 +95,33 @@ def test_patch_parallel_matches_unsharded_and_oracle(world, gs):
         assert max(eg) <= guided_tol(gs), (rank, eg)
         # every rank holds bit-identical latents (same kernels on identical gathered inputs)
         assert torch.equal(final, out[0][1])
+
+
+@pytest.mark.parametrize("world,gs", [(2, 7.5), (4, 7.5), (4, 1.0)])
+def test_patch_parallel_teacher_forced_every_step(world, gs):
+    """Row strips + CFG halves, every step on the ORACLE's step inputs: raw UNet outputs (both CFG halves)
+    against the oracle AND against the un-sharded engine (teacher-forced as well) at the 2e-2 bar — the
+    free-running comparison above measures how guidance amplifies bf16 trajectory drift, this one the
+    sharded forward itself."""
+    from oracle.pipeline import run_pipeline_sdxl
+    steps, size = 3, 128
+    unet, vae, pipe, inputs = _setup(steps, size)
+    pe, pooled, lat, noise = inputs
+    rec_o, rec_1 = {}, {}
+    run_pipeline_sdxl(unet, vae, pe, pooled, lat, noise, steps, gs, size, size, record=rec_o, output_type="latent")
+    teacher = teacher_inputs(lat, rec_o["latents"])
+    pipe.generate(pe, lat, noise, steps, gs, record=rec_1, pooled_embeds=pooled, teacher_latents=teacher)
+    torch.cuda.synchronize()
+    out = _run_world(pipe, inputs, world, steps, gs, teacher=teacher)
+    key = "noise_pred_raw" if gs > 1.0 else "noise_pred"
+    for rank, (rec, _) in enumerate(out):
+        e1 = [max_rel_err(a, b) for a, b in zip(rec[key], rec_1[key])]
+        eo = [max_rel_err(a.cpu(), b) for a, b in zip(rec[key], rec_o["noise_pred_raw"])]
+        if rank == 0:
+            print(f"world={world} gs={gs} teacher-forced: UNet output vs un-sharded {['%.2e' % e for e in e1]}  "
+                  f"vs oracle {['%.2e' % e for e in eo]}")
+        assert max(e1) <= NOISE_PRED_TOL, (rank, e1)
+        assert max(eo) <= NOISE_PRED_TOL, (rank, eo)
 
 
 def test_split_groupnorm_matches_fused():

@@ -15,19 +15,31 @@ PSNR_MIN_DB = 35.0
 
 
 def guided_tol(gs: float) -> float:
-    """Bar for the classifier-free-GUIDED prediction eps_u + gs (eps_t - eps_u): the 2e-2 bar
-    applies to what the UNet outputs (eps_u, eps_t); guidance is a linear map with gain
-    |1 - gs| + |gs| on those errors while random-init text conditioning barely moves the signal
-    (eps_t ~ eps_u), so the guided tensor is held to the propagated bound, capped at 10 %."""
+    """Bar for the classifier-free-GUIDED tensor eps_u + gs (eps_t - eps_u) ONLY (never for what the
+    UNet outputs).  Derivation: the guided tensor is the linear map (1 - gs) eps_u + gs eps_t of the
+    two UNet outputs, each of which is held to max|d| <= 2e-2 max|eps|; the worst case of the map is
+    (|1 - gs| + |gs|) * 2e-2 * max|eps| = 0.28 max|eps| at gs 7.5, while with random-init text
+    conditioning eps_t ~ eps_u, so max|guided| ~ max|eps|.  The bound is capped at 0.10 (measured:
+    5e-2 at gs 7.5): the guided tensor is reported for information, parity is asserted on the raw
+    UNet outputs — at every step on identical inputs by the teacher-forced tests below."""
     return min(NOISE_PRED_TOL * (abs(1.0 - gs) + abs(gs)), 0.10) if gs > 1.0 else NOISE_PRED_TOL
 
 
 def assert_unet_outputs(raw_errs, gs):
-    """Per-step UNet-output errors of a pipeline run: step 0 sees bit-identical inputs and is the
-    per-forward parity number (2e-2 bar); under CFG the later steps start from latents that
-    already carry the previous step's guided error, so they are held to the guided bar."""
+    """FREE-RUNNING pipeline runs: only step 0 sees inputs bit-identical to the oracle's, so only step 0
+    is a per-forward parity number (2e-2 bar).  Later free-running steps compare two trajectories
+    (the CUDA path starts them from its own bf16-rounded latents; guidance amplifies that drift), so
+    here they are only required to stay finite and bounded by the guided bar; the per-step bar is
+    asserted by `teacher_forced_errors` on the oracle's own step inputs."""
     assert raw_errs[0] <= NOISE_PRED_TOL, raw_errs
     assert max(raw_errs) <= guided_tol(gs), raw_errs
+
+
+def teacher_inputs(lat0, latents_after_each_step):
+    """[x_0, x_1, ..., x_{n-1}]: the latents the ORACLE fed to its UNet at each step (x_0 = initial latents
+    * init_noise_sigma (1.0), x_i = its scheduler output of step i-1) -> fp32 [n, B, 4, h, w]."""
+    xs = [torch.as_tensor(lat0).float()] + [torch.as_tensor(x).float() for x in latents_after_each_step[:-1]]
+    return torch.stack(xs)
 
 
 def max_rel_err(a, b):
@@ -183,3 +195,27 @@ def test_tiled_vae_decode_matches_oracle(h, w):
           f"tiled-vs-untiled-oracle {cross:.1f} dB")
     assert p >= PSNR_MIN_DB and pu >= PSNR_MIN_DB
     assert p > cross + 3.0          # it really follows the tiled arithmetic, not the untiled one
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher forcing: every step's UNet output on the ORACLE's step inputs (north_star: "per-step
+# noise_pred must match to max relative error <= 2e-2 in bf16")
+# ------------------------------------------------------------------------------------------------
+def test_sd15_lcm_512_teacher_forced_every_step_vs_committed_golden():
+    """Config C1: the CUDA UNet is fed the oracle's latents of every step (committed golden), so each of the
+    four noise_pred tensors is compared on identical inputs — no trajectory drift in the number."""
+    from oracle.pipeline import build_random_init, synthetic_inputs
+    from dreamlab_b200.engine import LCMPipelineB200
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sd15_lcm_512_4step.npz"))
+    unet, vae = build_random_init(seed=0)
+    pipe = LCMPipelineB200(unet.state_dict(), unet.cfg, vae.state_dict(), vae.cfg, "cuda:0")
+    pe, lat, noise = synthetic_inputs(1, 512, 512, 4)
+    rec = {}
+    pipe.generate(pe, lat, noise, 4, 1.0, record=rec, teacher_latents=teacher_inputs(lat, g["latents"]))
+    torch.cuda.synchronize()
+    errs = [max_rel_err(rec["noise_pred"][i].cpu(), torch.from_numpy(g["noise_pred"][i])) for i in range(4)]
+    lerr = [max_rel_err(rec["latents"][i].cpu(), torch.from_numpy(g["latents"][i])) for i in range(4)]
+    print(f"C1 teacher-forced noise_pred max-rel-err per step: {['%.2e' % e for e in errs]}  "
+          f"scheduler output {['%.2e' % e for e in lerr]}")
+    assert max(errs) <= NOISE_PRED_TOL, errs
+    assert max(lerr) <= NOISE_PRED_TOL, lerr

@@ -228,3 +228,60 @@ def test_cfg_workers_batch_by_guidance_scale(pool_factory):
     blocker.result(timeout=5)
     assert [f.result(timeout=5)[0] for f in futs] == [f"png-p{i}".encode() for i in range(6)]
     assert w.batches == [1, 3, 2, 1]
+
+
+def test_batch_window_collects_requests_below_saturation(pool_factory, monkeypatch):
+    """Four idle workers, requests trickling in 3 ms apart: with the collector role + batch window the first
+    idle thread gathers them into one batch instead of four threads taking one each."""
+    monkeypatch.setenv("B200_BATCH_WINDOW_MS", "60")
+    workers = {}
+
+    def factory(worker_id):
+        workers[worker_id] = FakeWorker(worker_id, delay=0.01)
+        return workers[worker_id]
+    pool = pool_factory(worker_factory=factory, num_workers=4, max_batch=8)
+    assert abs(pool.batch_window - 0.060) < 1e-9
+    futs = []
+    for i in range(6):
+        futs.append(pool.submit_job(GenerationJob(req=req(f"w{i}"))))
+        time.sleep(0.003)
+    assert [f.result(timeout=5)[0] for f in futs] == [f"png-w{i}".encode() for i in range(6)]
+    sizes = sorted(b for w in workers.values() for b in w.batches)
+    assert sizes == [6], sizes
+    # window 0: never waits (the reference's latency for a lone request)
+    monkeypatch.setenv("B200_BATCH_WINDOW_MS", "0")
+    pool0 = pool_factory(worker_factory=lambda worker_id: FakeWorker(worker_id), num_workers=1, max_batch=8)
+    t0 = time.perf_counter()
+    assert pool0.submit_job(GenerationJob(req=req("solo"))).result(timeout=5)[0] == b"png-solo"
+    assert time.perf_counter() - t0 < 0.5
+
+
+def test_failed_mode_switch_keeps_the_old_workers(pool_factory):
+    """A model that fails to load must not leave the pool without workers: the switch future
+    carries the error, the old mode keeps serving, MODEL / MODEL_ROOT are restored."""
+    import os
+    calls = []
+
+    def factory(worker_id):
+        calls.append(os.environ.get("MODEL"))
+        if os.environ.get("MODEL") == "alt":
+            raise RuntimeError("b200 worker needs a diffusers-layout model directory")
+        return FakeWorker(worker_id)
+    pool = pool_factory(worker_factory=factory, num_workers=2, max_batch=4)
+    old = list(pool._workers)
+    with pytest.raises(RuntimeError, match="diffusers-layout"):
+        pool.switch_mode("sd15-alt").result(timeout=5)
+    assert pool.get_current_mode() == "sd15-fast" and pool._workers == old
+    assert os.environ["MODEL"] == "sd15"
+    assert pool.submit_job(GenerationJob(req=req("still"))).result(timeout=5)[0] == b"png-still"
+
+
+def test_workers_are_created_concurrently(pool_factory):
+    """8 GPU workers each load their own copy of the weights: serial construction would make start-up and
+    every mode switch 8x longer."""
+    def factory(worker_id):
+        time.sleep(0.2)
+        return FakeWorker(worker_id)
+    t0 = time.perf_counter()
+    pool = pool_factory(worker_factory=factory, num_workers=4, max_batch=4)
+    assert time.perf_counter() - t0 < 0.6 and [w.worker_id for w in pool._workers] == [0, 1, 2, 3]
