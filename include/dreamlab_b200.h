@@ -116,6 +116,12 @@ int dl_groupnorm(const void* x0, int c0, const void* x1, int c1, int nimg, int h
  * [nimg, groups, 2] for dl_groupnorm_apply (nranks = 1); fp64 accumulation in fixed order.      */
 int dl_groupnorm_finalize(const float* partial, int nimg, int slots, int groups, long long count,
                           float* stats, void* stream);
+/* Per-CHANNEL records (dl_igemm_desc.gn_cpg == 1: [nimg, slots, n, 2], any channels-per-group, e.g. the
+ * UNet's 10 / 20 / 40) of one producer, or of the two producers of a channel concat [x0 | x1] (a group may
+ * straddle them) -> stats fp32 [nimg, groups, 2] (mean, M2) for dl_groupnorm_apply(nranks = 1).
+ * count = pixels per image x channels per group.                                                    */
+int dl_groupnorm_finalize_channels(const float* part0, int slots0, int c0, const float* part1, int slots1,
+                                   int c1, int nimg, int groups, long long count, float* stats, void* stream);
 size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups);
 int dl_groupnorm_stats(const void* x0, int c0, const void* x1, int c1, int nimg, int hw, int groups,
                        float* stats, void* workspace, void* stream);

@@ -36,9 +36,11 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow oursel
 
 constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
 constexpr int EPI_SLAB_BYTES = 2 * 2 * 256 * 4;    // (bias + row add) slab: [tile parity][image 0/1][256 cols]
-// GroupNorm partials of the OUTPUT tensor, emitted by the epilogue (VAE decoder: channels per
-// group 4 / 8 / 16 / 32 divide the 32-column chunk): [half][chunk-in-flight <= 4][quadrant][16] floats
-constexpr int EPI_GN_BYTES = 2 * 4 * 4 * 16 * 4;
+// GroupNorm partials of the OUTPUT tensor, emitted by the epilogue.  Channels per group 4 / 8 / 16 / 32
+// (VAE decoder) divide the 32-column chunk: per-group records, scratch [half][chunk-in-flight <= 4][quadrant][16]
+// floats.  Any other group width (UNet: 10 / 20 / 40 channels per group): per-CHANNEL records (gn_cpg == 1),
+// column sums over the staged bf16 tile, scratch [half][chunk <= 4][warp 0..3][16 column pairs][4] floats.
+constexpr int EPI_GN_BYTES = 2 * 4 * 4 * 16 * 4 * 4;
 // staging ring per epilogue half: 2 buffers for long-K tiles, 4 for short-K tiles whose TMA
 // stores queue behind a deep load pipeline (the epilogue must not wait on each store)
 
@@ -287,8 +289,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
     uint8_t* my_staging = staging + half * p.epi_nbuf * EPI_BUF_BYTES;
     float* slab = reinterpret_cast<float*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES);
     float* gn_scr = reinterpret_cast<float*>(staging + 2 * p.epi_nbuf * EPI_BUF_BYTES + EPI_SLAB_BYTES) +
-                    half * (4 * 4 * 16);                   // this half's [chunk][quadrant][16]
+                    half * (4 * 4 * 16 * 4);               // this half's scratch (see EPI_GN_BYTES)
     const bool gn_on = (p.gn_partial != nullptr);
+    const bool gn_chan = gn_on && p.gn_cpg == 1;           // per-channel records from the staged tile
     int acc = 0;
     uint32_t acc_phase = 0;
     const int tw_mask = (1 << p.tw_log2) - 1;
@@ -375,7 +378,7 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             for (int j = 0; j < 64; ++j)
               if (j < ncols) v[j] += __ldg(ra_row + col + j);
           }
-          if (gn_on) {
+          if (gn_on && !gn_chan) {
             float* dst = gn_scr + (g * 4 + quad) * 16;
             switch (p.gn_cpg) {
               case 4: gn_chunk_partials<4>(v, valid, dst); break;
@@ -407,6 +410,10 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
             }
             uint8_t* buf = my_staging + g * EPI_BUF_BYTES;
             const int sw = (r >> 1) & 3;             // 64B-swizzle phase of this 64-byte row
+            if (gn_chan && !valid) {                 // rows outside the tensor: clipped by the TMA store,
+#pragma unroll                                       // and they must not count in the column sums
+              for (int q4 = 0; q4 < 4; ++q4) ov[q4] = make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4)
               *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ sw) << 4)) = ov[q4];
@@ -450,7 +457,45 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         if (staged) {
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);
-          if (gn_on) {
+          if (gn_chan) {
+            // per-channel (sum, sum of squares) of the staged bf16 tile: thread = (column pair, 16-row group),
+            // then the two row groups of a warp (shuffle), then the four warps (scratch, fixed order)
+            const int th = threadIdx.x - 64 - 128 * half;
+            const int pr = th & 15, wi = th >> 5;
+            const int row0 = (th >> 4) * 16;
+            for (int gg = 0; gg < g; ++gg) {
+              const uint8_t* buf = my_staging + gg * EPI_BUF_BYTES;
+              float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int rr = row0 + i;
+                const uint32_t u = *reinterpret_cast<const uint32_t*>(
+                    buf + rr * 64 + (((pr >> 2) ^ ((rr >> 1) & 3)) << 4) + ((pr & 3) << 2));
+                const float2 f = unpack_bf16x2(u);
+                s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+                s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+              }
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16); q0 += __shfl_xor_sync(0xffffffffu, q0, 16);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+              if ((th & 16) == 0)
+                *reinterpret_cast<float4*>(gn_scr + ((gg * 4 + wi) * 16 + pr) * 4) = make_float4(s0, q0, s1, q1);
+            }
+            named_bar_sync(bar_id, 128);
+            for (int o = th; o < g * 64; o += 128) {
+              const int gg = o >> 6, pr2 = (o >> 2) & 15, k = o & 3;       // k: (sum, sumsq) of column 2 pr2, 2 pr2 + 1
+              const float* src = gn_scr + (gg * 4 * 16 + pr2) * 4 + k;
+              const float tot = (src[0] + src[64]) + (src[128] + src[192]);
+              const int col_c = col0 + c_group + gg * 2 * step + 2 * pr2 + (k >> 1);
+              int img = n0, slot = ty * p.tiles_x + tx;
+              if (p.gn_rows_per_img > 0) {                               // token rows: nimg=1, h=1, w=M
+                const long long row_first = (long long)tx << 7;
+                img = (int)(row_first / p.gn_rows_per_img);
+                slot = (int)((row_first % p.gn_rows_per_img) >> 7);
+              }
+              if (col_c < p.N && (p.gn_rows_per_img > 0 || img < p.NIMG))
+                p.gn_partial[(((long long)img * p.gn_slots + p.gn_slot0 + slot) * p.N + col_c) * 2 + (k & 1)] = tot;
+            }
+          } else if (gn_on) {
             // fold the four quadrants (32 rows each) in fixed order; one writer per (slot, group)
             const int ng2 = 2 * (32 / p.gn_cpg);
             const int th = threadIdx.x - 64 - 128 * half;
@@ -628,8 +673,9 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   if (d->gn_partial) {
     const int cpg = d->gn_cpg;
     DL_CHECK_ARG(d->mode == DL_EPI_BF16, "igemm: GroupNorm partials need DL_EPI_BF16");
-    DL_CHECK_ARG((cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && d->n % 32 == 0 && d->n % cpg == 0,
-                 "igemm: GroupNorm partials need 4/8/16/32 channels per group and n %% 32 == 0 (cpg=%d n=%d)", cpg, d->n);
+    DL_CHECK_ARG((cpg == 1 || cpg == 4 || cpg == 8 || cpg == 16 || cpg == 32) && d->n % 32 == 0 && d->n % cpg == 0,
+                 "igemm: GroupNorm partials need 1 (per-channel records) or 4/8/16/32 channels per group and n %% 32 == 0 "
+                 "(cpg=%d n=%d)", cpg, d->n);
     DL_CHECK_ARG(tn == 1 || d->gn_rows_per_img > 0, "igemm: GroupNorm partials need one image per M tile");
     DL_CHECK_ARG(d->gn_rows_per_img == 0 || (d->nimg == 1 && d->h == 1 && d->gn_rows_per_img % 128 == 0),
                  "igemm: gn_rows_per_img needs token rows (nimg=1,h=1) and a multiple of 128");

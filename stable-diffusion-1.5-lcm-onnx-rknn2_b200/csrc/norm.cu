@@ -689,6 +689,43 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
   }
 }
 
+// per-CHANNEL (sum, sumsq) records of one or two producers (channel concat [x0 | x1]) -> (mean, M2) per
+// (image, group).  A group may straddle the two sources (C0 = 1280, C1 = 640, 60 channels per group).
+// partial_k: fp32 [nimg][slots_k][C_k][2].  One CTA per (image, group), fp64 fixed-tree sum: deterministic.
+__global__ void __launch_bounds__(128) gn_finalize_chan_kernel(const float* __restrict__ part0, int slots0, int c0,
+                                                               const float* __restrict__ part1, int slots1, int c1,
+                                                               int groups, double count, float* __restrict__ stats) {
+  __shared__ double sh[2][128];
+  const int img = blockIdx.x / groups, g = blockIdx.x % groups;
+  const int cpg = (c0 + c1) / groups;
+  const int smax = slots0 > slots1 ? slots0 : slots1;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < smax * cpg; i += 128) {
+    const int slot = i / cpg, c = g * cpg + (i - slot * cpg);
+    float2 r = make_float2(0.f, 0.f);
+    if (c < c0) {
+      if (slot < slots0) r = __ldg(reinterpret_cast<const float2*>(part0 + (((long long)img * slots0 + slot) * c0 + c) * 2));
+    } else if (slot < slots1) {
+      r = __ldg(reinterpret_cast<const float2*>(part1 + (((long long)img * slots1 + slot) * c1 + (c - c0)) * 2));
+    }
+    s += (double)r.x;
+    q += (double)r.y;
+  }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = 64; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double mean = sh[0][0] / count;
+    const double m2 = sh[1][0] - sh[0][0] * mean;
+    stats[((long long)img * groups + g) * 2 + 0] = (float)mean;
+    stats[((long long)img * groups + g) * 2 + 1] = (float)(m2 > 0.0 ? m2 : 0.0);
+  }
+}
+
 static int gn_split_setup(GnSplitParams& p, const void* x0, int c0, const void* x1, int c1, int nimg,
                           int hw, int groups) {
   const int C = c0 + c1;
@@ -724,6 +761,19 @@ extern "C" int dl_groupnorm_finalize(const float* partial, int nimg, int slots, 
   gn_finalize_kernel<<<nimg * groups, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(partial, slots, groups,
                                                                                        (double)count, stats);
   return check_launch("groupnorm_finalize");
+}
+
+extern "C" int dl_groupnorm_finalize_channels(const float* part0, int slots0, int c0, const float* part1, int slots1,
+                                              int c1, int nimg, int groups, long long count, float* stats,
+                                              void* stream_) {
+  using namespace dl;
+  DL_CHECK_ARG(part0 && stats && nimg > 0 && slots0 > 0 && c0 > 0 && groups > 0 && count > 0,
+               "groupnorm_finalize_channels: bad args");
+  DL_CHECK_ARG(c1 == 0 || (part1 && slots1 > 0), "groupnorm_finalize_channels: c1 > 0 needs part1 / slots1");
+  DL_CHECK_ARG((c0 + c1) % groups == 0, "groupnorm_finalize_channels: C=%d not divisible by groups=%d", c0 + c1, groups);
+  gn_finalize_chan_kernel<<<nimg * groups, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      part0, slots0, c0, part1, c1 > 0 ? slots1 : 0, c1, groups, (double)count, stats);
+  return check_launch("groupnorm_finalize_channels");
 }
 
 extern "C" size_t dl_groupnorm_split_workspace_bytes(int nimg, int groups) {

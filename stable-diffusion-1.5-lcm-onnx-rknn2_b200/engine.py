@@ -80,11 +80,23 @@ class _Ctx:
 # building blocks
 # ------------------------------------------------------------------------------------------------
 def _gn_request(ctx, B, n_out, slots, phases=1):
-    """Partial-statistics buffer for an igemm whose output feeds a GroupNorm, or None."""
+    """(partial-statistics buffer, channels per record) for an igemm whose output feeds a GroupNorm, or
+    (None, 0).  Channels per group 4 / 8 / 16 / 32 (VAE decoder) line up with the epilogue's 32-column
+    chunks: per-group records [B, slots, groups, 2].  Anything else (UNet: 10 / 20 / 40): per-CHANNEL records
+    [B, slots, n_out, 2] (cpg 1), reduced per group by `groupnorm_finalize_channels`."""
     g = ctx.gn_fuse
-    if not g or n_out % g or n_out % 32 or (n_out // g) not in (4, 8, 16, 32) or slots <= 0:
-        return None
-    return ctx.empty(B, slots * phases, g, 2, dtype=torch.float32)
+    if not g or n_out % g or n_out % 32 or slots <= 0:
+        return None, 0
+    if (n_out // g) in (4, 8, 16, 32):
+        return ctx.empty(B, slots * phases, g, 2, dtype=torch.float32), n_out // g
+    return ctx.empty(B, slots * phases, n_out, 2, dtype=torch.float32), 1
+
+
+def _carry_gn(src, dst):
+    """Views are new tensor objects: hand the producer's GroupNorm records on."""
+    if hasattr(src, "_gn"):
+        dst._gn, dst._gn_cpg = src._gn, src._gn_cpg
+    return dst
 
 
 def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=lib.EPI_BF16,
@@ -98,14 +110,14 @@ def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=li
         H -= 2
     if out is None:
         out = ctx.empty(B, H, W, n_out, dtype=torch.float32 if mode == lib.EPI_F32 else None)
-    part = None
+    part, cpg = None, 0
     if feeds_norm and ctx.gn_fuse and mode == lib.EPI_BF16 and not halo:
-        part = _gn_request(ctx, B, n_out, lib.igemm_tiles_per_image(H, W))
+        part, cpg = _gn_request(ctx, B, n_out, lib.igemm_tiles_per_image(H, W))
     lib.igemm(x, w, out, nimg=B, h=H, w=W, taps=9, n=n_out, a1=x1, bias=b, rowadd=rowadd,
               residual=residual, mode=mode, ldo=ldo, in_rows=H + 2 if halo else 0,
-              in_row0=1 if halo else 0, gn_partial=part, gn_cpg=(n_out // ctx.gn_fuse) if part is not None else 0)
+              in_row0=1 if halo else 0, gn_partial=part, gn_cpg=cpg)
     if part is not None:
-        out._gn = part
+        out._gn, out._gn_cpg = part, cpg
     return out
 
 
@@ -118,16 +130,15 @@ def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, ou
     cols = out_cols if out_cols is not None else (n_out // 2 if mode == lib.EPI_GEGLU else n_out)
     if out is None:
         out = ctx.empty(*lead, cols, dtype=torch.float32 if mode == lib.EPI_F32 else None)
-    part = None
+    part, cpg = None, 0
     if norm_rows_per_img and norm_rows_per_img % 128 == 0 and mode == lib.EPI_BF16 and M % norm_rows_per_img == 0:
-        part = _gn_request(ctx, M // norm_rows_per_img, n_out, norm_rows_per_img // 128)
+        part, cpg = _gn_request(ctx, M // norm_rows_per_img, n_out, norm_rows_per_img // 128)
     lib.igemm(x, w, out, nimg=1, h=1, w=M, taps=1, n=n_out, a1=x1, bias=b, residual=residual,
               mode=mode, alpha=alpha, a0_stride=x.stride(-2), a1_stride=None if x1 is None else x1.stride(-2),
               ldo=cols, ldr=None if residual is None else residual.shape[-1], gn_partial=part,
-              gn_cpg=(n_out // ctx.gn_fuse) if part is not None else 0,
-              gn_rows_per_img=norm_rows_per_img if part is not None else 0)
+              gn_cpg=cpg, gn_rows_per_img=norm_rows_per_img if part is not None else 0)
     if part is not None:
-        out._gn = part
+        out._gn, out._gn_cpg = part, cpg
     return out
 
 
@@ -136,12 +147,22 @@ def groupnorm(ctx, x, gw, gb, *, eps, silu, x1=None, groups=32, halo=False):
     B, H, W, C0 = x.shape
     C = C0 + (x1.shape[-1] if x1 is not None else 0)
     part = getattr(x, "_gn", None)
-    if ctx.comm is None and part is not None and x1 is None and part.shape[2] == groups:
+    if ctx.comm is None and part is not None and x1 is None and x._gn_cpg > 1 and part.shape[2] == groups:
         # the producing conv left (sum, sumsq) per M tile: one tiny reduction, then ONE pass over x
         stats = ctx.empty(1, B, groups, 2, dtype=torch.float32)
         lib.groupnorm_finalize(part, stats, H * W * (C // groups))
         out = ctx.empty(B, H, W, C)
         lib.groupnorm_apply(x, out, gw, gb, stats, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu)
+        return out
+    part1 = getattr(x1, "_gn", None) if x1 is not None else None
+    if (ctx.comm is None and part is not None and x._gn_cpg == 1 and
+            (x1 is None or (part1 is not None and x1._gn_cpg == 1))):
+        # per-channel records of the producer(s) (the skip-concat partner included): finalize per group,
+        # then ONE pass over [x | x1] — no statistics pass, no grid barrier
+        stats = ctx.empty(1, B, groups, 2, dtype=torch.float32)
+        lib.groupnorm_finalize_channels(part, part1, stats, groups, H * W * (C // groups))
+        out = ctx.empty(B, H, W, C)
+        lib.groupnorm_apply(x, out, gw, gb, stats, nimg=B, hw=H * W, groups=groups, eps=eps, silu=silu, x1=x1)
         return out
     if ctx.comm is None:
         out = ctx.empty(B, H, W, C)
@@ -236,8 +257,8 @@ def transformer(ctx, x, p: Packed, kvs, *, groups=32):
     for q, kv in zip(p["blocks"], kvs):
         h = transformer_block(ctx, h, q, kv, B=B, S=S, C=C, heads=p["heads"], d=p["d"],
                               hstride=p["hstride"])
-    out = linear(ctx, h, p["proj_out_w"], p["proj_out_b"], C, residual=x.view(B * S, C))
-    return out.view(B, H, W, C)
+    out = linear(ctx, h, p["proj_out_w"], p["proj_out_b"], C, residual=x.view(B * S, C), norm_rows_per_img=S)
+    return _carry_gn(out, out.view(B, H, W, C))
 
 
 def downsample(ctx, x, p: Packed):
@@ -248,8 +269,8 @@ def downsample(ctx, x, p: Packed):
     else:
         xp = ctx.pad_rows(x)
         lib.im2col_s2_halo(xp.t, cols, nimg=B, in_rows=H + 2, in_row0=1, h=H, w=W)
-    out = linear(ctx, cols, p["w"], p["b"], C)
-    return out.view(B, H // 2, W // 2, C)
+    out = linear(ctx, cols, p["w"], p["b"], C, norm_rows_per_img=(H // 2) * (W // 2))
+    return _carry_gn(out, out.view(B, H // 2, W // 2, C))
 
 
 def upsample(ctx, x, p: Packed):
@@ -262,15 +283,14 @@ def upsample(ctx, x, p: Packed):
     if ctx.comm is not None:
         src, halo = ctx.pad_rows(x).t, dict(in_rows=H + 2, in_row0=1)
     T = lib.igemm_tiles_per_image(H, W) if ctx.gn_fuse else 0
-    part = _gn_request(ctx, B, C, T, phases=4)
+    part, cpg = _gn_request(ctx, B, C, T, phases=4)
     for ph in range(4):
         a, b = ph >> 1, ph & 1
         view = out[:, a:, b:, :]                            # base pointer of phase (a, b)
         lib.igemm(src, p["w"][ph], view, nimg=B, h=H, w=W, taps=4, n=C, bias=p["b"], tap_phase=ph,
-                  ldo=C, out_strides=strides, gn_partial=part, gn_cpg=(C // ctx.gn_fuse) if part is not None else 0,
-                  gn_slot0=ph * T, **halo)
+                  ldo=C, out_strides=strides, gn_partial=part, gn_cpg=cpg, gn_slot0=ph * T, **halo)
     if part is not None:
-        out._gn = part
+        out._gn, out._gn_cpg = part, cpg
     return out
 
 
@@ -294,6 +314,8 @@ class UNetB200:
         with pack_dtype(self.dt):
             self.P = pack_unet(state_dict, cfg, self.device)
         self.groups = getattr(cfg, "norm_num_groups", 32)
+        import os
+        self.fuse_gn_stats = os.environ.get("DL_UNET_GN_FUSE", "1") not in ("0", "false")
 
     @torch.no_grad()
     def encode_context(self, prompt_embeds: torch.Tensor) -> List[List[torch.Tensor]]:
@@ -366,8 +388,10 @@ class UNetB200:
         if comm is not None and self.dt != BF16:
             raise RuntimeError("patch parallel runs on the bf16 path only (the split GroupNorm kernels have no "
                                "fp32 variant); the fp32 precision mode is a one-GPU parity mode")
-        ctx = _Ctx(self.device, B, comm, dt=self.dt)
         g = self.groups
+        # GroupNorm statistics from the producers' epilogues (per-channel records): every GroupNorm of the
+        # UNet becomes finalize + ONE pass; DL_UNET_GN_FUSE=0 keeps the cooperative two-phase kernel (A/B)
+        ctx = _Ctx(self.device, B, comm, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt)
         ch = self.cfg.block_out_channels
         kv_it = iter(kvs)
         if comm is None:
@@ -388,7 +412,7 @@ class UNetB200:
                     lib.pack_latent(latents_nhwc[i, lo:hi], xp[r * b0 + i, lo - (r0 - 1):hi - (r0 - 1)], cin=Cin)
             xin = Padded(xp)
             H = hl
-        h = conv3x3(ctx, xin, P["conv_in_w"], P["conv_in_b"], ch[0])
+        h = conv3x3(ctx, xin, P["conv_in_w"], P["conv_in_b"], ch[0], feeds_norm=True)
         skips = [h]
         for blk in P["down"]:
             for j, r in enumerate(blk["resnets"]):
@@ -465,10 +489,7 @@ class VAEDecoderB200:
             lib.softmax_rows(scores, probs)
             lib.igemm(probs, vt, o[rows], nimg=1, h=1, w=S, taps=1, n=C, a0_stride=S, ldo=C)
         out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C), norm_rows_per_img=S)
-        res = out.view(B, H, W, C)
-        if hasattr(out, "_gn"):
-            res._gn = out._gn
-        return res
+        return _carry_gn(out, out.view(B, H, W, C))
 
     def _mid_attention_strips(self, ctx, x, hn2, a: Packed):
         """Row strips (VAE row): the queries of this rank's S tokens attend to the
@@ -653,7 +674,10 @@ class _StaticGraph:
             torch.cuda.synchronize(dev)
             self.graph = torch.cuda.CUDAGraph()
             n0 = lib.launch_count
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            # an explicit capture stream on THIS device: torch.cuda.graph's default capture stream is one
+            # class-wide stream created on whichever device captured first, so a second worker (another GPU,
+            # same process) would capture on the wrong device
+            with torch.cuda.graph(self.graph, stream=s, capture_error_mode="thread_local"):
                 self.img, self.final = pipe.run_static(*args, **kw)
             self.launches = lib.launch_count - n0        # native kernel launches per replay
 

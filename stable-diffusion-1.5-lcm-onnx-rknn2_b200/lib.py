@@ -25,7 +25,7 @@ EXPORTS = [
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
     "dl_cfg_combine", "dl_groupnorm_split_workspace_bytes", "dl_groupnorm_stats", "dl_groupnorm_apply",
     "dl_im2col_s2_halo", "dl_tile_blend", "dl_image_crop_u8", "dl_igemm_tiles_per_image",
-    "dl_groupnorm_finalize", "dl_embed_tokens", "dl_act_bf16",
+    "dl_groupnorm_finalize", "dl_groupnorm_finalize_channels", "dl_embed_tokens", "dl_act_bf16",
     "dl_peer_allgather", "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
     "dl_im2col_s2_f32", "dl_softmax_rows_f32", "dl_small_linear_f32",
     "dl_png_stored_size", "dl_png_stored_workspace_bytes", "dl_png_stored",
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
             lib.dl_igemm_tiles_per_image.argtypes = [C.c_int, C.c_int]
             lib.dl_groupnorm_finalize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
                                                   C.c_void_p, C.c_void_p]
+            lib.dl_groupnorm_finalize_channels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                                           C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p]
             lib.dl_groupnorm_split_workspace_bytes.restype = C.c_size_t
             lib.dl_groupnorm_split_workspace_bytes.argtypes = [C.c_int, C.c_int]
             lib.dl_groupnorm_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
@@ -334,6 +336,16 @@ def groupnorm_finalize(partial, stats, count):
     nimg, slots, groups, _ = partial.shape
     _check(load().dl_groupnorm_finalize(partial.data_ptr(), nimg, slots, groups, int(count), stats.data_ptr(),
                                         _stream()), "groupnorm_finalize")
+    _count()
+
+
+def groupnorm_finalize_channels(part0, part1, stats, groups, count):
+    """part_k fp32 [nimg, slots_k, C_k, 2] per-channel (sum, sumsq) of the producer(s) of [x0 | x1] ->
+    stats fp32 [nimg, groups, 2] (mean, M2)."""
+    nimg, s0, c0, _ = part0.shape
+    s1, c1 = (part1.shape[1], part1.shape[2]) if part1 is not None else (0, 0)
+    _check(load().dl_groupnorm_finalize_channels(part0.data_ptr(), s0, c0, _ptr(part1), s1, c1, nimg, groups,
+                                                 int(count), stats.data_ptr(), _stream()), "groupnorm_finalize_channels")
     _count()
 
 

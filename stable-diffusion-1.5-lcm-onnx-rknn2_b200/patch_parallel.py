@@ -363,7 +363,7 @@ class PatchParallelDenoiser:
                 torch.cuda.synchronize(dev)
                 graph = torch.cuda.CUDAGraph()
                 f0 = getattr(comm, "_fcalls", 0)
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                with torch.cuda.graph(graph, stream=s, capture_error_mode="thread_local"):
                     st["out"] = self._loop(*args())
                 if (getattr(comm, "_fcalls", 0) - f0) % 2:
                     raise RuntimeError("patch parallel: a captured loop must issue an even number of fused "

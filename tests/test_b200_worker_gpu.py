@@ -242,3 +242,56 @@ def test_gpu_png_mode_same_pixels_and_deterministic(worker, monkeypatch):
     monkeypatch.setenv("B200_PNG", "jpeg")
     with pytest.raises(RuntimeError, match="B200_PNG"):
         worker.run_job(job(seed=42))
+
+
+def test_two_real_workers_capture_and_serve_concurrently(tmp_path):
+    """WorkerPool with TWO real B200Workers in one process (on a one-GPU box both land on cuda:0): every
+    worker captures its CUDA graphs lazily on first use of a geometry, so mixed batch sizes arriving at
+    once make the two threads warm up / capture / replay concurrently (capture in "global" error
+    mode made the other thread's CUDA calls fail).  Every request must come back, and equal the same request
+    served alone."""
+    from dreamlab_b200 import synthetic as S
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from backends.worker_factory import create_cuda_worker
+    from backends.worker_pool import GenerationJob, WorkerPool
+    from unittest.mock import Mock
+    ucfg = UNetConfig.tiny()
+    ucfg.cross_attention_dim = 768
+    S.write_model_dir(str(tmp_path / "tiny-lcm"), ucfg, VAEConfig.tiny())
+    old = {k: os.environ.get(k) for k in ("MODEL_ROOT", "MODEL", "CUDA_DEVICE")}
+    os.environ["MODEL_ROOT"], os.environ["MODEL"] = str(tmp_path), "tiny-lcm"
+    os.environ.pop("CUDA_DEVICE", None)
+    try:
+        cfg = Mock()
+        cfg.config.model_root = str(tmp_path)
+        cfg.get_mode.return_value = Mock(model="tiny-lcm", model_path="x", loras=[])
+        cfg.get_default_mode.return_value = "tiny"
+        reg = Mock()
+        reg.get_used_vram.return_value = 0
+        pool = WorkerPool(queue_max=256, worker_factory=create_cuda_worker, mode_config=cfg, registry=reg,
+                          num_workers=2, max_batch=4)
+        assert len(pool._workers) == 2 and pool._workers[0] is not pool._workers[1]
+        reqs = []
+        for rnd in range(3):                                   # bursts of different geometry / batch size
+            for i, (size, steps) in enumerate([("64x64", 2)] * 3 + [("128x128", 2)] * 5 + [("64x128", 1)] * 2):
+                reqs.append(job(prompt=f"r{rnd}-{i}", size=size, steps=steps, seed=1000 * rnd + i).req)
+        futs = [pool.submit_job(GenerationJob(req=r)) for r in reqs]
+        res = [f.result(timeout=300) for f in futs]
+        assert all(png[:8] == b"\x89PNG\r\n\x1a\n" for png, _ in res)
+        assert [s for _, s in res] == [r.seed for r in reqs]
+        solo = pool._workers[0]
+        import numpy as np
+        from PIL import Image
+        for k in (0, 4, 9, 17, 29):
+            png, _ = solo.run_job(SimpleNamespace(req=reqs[k]))
+            a = np.asarray(Image.open(io.BytesIO(png))).astype(int)
+            b = np.asarray(Image.open(io.BytesIO(res[k][0]))).astype(int)
+            assert np.abs(a - b).max() <= 1, k                 # batch-invariance bar of test_batch_invariance
+        pool.shutdown()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v

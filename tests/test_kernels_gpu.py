@@ -409,6 +409,78 @@ def test_igemm_groupnorm_partials(B, H, W, C, N, res):
     assert (a.float() - b.float()).abs().max().item() <= 0.0625
 
 
+@pytest.mark.parametrize("B,H,W,C0,C1,res", [(2, 32, 32, 320, 0, True), (3, 16, 16, 1280, 640, False),
+                                              (2, 64, 64, 320, 320, True), (1, 48, 48, 640, 0, False),
+                                              (2, 24, 32, 640, 320, True)])
+def test_igemm_groupnorm_channel_records(B, H, W, C0, C1, res):
+    """Per-CHANNEL GroupNorm records (gn_cpg = 1: the UNet's 10 / 20 / 40 / 60 channels per group do not line up
+    with the epilogue's 32-column chunks): the records of one producer, or of the two producers of a
+    skip-concat [x0 | x1] whose groups straddle the two sources, -> dl_groupnorm_finalize_channels ->
+    (mean, M2) equal to statistics of the tensors themselves; the one-pass norm on them matches the two-phase
+    kernel."""
+    lib = L()
+    G = 32
+    outs, parts = [], []
+    for k, N in enumerate([C0, C1]):
+        if N == 0:
+            outs.append(None); parts.append(None)
+            continue
+        Cin = 64
+        x = bf(rand(B, H, W, Cin, seed=1 + k))
+        wt = bf(rand(N, 9 * Cin, seed=3 + k, scale=(9 * Cin) ** -0.5))
+        bias = rand(N, seed=4 + k)
+        r = bf(rand(B, H, W, N, seed=5 + k)) if res else None
+        out = torch.empty(B, H, W, N, device=DEV, dtype=torch.bfloat16)
+        slots = lib.igemm_tiles_per_image(H, W)
+        assert slots > 0
+        part = torch.full((B, slots, N, 2), float("nan"), device=DEV)
+        lib.igemm(x, wt, out, nimg=B, h=H, w=W, taps=9, n=N, bias=bias, residual=r, gn_partial=part, gn_cpg=1)
+        outs.append(out); parts.append(part)
+    C = C0 + C1
+    cpg = C // G
+    stats = torch.empty(B, G, 2, device=DEV)
+    lib.groupnorm_finalize_channels(parts[0], parts[1], stats, G, H * W * cpg)
+    torch.cuda.synchronize()
+    assert not any(torch.isnan(p_).any() for p_ in parts if p_ is not None)     # every (slot, channel) written
+    cat = torch.cat([o for o in outs if o is not None], -1).float()
+    o = cat.view(B, H * W, G, cpg).permute(0, 2, 1, 3).reshape(B, G, -1).double()
+    mean = o.mean(-1)
+    m2 = ((o - mean[..., None]) ** 2).sum(-1)
+    assert torch.allclose(stats[..., 0].double(), mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[..., 1].double(), m2, rtol=1e-4, atol=1e-3)
+    gw, gb = rand(C, seed=6), rand(C, seed=7)
+    a = torch.empty(B, H, W, C, device=DEV, dtype=torch.bfloat16)
+    lib.groupnorm_apply(outs[0], a, gw, gb, stats.unsqueeze(0), nimg=B, hw=H * W, groups=G, eps=1e-5, silu=True,
+                        x1=outs[1])
+    ws = torch.empty(lib.groupnorm_workspace_bytes(B, G), device=DEV, dtype=torch.uint8)
+    b = torch.empty_like(a)
+    lib.groupnorm(outs[0], b, gw, gb, ws, nimg=B, hw=H * W, groups=G, eps=1e-5, silu=True, x1=outs[1])
+    torch.cuda.synchronize()
+    assert (a.float() - b.float()).abs().max().item() <= 0.0625
+
+
+def test_linear_groupnorm_channel_records_token_rows():
+    """The same records from a token-row GEMM (Transformer2DModel.proj_out + residual): M = B*S rows, one slot
+    per 128 rows of an image."""
+    lib = L()
+    B, S, K, N, G = 3, 1024, 640, 640, 32
+    x = bf(rand(B * S, K, seed=1))
+    wt = bf(rand(N, K, seed=2, scale=K ** -0.5))
+    r = bf(rand(B * S, N, seed=3))
+    out = torch.empty(B * S, N, device=DEV, dtype=torch.bfloat16)
+    part = torch.full((B, S // 128, N, 2), float("nan"), device=DEV)
+    lib.igemm(x, wt, out, nimg=1, h=1, w=B * S, taps=1, n=N, bias=rand(N, seed=4), residual=r, ldr=N, ldo=N,
+              gn_partial=part, gn_cpg=1, gn_rows_per_img=S)
+    stats = torch.empty(B, G, 2, device=DEV)
+    lib.groupnorm_finalize_channels(part, None, stats, G, S * (N // G))
+    torch.cuda.synchronize()
+    assert not torch.isnan(part).any()
+    o = out.float().view(B, S, G, N // G).permute(0, 2, 1, 3).reshape(B, G, -1).double()
+    mean = o.mean(-1)
+    assert torch.allclose(stats[..., 0].double(), mean, atol=1e-5, rtol=1e-5)
+    assert torch.allclose(stats[..., 1].double(), ((o - mean[..., None]) ** 2).sum(-1), rtol=1e-4, atol=1e-3)
+
+
 def test_igemm_dual_subtile_residual_and_u8():
     """Narrow-N layers big enough for the two-sub-tile mode (two 128-pixel tiles share a weight
     tile): fused residual + GroupNorm partials, and the u8 image tail (N = 3), odd tile count."""
