@@ -105,8 +105,13 @@ class B200Worker(PipelineWorker):
         if not model_name:
             raise RuntimeError(f"MODEL is required for {self._env_what}")
         path = os.path.join(model_root, model_name)
-        if not (os.path.isdir(path) and os.path.exists(os.path.join(path, "model_index.json"))):
-            raise RuntimeError(f"b200 worker needs a diffusers-layout model directory, got: {path}")
+        # a diffusers-layout directory (`from_pretrained`, reference `backends/cuda_worker.py:70-77`) or a
+        # single-file checkpoint in the original layout (`from_single_file`, `:79-85`; every model of the
+        # reference's modes.yaml.example is one)
+        single = os.path.isfile(path) and path.lower().endswith(".safetensors")
+        if not single and not (os.path.isdir(path) and os.path.exists(os.path.join(path, "model_index.json"))):
+            raise RuntimeError(f"b200 worker needs a diffusers-layout model directory or a single-file "
+                               f".safetensors checkpoint, got: {path}")
         if not torch.cuda.is_available():
             raise RuntimeError("b200 worker needs a CUDA device (sm_100a); there is no CPU fallback")
 
@@ -122,10 +127,18 @@ class B200Worker(PipelineWorker):
         self.dtype = {"bf16": torch.bfloat16, "fp32": torch.float32}.get(dtype_str, torch.float16)
         torch.cuda.set_device(self.device)
 
-        with open(os.path.join(path, "model_index.json")) as f:
-            self._model_index = json.load(f)
-        ucfg_json, unet_sd = _load_component(os.path.join(path, "unet"))
-        vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
+        self._single = None
+        if single:
+            from dreamlab_b200.single_file import load_single_file
+            self._single = load_single_file(path)
+            self._model_index = self._single["model_index"]
+            ucfg_json, unet_sd = self._single["unet"]
+            vcfg_json, vae_sd = self._single["vae"]
+        else:
+            with open(os.path.join(path, "model_index.json")) as f:
+                self._model_index = json.load(f)
+            ucfg_json, unet_sd = _load_component(os.path.join(path, "unet"))
+            vcfg_json, vae_sd = _load_component(os.path.join(path, "vae"))
         # vae_tiling: the reference switches `pipe.vae.enable_tiling()` on unconditionally
         # (`backends/cuda_worker.py:91`, `:390`)
         # CUDA_DTYPE=fp32 selects the fp32 precision mode (CUDA-core kernels, parity bar 1e-4);
@@ -134,6 +147,7 @@ class B200Worker(PipelineWorker):
                                     vae_cfg_from_json(vcfg_json), self.device, vae_tiling=True,
                                     precision="fp32" if dtype_str == "fp32" else "bf16")
         self._text = self._make_text_encoder(path)
+        self._single = None                               # the converted state dicts are packed: drop the copies
         # the attributes the reference's worker tests look for on `pipe` (`tests/test_sdxl_worker.py:127-130`)
         towers = getattr(self._text, "models", None) or (getattr(self._text, "model", None),)
         self.pipe.text_encoder = towers[0] if towers else None
@@ -193,7 +207,7 @@ class B200Worker(PipelineWorker):
         return (style, level) if style and level > 0 else (None, 0)
 
     def _make_text_encoder(self, path):
-        return _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim)
+        return _TextEncoder(path, self.device, self.pipe.unet.cfg.cross_attention_dim, single=self._single)
 
     # one CUDA-graph replay per request batch (captured per (batch, size, steps) on first use; LRU
     # of LCMPipelineB200.max_graphs geometries): at small batches the eager path is bound by
@@ -212,11 +226,11 @@ class B200Worker(PipelineWorker):
         (zeros are an SDXL-only convention, `force_zeros_for_empty_prompt`)."""
         return self._text.encode([""] * n)
 
-    def _generate(self, prompts, lat, noise, steps, gs, height, width):
+    def _generate(self, prompts, lat, noise, steps, gs, height, width, decode=True):
         pe = self._text.encode(prompts)
         neg = self._negative(len(prompts)) if self.pipe.cfg_scale_for(gs) is not None else None
         return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, use_graph=self._use_graph,
-                                  negative_prompt_embeds=neg)
+                                  negative_prompt_embeds=neg, decode=decode)
 
     # ------------------------------------------------------------------ jobs
     def _parse(self, req):
@@ -250,7 +264,7 @@ class B200Worker(PipelineWorker):
 
     @torch.no_grad()
     def run_batch(self, jobs: Sequence, with_latents: bool = False, deferred: bool = False,
-                  raw: bool = False) -> List:
+                  raw: bool = False, latents_only: bool = False) -> List:
         """All jobs must share size / steps / style; guidance may differ per job.
         deferred=True returns one zero-argument callable per job that PNG-encodes its image when
         called: the pool runs them on encoder threads while this worker's thread already drives
@@ -274,10 +288,15 @@ class B200Worker(PipelineWorker):
             self._apply_style(*next(iter(styles)))
             try:
                 img, final = self._generate([str(j.req.prompt) for j in jobs], lat, noise, steps, gs,
-                                            height, width)
+                                            height, width, decode=not latents_only)
             finally:
                 self._apply_style(None, 0)          # reset: no state bleed into the next job
             from dreamlab_b200 import lib
+            if latents_only:
+                # denoised latents, fp32 NCHW like the reference's `output_type="latent"` pass
+                # (`backends/cuda_worker.py:273-283`): no VAE decode, no PNG
+                lat_out = final.permute(0, 3, 1, 2).contiguous().cpu().numpy()
+                return [(lat_out[i], parsed[i][2]) for i in range(len(jobs))]
             pooled = None
             if with_latents:
                 pooled = torch.empty(len(jobs), 4, 8, 8, device=self.device, dtype=torch.float16)
@@ -311,6 +330,13 @@ class B200Worker(PipelineWorker):
     def run_job_with_latents(self, job) -> Tuple[bytes, int, bytes]:
         return self.run_batch([job], with_latents=True)[0]
 
+    def run_job_latents(self, job):
+        """Extension for callers that score candidates in latent space (the Yume dream
+        loop `yume/dream_worker.py:203-306` renders a 64x64 1-step candidate only to hash / score it): the
+        denoise loop alone -> (fp32 latents [4, H/8, W/8], seed); the VAE decode and the PNG are skipped.
+        `run_batch(jobs, latents_only=True)` does the same for many candidates in one pass."""
+        return self.run_batch([job], latents_only=True)[0]
+
     def run_job_array(self, job):
         """Extension for callers that score pixels instead of shipping a file (the Yume dream
         loop renders 64x64 1-step candidates through `run_job` and immediately decodes the PNG
@@ -331,9 +357,9 @@ class B200SDXLWorker(B200Worker):
         if not self.pipe.is_sdxl:
             raise RuntimeError("B200SDXLWorker needs an SDXL-class UNet (addition_embed_type=text_time)")
         pooled = ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim
-        return _SDXLTextEncoder(path, self.device, ucfg.cross_attention_dim, pooled)
+        return _SDXLTextEncoder(path, self.device, ucfg.cross_attention_dim, pooled, single=self._single)
 
-    def _generate(self, prompts, lat, noise, steps, gs, height, width):
+    def _generate(self, prompts, lat, noise, steps, gs, height, width, decode=True):
         pe, pooled = self._text.encode(prompts)
         neg = negp = None
         # `force_zeros_for_empty_prompt` (model_index.json; True for SDXL-base): zeros for the unconditional
@@ -342,7 +368,7 @@ class B200SDXLWorker(B200Worker):
             neg, negp = self._text.encode([""] * len(prompts))
         return self.pipe.generate(pe, lat, noise, steps, gs, return_latents=True, pooled_embeds=pooled,
                                   use_graph=self._use_graph, negative_prompt_embeds=neg,
-                                  negative_pooled_embeds=negp)
+                                  negative_pooled_embeds=negp, decode=decode)
 
 
 _ENCODERS = None
@@ -408,6 +434,26 @@ def _load_clip(te_dir: str, device: str):
     raise RuntimeError(f"no safetensors weights under {te_dir}")
 
 
+def _clip_from(component, device: str):
+    """(config dict, transformers-named state dict) of a converted single-file text tower -> CLIPTextB200."""
+    from dreamlab_b200.clip import CLIPTextB200, clip_cfg_from_json
+    cfg, sd = component
+    return CLIPTextB200(sd, clip_cfg_from_json(cfg), device)
+
+
+def _side_tokenizer(checkpoint_path: str, name: str):
+    """A single-file checkpoint carries no tokenizer files (diffusers fetches them from the hub): look for
+    `<name>/vocab.json` next to the file, or under B200_TOKENIZER_ROOT.  None -> hashed stand-in tokens."""
+    for root in (os.path.dirname(checkpoint_path), os.environ.get("B200_TOKENIZER_ROOT", "")):
+        tk = os.path.join(root, name) if root else ""
+        if tk and os.path.exists(os.path.join(tk, "vocab.json")):
+            from transformers import CLIPTokenizer
+            return CLIPTokenizer.from_pretrained(tk)
+    print(f"[b200] no {name}/vocab.json next to {checkpoint_path} (or under B200_TOKENIZER_ROOT): prompts are "
+          f"tokenised by a hashing stand-in")
+    return None
+
+
 def _hash_tokens(prompts: List[str], eos: int = 49407, bos: int = 49406) -> torch.Tensor:
     """Deterministic stand-in token ids when the model dir ships no tokenizer files (offline
     fixtures): good for synthetic load, meaningless for real prompts."""
@@ -434,10 +480,15 @@ class _TextEncoder:
     (tokenisation is the stock `transformers` CLIPTokenizer, pure host code).  Without a text
     tower (offline fixtures): seeded N(0,1) embeddings keyed by the prompt."""
 
-    def __init__(self, model_dir: str, device: str, dim: int):
+    def __init__(self, model_dir: str, device: str, dim: int, single=None):
         self.device, self.dim = device, dim
         self.model = None
         self.tokenizer = None
+        if single is not None:
+            if single.get("text_encoder"):
+                self.model = _clip_from(single["text_encoder"], device)
+            self.tokenizer = _side_tokenizer(model_dir, "tokenizer")
+            return
         te = os.path.join(model_dir, "text_encoder")
         if os.path.exists(os.path.join(te, "config.json")):
             self.model = _load_clip(te, device)
@@ -465,10 +516,15 @@ class _SDXLTextEncoder:
     (`dreamlab_b200.clip`).  Without them in the model dir (offline fixtures): seeded N(0,1)
     embeddings keyed by the prompt."""
 
-    def __init__(self, model_dir: str, device: str, dim: int, pooled_dim: int):
+    def __init__(self, model_dir: str, device: str, dim: int, pooled_dim: int, single=None):
         self.device, self.dim, self.pooled_dim = device, dim, pooled_dim
         self.models = None
         self.tokenizers = (None, None)
+        if single is not None:
+            if single.get("text_encoder") and single.get("text_encoder_2"):
+                self.models = (_clip_from(single["text_encoder"], device), _clip_from(single["text_encoder_2"], device))
+            self.tokenizers = (_side_tokenizer(model_dir, "tokenizer"), _side_tokenizer(model_dir, "tokenizer_2"))
+            return
         te1, te2 = os.path.join(model_dir, "text_encoder"), os.path.join(model_dir, "text_encoder_2")
         if os.path.exists(os.path.join(te1, "config.json")) and os.path.exists(os.path.join(te2, "config.json")):
             self.models = (_load_clip(te1, device), _load_clip(te2, device))

@@ -63,37 +63,25 @@ class Job:
     submitted_at: float
 
 
+@dataclass(frozen=True)
 class ModelPaths:
-    """Sub-paths of a component-per-directory model root (the layout the reference's RKNN worker
-    loads from).  Not used by the b200 path, which reads a diffusers directory; kept so that
-    `from backends.base import ModelPaths` keeps working when this package replaces the
-    reference's."""
+    """Sub-paths of a component-per-directory model root (the layout the reference's RKNN worker loads from,
+    reference `backends/base.py`).  Not used by the b200 path, which reads a diffusers directory; kept so that
+    `from backends.base import ModelPaths` keeps working when this package replaces the reference's."""
+    root: str
 
-    _LAYOUT = {
-        "scheduler_config": ("scheduler", "scheduler_config.json"),
-        "text_encoder": ("text_encoder",),
-        "unet": ("unet",),
-        "vae_decoder": ("vae_decoder",),
-    }
-    __slots__ = ("root",)
+    @property
+    def scheduler_config(self) -> str:
+        return os.path.join(self.root, "scheduler", "scheduler_config.json")
 
-    def __init__(self, root: str):
-        object.__setattr__(self, "root", root)
+    @property
+    def text_encoder(self) -> str:
+        return os.path.join(self.root, "text_encoder")
 
-    def __setattr__(self, name, value):             # frozen, like the reference's dataclass
-        raise AttributeError(f"ModelPaths is immutable (tried to set {name!r})")
+    @property
+    def unet(self) -> str:
+        return os.path.join(self.root, "unet")
 
-    def __getattr__(self, name: str) -> str:
-        parts = self._LAYOUT.get(name)
-        if parts is None:
-            raise AttributeError(name)
-        return os.path.join(self.root, *parts)
-
-    def __eq__(self, other):
-        return isinstance(other, ModelPaths) and other.root == self.root
-
-    def __hash__(self):
-        return hash(("ModelPaths", self.root))
-
-    def __repr__(self):
-        return f"ModelPaths(root={self.root!r})"
+    @property
+    def vae_decoder(self) -> str:
+        return os.path.join(self.root, "vae_decoder")

@@ -5,8 +5,8 @@ Keeps the reference's entry points (`backends/worker_factory.py:17-100`):
 `MODEL_ROOT`/`MODEL` (768/1024 -> sd15, 1280/2048 -> sdxl, anything else raises) and
 `create_cuda_worker(worker_id)`.  The only behavioural change: SD1.5-class models now get the
 B200-native `B200Worker` instead of `DiffusersCudaWorker`, SDXL-class models `B200SDXLWorker`
-instead of `DiffusersSDXLCudaWorker`.  Set `B200_WORKER=0` to get the
-reference's diffusers worker back when running inside the reference tree.
+instead of `DiffusersSDXLCudaWorker`.  There is no switch back to a diffusers worker and no other
+backend: this package is the B200 path only.
 """
 from __future__ import annotations
 
@@ -26,8 +26,15 @@ _SD15_DIMS = (768, 1024)       # SD1.x / SD2.x
 
 
 def _builtin_detect(model_path: str):
-    """Minimal stand-in for the reference's `utils.model_detector.detect_model` when this
-    package runs outside the reference tree: diffusers-layout dirs only (unet/config.json)."""
+    """Stand-in for the reference's `utils.model_detector.detect_model`: diffusers-layout dirs
+    (unet/config.json) and single-file .safetensors checkpoints (header only).  For single files it is used even
+    inside the reference tree: the reference's SafetensorsDetector reads `attn2.to_k.weight.shape[0]`, the
+    OUTPUT dim of that Linear (320 / 640 / 1280), not cross_attention_dim."""
+    if os.path.isfile(model_path):
+        from dreamlab_b200.single_file import sniff
+        info = sniff(model_path)
+        return SimpleNamespace(cross_attention_dim=info["cross_attention_dim"], confidence=1.0,
+                               variant=SimpleNamespace(value=info["variant"]))
     cfg = os.path.join(model_path, "unet", "config.json")
     if not os.path.exists(cfg):
         raise RuntimeError(f"cannot inspect {model_path}: no unet/config.json "
@@ -39,6 +46,8 @@ def _builtin_detect(model_path: str):
 
 
 def _detect_model(model_path: str):
+    if os.path.isfile(model_path) and model_path.lower().endswith(".safetensors"):
+        return _builtin_detect(model_path)
     try:
         from utils.model_detector import detect_model      # reference tree
     except ImportError:
@@ -72,24 +81,14 @@ def detect_worker_type() -> str:
         raise RuntimeError(f"Model detection failed: {e}")
 
 
-def _use_b200() -> bool:
-    return os.environ.get("B200_WORKER", "1").lower() not in ("0", "false", "no", "off")
-
-
 def create_cuda_worker(worker_id: int) -> "PipelineWorker":
     worker_type = detect_worker_type()
     if worker_type == "sdxl":
-        if _use_b200():
-            from backends.b200_worker import B200SDXLWorker
-            worker = B200SDXLWorker(worker_id=worker_id)
-            logger.info("[WorkerFactory] Created B200SDXLWorker (worker %d)", worker_id)
-            return worker
-        from backends.cuda_worker import DiffusersSDXLCudaWorker
-        return DiffusersSDXLCudaWorker(worker_id=worker_id)
-    if _use_b200():
-        from backends.b200_worker import B200Worker
-        worker = B200Worker(worker_id=worker_id)
-        logger.info("[WorkerFactory] Created B200Worker (worker %d)", worker_id)
+        from backends.b200_worker import B200SDXLWorker
+        worker = B200SDXLWorker(worker_id=worker_id)
+        logger.info("[WorkerFactory] Created B200SDXLWorker (worker %d)", worker_id)
         return worker
-    from backends.cuda_worker import DiffusersCudaWorker
-    return DiffusersCudaWorker(worker_id=worker_id)
+    from backends.b200_worker import B200Worker
+    worker = B200Worker(worker_id=worker_id)
+    logger.info("[WorkerFactory] Created B200Worker (worker %d)", worker_id)
+    return worker

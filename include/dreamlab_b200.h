@@ -88,9 +88,26 @@ typedef struct dl_igemm_desc {
   int in_rows;               /* halo-padded row strips (SDXL patch parallel): a0/a1 */
   int in_row0;               /*   hold in_rows >= h rows per image and output row y reads input rows
                                 y + dy + in_row0; 0/0 = dense (in_rows = h)                    */
+  /* LayerNorm folded into the GEMMs around it (BasicTransformerBlock norm1/2/3): no LayerNorm pass.
+     PRODUCER (the GEMM whose bf16 output is the LayerNorm input, DL_EPI_BF16): row_stats_out fp32
+     [rows, row_stats_slots, 2] receives per-row (sum, sum of squares) partials of the output, one slot per
+     (N tile, epilogue half): row_stats_slots = 2 * ceil(n / dl_igemm_plan_bn(desc)).
+     CONSUMER (the GEMM that reads LayerNorm(x): weights pre-multiplied by gamma, W'[j,k] = W[j,k] gamma[k]):
+     ln_stats = the producer's records of its A rows (ln_slots slots), ln_colsum[j] = sum_k W'[j,k],
+     bias[j] = b[j] + sum_k beta[k] W[j,k]; the epilogue computes
+       out = rstd_r * (acc - mean_r * ln_colsum[j]) + bias[j],  mean / rstd over the ln_c = K channels.   */
+  float* row_stats_out;
+  int row_stats_slots;
+  const float* ln_stats;
+  int ln_slots;
+  const float* ln_colsum;
+  int ln_c;
+  float ln_eps;
 } dl_igemm_desc;
 
 int dl_igemm(const dl_igemm_desc* desc, void* stream);
+/* the N tile dl_igemm will use for this descriptor (host only, no launch)                         */
+int dl_igemm_plan_bn(const dl_igemm_desc* desc);
 /* M tiles per image of an h x w conv (slots a gn_partial buffer needs); 0 if tiles span images   */
 int dl_igemm_tiles_per_image(int h, int w);
 /* fills a caller-owned 256x256 bf16 device buffer (128 KB) with the identity matrix            */
@@ -251,6 +268,13 @@ int dl_im2col_s2_f32(const float* x, int nimg, int h, int w, int c, float* cols,
 int dl_softmax_rows_f32(const float* scores, long long rows, int cols, float* out, void* stream);
 int dl_small_linear_f32(const float* x, int m, int k, const float* w, const float* bias,
                         const float* add, int n, int silu_in, int silu_out, float* out, void* stream);
+
+/* ---- narrow-output conv3x3 = 1x1 GEMM + tap sum (AutoencoderKL decoder conv_out, 128 -> 3) -----------------
+ * y: fp32 [nimg,h,w,ldy] with y[q, t*nout + oc] = w[oc, tap t, :] . in[q, :] (one dl_igemm with taps = 1 and the
+ * weight rows regrouped tap-major); out[p, oc] = bias[oc] + sum_t y[p + offset(t), t*nout + oc], zero padding.
+ * out_u8 != 0: u8 NHWC with the VaeImageProcessor tail (as DL_EPI_U8_IMAGE); else fp32 NHWC.  nout <= 4.   */
+int dl_conv_tapsum(const float* y, int nimg, int h, int w, int ldy, int nout, const float* bias, void* out,
+                   int out_u8, void* stream);
 
 /* ---- PNG files assembled on the device (B200_PNG=gpu) -------------------------------------------
  * Replaces the host-side `img.save(buf, format="PNG")` that ends every job (reference

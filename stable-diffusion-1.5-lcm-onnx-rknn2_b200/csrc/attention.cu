@@ -24,6 +24,11 @@ namespace dl {
 int attn_simt_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v,
                      long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                      int skv, int heads, int d, float scale, int causal, cudaStream_t stream);
+// attention_x.cu: short key lists (cross-attention, S_kv <= 128): one CTA per (image, head) and query range;
+// -1 = shape not covered
+int attn_x_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
+                  int dh_stride, void* out, long long ldo, int batch, int sq, int skv, int heads, int d,
+                  float scale, int v_ones, cudaStream_t stream);
 // attention_pp.cu: two query tiles per CTA, one softmax thread per row (long keys, head dim <= 56);
 // -1 = shape not covered
 int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv,
@@ -532,6 +537,9 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   static int force_mode = -1;
   if (force_mode < 0) { const char* e = getenv("DL_ATTN_MODE"); force_mode = e ? atoi(e) : 0; }
   if (force_mode == 0 && g_attn_trace == nullptr) {
+    const int rx = attn_x_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d, scale, v_ones,
+                                 stream);
+    if (rx >= 0) return rx;
     const int rc = attn_pp_launch(q, ldq, k, ldk, v, ldv, dh_stride, out, ldo, batch, sq, skv, heads, d, scale,
                                   v_ones, stream);
     if (rc >= 0) return rc;

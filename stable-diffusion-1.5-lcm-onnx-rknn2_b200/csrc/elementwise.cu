@@ -370,6 +370,49 @@ __global__ void latent_pool8_kernel(const float* __restrict__ lat, int nimg, int
   out[i] = __float2half_rn(s / (float)((y1 - y0) * (x1 - x0)));
 }
 
+// ---- narrow-output conv3x3 as a 1x1 GEMM + tap sum (VAE conv_out, 128 -> 3 channels) -----------------------
+// A 3x3 conv with 3 output channels wastes the tensor core (N = 16 tile at 2 % of peak) and re-reads its 1 GB
+// input nine times through the TMA pipeline.  Instead ONE 1x1 GEMM computes, per INPUT pixel q, the 27 partial
+// products Y[q, t, oc] = w[oc, tap t, :] . in[q, :] (input read once), and this kernel gathers
+//   out[p, oc] = bias[oc] + sum_t Y[p + offset(t), t, oc]          (zero padding: out-of-image taps skipped)
+// and applies the VaeImageProcessor tail (reference `backends/rknnlcm.py:220-235`) when the output is u8.
+template <bool U8>
+__global__ void conv_tapsum_kernel(const float* __restrict__ yp, int nimg, int h, int w, int ldy, int nout,
+                                   const float* __restrict__ bias, void* __restrict__ out) {
+  const long long total = (long long)nimg * h * w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    float acc[4];
+#pragma unroll
+    for (int oc = 0; oc < 4; ++oc) acc[oc] = oc < nout ? __ldg(bias + oc) : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
+      const float* q = yp + (i + (long long)(t / 3 - 1) * w + (t % 3 - 1)) * ldy + t * nout;
+#pragma unroll
+      for (int oc = 0; oc < 4; ++oc)
+        if (oc < nout) acc[oc] += __ldg(q + oc);
+    }
+    if (U8) {
+      uint8_t* o = reinterpret_cast<uint8_t*>(out) + i * nout;
+#pragma unroll
+      for (int oc = 0; oc < 4; ++oc)
+        if (oc < nout) {
+          const float xb = __bfloat162float(__float2bfloat16(acc[oc]));   // the decoder's output dtype
+          o[oc] = (uint8_t)__float2int_rn(fminf(fmaxf(xb * 0.5f + 0.5f, 0.0f), 1.0f) * 255.0f);
+        }
+    } else {
+      float* o = reinterpret_cast<float*>(out) + i * nout;
+#pragma unroll
+      for (int oc = 0; oc < 4; ++oc)
+        if (oc < nout) o[oc] = acc[oc];
+    }
+  }
+}
+
 static inline unsigned grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = (long long)num_sms() * 16;
@@ -566,6 +609,18 @@ extern "C" int dl_image_crop_u8(const float* src, int nimg, int hs, int ws, int 
   image_crop_u8_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
       src, nimg, hs, ws, c, crop_h, crop_w, reinterpret_cast<uint8_t*>(dst_u8), dst_row_stride, dst_img_stride);
   return check_launch("image_crop_u8");
+}
+
+extern "C" int dl_conv_tapsum(const float* y, int nimg, int h, int w, int ldy, int nout, const float* bias,
+                              void* out, int out_u8, void* stream_) {
+  DL_CHECK_ARG(y && bias && out && nimg > 0 && h > 0 && w > 0, "conv_tapsum: bad args");
+  DL_CHECK_ARG(nout >= 1 && nout <= 4 && ldy >= 9 * nout, "conv_tapsum: nout in [1,4], ldy >= 9*nout (got %d, %d)", nout, ldy);
+  const long long total = (long long)nimg * h * w;
+  if (out_u8)
+    conv_tapsum_kernel<true><<<grid_for(total, 256), 256, 0, STREAM>>>(y, nimg, h, w, ldy, nout, bias, out);
+  else
+    conv_tapsum_kernel<false><<<grid_for(total, 256), 256, 0, STREAM>>>(y, nimg, h, w, ldy, nout, bias, out);
+  return check_launch("conv_tapsum");
 }
 
 extern "C" int dl_cfg_combine(const float* eps_uncond, const float* eps_text, float guidance_scale,

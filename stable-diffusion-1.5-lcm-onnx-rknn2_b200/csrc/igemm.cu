@@ -35,7 +35,8 @@ constexpr int IGEMM_THREADS = 320;            // TMA warp, MMA warp, 8 epilogue 
 constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // dynamic smem we allow ourselves
 
 constexpr int EPI_BUF_BYTES = BM * 32 * 2;        // one staged 128 x 32 bf16 output chunk (8 KB)
-constexpr int EPI_SLAB_BYTES = 2 * 2 * 256 * 4;    // (bias + row add) slab: [tile parity][image 0/1][256 cols]
+// (bias + row add) slab: [tile parity][image 0/1][256 cols], then the folded-LayerNorm column sums [tile parity][256]
+constexpr int EPI_SLAB_BYTES = 2 * 2 * 256 * 4 + 2 * 256 * 4;
 // GroupNorm partials of the OUTPUT tensor, emitted by the epilogue.  Channels per group 4 / 8 / 16 / 32
 // (VAE decoder) divide the 32-column chunk: per-group records, scratch [half][chunk-in-flight <= 4][quadrant][16]
 // floats.  Any other group width (UNet: 10 / 20 / 40 channels per group): per-CHANNEL records (gn_cpg == 1),
@@ -77,6 +78,13 @@ struct IgemmParams {
   // slot per M tile of the image; every (slot, group) is written by exactly one CTA (fixed order)
   float* gn_partial;
   int gn_cpg, gn_groups, gn_slots, gn_slot0, gn_rows_per_img;
+  // LayerNorm fold (see dl_igemm_desc): producer side / consumer side
+  float* row_stats_out;
+  int row_stats_slots;
+  const float* ln_stats;
+  int ln_slots;
+  const float* ln_colsum;
+  float ln_inv_c, ln_eps;
 };
 
 // Per-thread (= per output pixel) partial sums of one 32-column chunk, CPG channels per group,
@@ -333,6 +341,23 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         }
         sl[idx] = vs;
       }
+      float* cs_slab = slab + 1024 + ((tile_iter * MS + sub) & 1) * 256;
+      if (p.ln_stats != nullptr && et < 256) {
+        const int col = col0 + et;
+        cs_slab[et] = (et < p.BN && col < p.N) ? __ldg(p.ln_colsum + col) : 0.f;
+      }
+      // folded LayerNorm: this row's (mean, rstd) from the producer's partial records, fixed order
+      float ln_rstd = 1.f, ln_nmr = 0.f;
+      if (p.ln_stats != nullptr && valid) {
+        const float2* rs = reinterpret_cast<const float2*>(p.ln_stats) + row * p.ln_slots;
+        float sm = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_slots; ++i) { const float2 t = __ldg(rs + i); sm += t.x; sq += t.y; }
+        const float mean = sm * p.ln_inv_c;
+        const float var = fmaxf(sq * p.ln_inv_c - mean * mean, 0.f);
+        ln_rstd = rsqrtf(var + p.ln_eps);
+        ln_nmr = -mean * ln_rstd;
+      }
+      float rs_sum = 0.f, rs_sq = 0.f;                 // producer side: row sums of this tile's bf16 output
       named_bar_sync(3, 256);
       const float* sl_row = sl + (slab_rowadd ? min(r >> img_shift, 1) : 0) * 256;
       const float* ra_row = (p.rowadd && !slab_rowadd && n < p.NIMG)
@@ -367,11 +392,25 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
           }
           const int col = col0 + c;
           const int ncols = min(min(step, p.BN - c), p.N - col);
+          if (p.ln_stats != nullptr) {
+            // out = rstd * (acc - mean * colsum) + bias'  (LayerNorm of the A rows folded into this GEMM)
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
-            if (j4 * 4 >= step) break;
-            const float4 bv = *reinterpret_cast<const float4*>(sl_row + c + j4 * 4);   // zeros past N
-            v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+            for (int j4 = 0; j4 < 16; ++j4) {
+              if (j4 * 4 >= step) break;
+              const float4 bv = *reinterpret_cast<const float4*>(sl_row + c + j4 * 4);
+              const float4 cv = *reinterpret_cast<const float4*>(cs_slab + c + j4 * 4);
+              v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], ln_rstd, fmaf(ln_nmr, cv.x, bv.x));
+              v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], ln_rstd, fmaf(ln_nmr, cv.y, bv.y));
+              v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], ln_rstd, fmaf(ln_nmr, cv.z, bv.z));
+              v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], ln_rstd, fmaf(ln_nmr, cv.w, bv.w));
+            }
+          } else {
+#pragma unroll
+            for (int j4 = 0; j4 < 16; ++j4) {
+              if (j4 * 4 >= step) break;
+              const float4 bv = *reinterpret_cast<const float4*>(sl_row + c + j4 * 4);   // zeros past N
+              v[j4 * 4 + 0] += bv.x; v[j4 * 4 + 1] += bv.y; v[j4 * 4 + 2] += bv.z; v[j4 * 4 + 3] += bv.w;
+            }
           }
           if (ra_row != nullptr) {       // rare: more than two images per tile (tiny spatial dims)
 #pragma unroll
@@ -407,6 +446,19 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
                                     pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]),
                                     pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
                                     pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+            }
+            if (p.row_stats_out != nullptr) {        // row sums of the bf16 values the consumer will read
+              const int nv = min(32, p.N - col);     // columns of this chunk inside the tensor
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint32_t w4[4] = {ov[q4].x, ov[q4].y, ov[q4].z, ov[q4].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = unpack_bf16x2(w4[j]);
+                  if (q4 * 8 + 2 * j < nv) { rs_sum += f.x; rs_sq = fmaf(f.x, f.x, rs_sq); }
+                  if (q4 * 8 + 2 * j + 1 < nv) { rs_sum += f.y; rs_sq = fmaf(f.y, f.y, rs_sq); }
+                }
+              }
             }
             uint8_t* buf = my_staging + g * EPI_BUF_BYTES;
             const int sw = (r >> 1) & 3;             // 64B-swizzle phase of this 64-byte row
@@ -534,6 +586,9 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
+      if (p.row_stats_out != nullptr && valid)       // one record per (row, N tile, half): no atomics
+        reinterpret_cast<float2*>(p.row_stats_out)[row * p.row_stats_slots + n_blk * 2 + half] =
+            make_float2(rs_sum, rs_sq);
      }   // sub
       if (p.acc_bufs == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1; }
       else acc_phase ^= 1;
@@ -670,6 +725,21 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   p.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual); p.ldr = d->ldr;
   p.mode = d->mode;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+  if (d->row_stats_out) {
+    DL_CHECK_ARG(d->mode == DL_EPI_BF16, "igemm: row statistics need DL_EPI_BF16");
+    DL_CHECK_ARG(d->row_stats_slots == 2 * p.n_tiles, "igemm: row_stats_slots=%d must be 2 * N tiles = %d (dl_igemm_plan_bn)",
+                 d->row_stats_slots, 2 * p.n_tiles);
+    p.row_stats_out = d->row_stats_out; p.row_stats_slots = d->row_stats_slots;
+  }
+  if (d->ln_stats) {
+    DL_CHECK_ARG(d->ln_colsum && d->ln_slots > 0 && d->ln_slots <= 256 && d->ln_c > 0 && d->bias,
+                 "igemm: folded LayerNorm needs ln_colsum, bias, ln_slots in [1,256], ln_c (ln_slots=%d)", d->ln_slots);
+    DL_CHECK_ARG(d->mode == DL_EPI_BF16 || d->mode == DL_EPI_GEGLU, "igemm: folded LayerNorm needs a bf16 output mode");
+    DL_CHECK_ARG(d->taps == 1 && d->c1 == 0 && !d->rowadd && (d->alpha == 0.0f || d->alpha == 1.0f),
+                 "igemm: folded LayerNorm is for single-source linear layers");
+    p.ln_stats = d->ln_stats; p.ln_slots = d->ln_slots; p.ln_colsum = d->ln_colsum;
+    p.ln_inv_c = 1.0f / (float)d->ln_c; p.ln_eps = d->ln_eps;
+  }
   if (d->gn_partial) {
     const int cpg = d->gn_cpg;
     DL_CHECK_ARG(d->mode == DL_EPI_BF16, "igemm: GroupNorm partials need DL_EPI_BF16");
@@ -784,6 +854,16 @@ extern "C" int dl_igemm_tiles_per_image(int h, int w) {
   const int th = dl::pick_extent(h, 128 / tw);
   if (tw * th != 128) return 0;
   return ((w + tw - 1) / tw) * ((h + th - 1) / th);
+}
+
+extern "C" int dl_igemm_plan_bn(const dl_igemm_desc* d) {
+  if (!d || d->n <= 0 || d->nimg <= 0 || d->h <= 0 || d->w <= 0) return 0;
+  if (d->bn > 0) return d->bn;
+  const int tw = dl::pick_extent(d->w, 128);
+  const int th = dl::pick_extent(d->h, 128 / tw);
+  const int tn = 128 / (tw * th);
+  const long long m_tiles = (long long)((d->w + tw - 1) / tw) * ((d->h + th - 1) / th) * ((d->nimg + tn - 1) / tn);
+  return dl::pick_bn(d->n, m_tiles, dl::num_sms(), d->mode == DL_EPI_GEGLU ? 64 : 32);
 }
 
 extern "C" int dl_igemm(const dl_igemm_desc* d, void* stream) {

@@ -42,10 +42,12 @@ class _Ctx:
     """Per-forward scratch: device, batch, the GroupNorm workspace and (patch-parallel runs)
     the strip communicator.  comm=None is the single-GPU path."""
 
-    def __init__(self, device, batch, comm=None, gn_fuse=0, dt=BF16):
+    def __init__(self, device, batch, comm=None, gn_fuse=0, dt=BF16, ln_fold=False):
         self.device = device
         self.batch = batch
         self.comm = comm
+        # LayerNorm folded into the neighbouring GEMMs (transformer_block); bf16 one-GPU path only
+        self.ln_fold = bool(ln_fold) and comm is None and dt == BF16
         self.dt = dt          # activation dtype: bf16 (tcgen05 path) or fp32 (precision mode, CUDA cores)
         if dt != BF16:
             gn_fuse = 0
@@ -122,9 +124,12 @@ def conv3x3(ctx, x, w, b, n_out, *, x1=None, rowadd=None, residual=None, mode=li
 
 
 def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, out_cols=None,
-           alpha=1.0, out=None, norm_rows_per_img=0):
+           alpha=1.0, out=None, norm_rows_per_img=0, row_stats=False, ln=None):
     """x: [..., K] bf16 rows (any leading shape); returns [..., n_out] (or n_out/2 for GEGLU).
-    norm_rows_per_img > 0: the output (token rows of images of that many pixels) feeds a GroupNorm."""
+    norm_rows_per_img > 0: the output (token rows of images of that many pixels) feeds a GroupNorm.
+    row_stats: the output feeds a LayerNorm that is folded into its consumer — the epilogue leaves per-row
+    (sum, sumsq) records in `out._rs`.  ln=(records, colsum, eps): this GEMM consumes LayerNorm(x) (w is the
+    gamma-scaled weight, b the folded bias)."""
     lead = x.shape[:-1]
     M = x.numel() // x.shape[-1]
     cols = out_cols if out_cols is not None else (n_out // 2 if mode == lib.EPI_GEGLU else n_out)
@@ -133,12 +138,15 @@ def linear(ctx, x, w, b, n_out, *, x1=None, residual=None, mode=lib.EPI_BF16, ou
     part, cpg = None, 0
     if norm_rows_per_img and norm_rows_per_img % 128 == 0 and mode == lib.EPI_BF16 and M % norm_rows_per_img == 0:
         part, cpg = _gn_request(ctx, M // norm_rows_per_img, n_out, norm_rows_per_img // 128)
-    lib.igemm(x, w, out, nimg=1, h=1, w=M, taps=1, n=n_out, a1=x1, bias=b, residual=residual,
-              mode=mode, alpha=alpha, a0_stride=x.stride(-2), a1_stride=None if x1 is None else x1.stride(-2),
-              ldo=cols, ldr=None if residual is None else residual.shape[-1], gn_partial=part,
-              gn_cpg=cpg, gn_rows_per_img=norm_rows_per_img if part is not None else 0)
+    rs = lib.igemm(x, w, out, nimg=1, h=1, w=M, taps=1, n=n_out, a1=x1, bias=b, residual=residual,
+                   mode=mode, alpha=alpha, a0_stride=x.stride(-2), a1_stride=None if x1 is None else x1.stride(-2),
+                   ldo=cols, ldr=None if residual is None else residual.shape[-1], gn_partial=part,
+                   gn_cpg=cpg, gn_rows_per_img=norm_rows_per_img if part is not None else 0,
+                   row_stats=row_stats, ln=ln)
     if part is not None:
         out._gn, out._gn_cpg = part, cpg
+    if rs is not None:
+        out._rs = rs
     return out
 
 
@@ -201,19 +209,30 @@ def resnet(ctx, x, p: Packed, *, temb=None, x1=None, eps=1e-5, groups=32):
     return conv3x3(ctx, h, p["conv2_w"], p["conv2_b"], cout, residual=sc, feeds_norm=True)
 
 
-def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
-    """One BasicTransformerBlock on token rows h [B*S, C]; kv = hoisted cross-attn K/V."""
+def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride, last=True):
+    """One BasicTransformerBlock on token rows h [B*S, C]; kv = hoisted cross-attn K/V.
+    With `ctx.ln_fold` (one GPU, bf16, no style LoRA on the weights) the three LayerNorms are never
+    materialised: every GEMM that produces a LayerNorm input leaves per-row (sum, sumsq) records in its
+    epilogue (`h._rs`) and the consuming projection applies mean / rstd / gamma / beta in its own epilogue
+    (weights pre-multiplied by gamma at load, `weights.fold_layernorm`).  last=False: the block's output
+    feeds the next block's LayerNorm, so the final GEMM emits records too."""
     hs = heads * hstride
     scale = 1.0 / math.sqrt(d)
+    fold = ctx.ln_fold and ctx.comm is None and q["qkv_wf"] is not None and hasattr(h, "_rs")
     # --- self attention
-    n1 = ctx.empty(B * S, C)
-    lib.layernorm(h, n1, q["ln1_w"], q["ln1_b"])
     a = ctx.empty(B * S, C)
     if ctx.comm is None:
-        qkv = linear(ctx, n1, q["qkv_w"], q["qkv_b"], 3 * hs)
+        if fold:
+            qkv = linear(ctx, h, q["qkv_wf"], q["qkv_bf"], 3 * hs, ln=(h._rs, q["qkv_cs"], 1e-5))
+        else:
+            n1 = ctx.empty(B * S, C)
+            lib.layernorm(h, n1, q["ln1_w"], q["ln1_b"])
+            qkv = linear(ctx, n1, q["qkv_w"], q["qkv_b"], 3 * hs)
         lib.attention(qkv, qkv[:, hs:], qkv[:, 2 * hs:], a, batch=B, sq=S, skv=S, heads=heads, d=d,
                       dh_stride=hstride, ldq=3 * hs, ldk=3 * hs, ldv=3 * hs, ldo=C, scale=scale, v_ones=True)
     else:
+        n1 = ctx.empty(B * S, C)
+        lib.layernorm(h, n1, q["ln1_w"], q["ln1_b"])
         # row strips: queries stay local, keys/values of every strip are all-gathered
         # (SURVEY.md §8e exchange X2); key order = rank order = image row order
         qs = linear(ctx, n1, q["qkv_w"][:hs], None, hs)
@@ -231,21 +250,27 @@ def transformer_block(ctx, h, q: Packed, kv, *, B, S, C, heads, d, hstride):
         kvf = kvf.view(B * skv_all, 2 * hs)
         lib.attention(qs, kvf, kvf[:, hs:], a, batch=B, sq=S, skv=skv_all, heads=heads, d=d,
                       dh_stride=hstride, ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale, v_ones=True)
-    h = linear(ctx, a, q["o1_w"], q["o1_b"], C, residual=h)
+    h = linear(ctx, a, q["o1_w"], q["o1_b"], C, residual=h, row_stats=fold)
     # --- cross attention (K/V precomputed once per request)
-    n2 = ctx.empty(B * S, C)
-    lib.layernorm(h, n2, q["ln2_w"], q["ln2_b"])
-    qq = linear(ctx, n2, q["q2_w"], None, hs)
+    if fold:
+        qq = linear(ctx, h, q["q2_wf"], q["q2_bf"], hs, ln=(h._rs, q["q2_cs"], 1e-5))
+    else:
+        n2 = ctx.empty(B * S, C)
+        lib.layernorm(h, n2, q["ln2_w"], q["ln2_b"])
+        qq = linear(ctx, n2, q["q2_w"], None, hs)
     skv = kv.shape[0] // B
     a2 = ctx.empty(B * S, C)
     lib.attention(qq, kv, kv[:, hs:], a2, batch=B, sq=S, skv=skv, heads=heads, d=d, dh_stride=hstride,
                   ldq=hs, ldk=2 * hs, ldv=2 * hs, ldo=C, scale=scale, v_ones=True)
-    h = linear(ctx, a2, q["o2_w"], q["o2_b"], C, residual=h)
+    h = linear(ctx, a2, q["o2_w"], q["o2_b"], C, residual=h, row_stats=fold)
     # --- GEGLU feed-forward
-    n3 = ctx.empty(B * S, C)
-    lib.layernorm(h, n3, q["ln3_w"], q["ln3_b"])
-    g = linear(ctx, n3, q["ff1_w"], q["ff1_b"], 8 * C, mode=lib.EPI_GEGLU)
-    return linear(ctx, g, q["ff2_w"], q["ff2_b"], C, residual=h)
+    if fold:
+        g = linear(ctx, h, q["ff1_wf"], q["ff1_bf"], 8 * C, mode=lib.EPI_GEGLU, ln=(h._rs, q["ff1_cs"], 1e-5))
+    else:
+        n3 = ctx.empty(B * S, C)
+        lib.layernorm(h, n3, q["ln3_w"], q["ln3_b"])
+        g = linear(ctx, n3, q["ff1_w"], q["ff1_b"], 8 * C, mode=lib.EPI_GEGLU)
+    return linear(ctx, g, q["ff2_w"], q["ff2_b"], C, residual=h, row_stats=fold and not last)
 
 
 def transformer(ctx, x, p: Packed, kvs, *, groups=32):
@@ -253,10 +278,12 @@ def transformer(ctx, x, p: Packed, kvs, *, groups=32):
     B, H, W, C = x.shape
     S = H * W
     hn = groupnorm(ctx, x, p["norm_w"], p["norm_b"], eps=1e-6, silu=False, groups=groups)
-    h = linear(ctx, hn.view(B * S, C), p["proj_in_w"], p["proj_in_b"], C)
-    for q, kv in zip(p["blocks"], kvs):
+    h = linear(ctx, hn.view(B * S, C), p["proj_in_w"], p["proj_in_b"], C,
+               row_stats=ctx.ln_fold and ctx.comm is None and ctx.dt == BF16)
+    nb = len(p["blocks"])
+    for i, (q, kv) in enumerate(zip(p["blocks"], kvs)):
         h = transformer_block(ctx, h, q, kv, B=B, S=S, C=C, heads=p["heads"], d=p["d"],
-                              hstride=p["hstride"])
+                              hstride=p["hstride"], last=i == nb - 1)
     out = linear(ctx, h, p["proj_out_w"], p["proj_out_b"], C, residual=x.view(B * S, C), norm_rows_per_img=S)
     return _carry_gn(out, out.view(B, H, W, C))
 
@@ -316,6 +343,9 @@ class UNetB200:
         self.groups = getattr(cfg, "norm_num_groups", 32)
         import os
         self.fuse_gn_stats = os.environ.get("DL_UNET_GN_FUSE", "1") not in ("0", "false")
+        # DL_UNET_LN_FOLD=0 keeps the standalone LayerNorm kernel (A/B).  Style LoRAs update the packed
+        # projection weights in place (lora.py): `StyleManager` switches the fold off for such a UNet
+        self.fold_ln = os.environ.get("DL_UNET_LN_FOLD", "1") not in ("0", "false")
 
     @torch.no_grad()
     def encode_context(self, prompt_embeds: torch.Tensor) -> List[List[torch.Tensor]]:
@@ -391,7 +421,7 @@ class UNetB200:
         g = self.groups
         # GroupNorm statistics from the producers' epilogues (per-channel records): every GroupNorm of the
         # UNet becomes finalize + ONE pass; DL_UNET_GN_FUSE=0 keeps the cooperative two-phase kernel (A/B)
-        ctx = _Ctx(self.device, B, comm, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt)
+        ctx = _Ctx(self.device, B, comm, gn_fuse=g if self.fuse_gn_stats else 0, dt=self.dt, ln_fold=self.fold_ln)
         ch = self.cfg.block_out_channels
         kv_it = iter(kvs)
         if comm is None:
@@ -456,6 +486,13 @@ class VAEDecoderB200:
         self.groups = cfg.norm_num_groups
         import os
         self.fuse_gn_stats = os.environ.get("DL_VAE_GN_FUSE", "1") not in ("0", "false")
+        self.conv_out_tapsum = (os.environ.get("DL_VAE_CONV_OUT_TAPSUM", "1") not in ("0", "false")
+                                and self.dt == BF16 and self.P["conv_out_w"].shape[0] == 3)
+        if self.conv_out_tapsum:
+            # conv_out weights regrouped tap-major for the 1x1-GEMM + tap-sum form: row t*3 + oc = w[oc, tap t, :]
+            cl = self.P["conv_out_w"].shape[1] // 9
+            w27 = self.P["conv_out_w"].view(3, 9, cl).permute(1, 0, 2).reshape(27, cl)
+            self.P["conv_out_w27"] = torch.cat([w27, w27.new_zeros(5, cl)], 0).contiguous()
 
     def _mid_attention(self, ctx, x, a: Packed):
         """heads=1, d=C (512): QK^T and PV through the tcgen05 GEMM, fp32 scores, per image."""
@@ -619,7 +656,17 @@ class VAEDecoderB200:
                 h = upsample(ctx, h, blk["up"])
         hn = groupnorm(ctx, h, P["norm_out_w"], P["norm_out_b"], eps=1e-6, silu=True, groups=g,
                        halo=comm is not None)
-        Bo, Ho, Wo, _ = h.shape
+        Bo, Ho, Wo, Cl = h.shape
+        if comm is None and self.dt == BF16 and self.conv_out_tapsum:
+            # conv_out (C -> 3) as ONE 1x1 GEMM over the input (27 tap-major partial products per pixel, input
+            # read once) + a tap-sum kernel with the image tail, instead of a 3x3 implicit GEMM with a 16-wide
+            # N tile that re-reads the 1 GB input nine times at 2 % of the tensor peak
+            y = ctx.empty(Bo, Ho, Wo, 32, dtype=torch.float32)
+            lib.igemm(hn, P["conv_out_w27"], y, nimg=Bo, h=Ho, w=Wo, taps=1, n=32, mode=lib.EPI_F32, ldo=32)
+            img = (torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.float32) if f32_out else
+                   (out_u8 if out_u8 is not None else torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.uint8)))
+            lib.conv_tapsum(y, P["conv_out_b"], img)
+            return img
         if f32_out:
             img = torch.empty(Bo, Ho, Wo, 3, device=self.device, dtype=torch.float32)
             conv3x3(ctx, hn, P["conv_out_w"], P["conv_out_b"], 3, mode=lib.EPI_F32, out=img, ldo=3)
@@ -646,7 +693,7 @@ CAPTURE_LOCK = _threading.Lock()
 class _StaticGraph:
     """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps[, gs])."""
 
-    def __init__(self, pipe: "LCMPipelineB200", B, h, w, steps, cfg_scale=None):
+    def __init__(self, pipe: "LCMPipelineB200", B, h, w, steps, cfg_scale=None, decode=True):
         dev = pipe.device
         ucfg = pipe.unet.cfg
         D = ucfg.cross_attention_dim
@@ -663,7 +710,7 @@ class _StaticGraph:
         self.noise = torch.zeros(max(steps - 1, 1), B, 4, h, w, device=dev, dtype=torch.float32)
         self.steps = steps
         args = (self.pe, self.w_emb, self.lat, self.noise, steps)
-        kw = dict(add=self.add, cfg_scale=cfg_scale)
+        kw = dict(add=self.add, cfg_scale=cfg_scale, decode=decode)
         with CAPTURE_LOCK:
             # warm-up on a side stream (lazy per-device init: smem attributes, module load)
             s = torch.cuda.Stream(device=dev)
@@ -726,7 +773,7 @@ class LCMPipelineB200:
 
     @torch.no_grad()
     def run_static(self, pe_bf16, w_emb, lat_nchw, noise_nchw, steps: int, record: dict = None,
-                   add=None, cfg_scale: Optional[float] = None, teacher=None):
+                   add=None, cfg_scale: Optional[float] = None, teacher=None, decode: bool = True):
         """Everything on device, no host sync, graph-capturable.  Returns (u8 images, latents).
         pe_bf16 / add carry 2B rows ([uncond, cond]) when cfg_scale is set."""
         B = lat_nchw.shape[0]
@@ -736,18 +783,20 @@ class LCMPipelineB200:
         aug = self.unet.addition_embedding(*add) if add is not None else None
         tembs = self.unet.time_embeddings(sched.timesteps, Bu, w_emb, aug)
         lat = self.denoise(lat_nchw, noise_nchw, sched, kvs, tembs, record, cfg_scale=cfg_scale, teacher=teacher)
+        if not decode:                   # latent-only callers (candidate scoring): no VAE pass at all
+            return None, lat
         return self.vae.decode(lat, tiling=self.vae_tiling), lat
 
     max_graphs = 12       # captured geometries kept per pipeline (each owns its activation pool)
 
-    def graph_for(self, B, h, w, steps, cfg_scale=None) -> _StaticGraph:
-        key = (B, h, w, steps, cfg_scale)
+    def graph_for(self, B, h, w, steps, cfg_scale=None, decode=True) -> _StaticGraph:
+        key = (B, h, w, steps, cfg_scale, decode)
         g = self._graphs.pop(key, None)
         if g is None:
             while len(self._graphs) >= self.max_graphs:          # least recently used goes first
                 self._graphs.pop(next(iter(self._graphs)))
             with torch.cuda.device(self.device):
-                g = _StaticGraph(self, B, h, w, steps, cfg_scale)
+                g = _StaticGraph(self, B, h, w, steps, cfg_scale, decode)
         self._graphs[key] = g                                     # dict order = recency
         return g
 
@@ -820,7 +869,8 @@ class LCMPipelineB200:
     def generate(self, prompt_embeds, latents_nchw, step_noise_nchw, num_inference_steps: int,
                  guidance_scale=1.0, record: dict = None, return_latents: bool = False,
                  use_graph: bool = False, pooled_embeds=None, time_ids=None,
-                 negative_prompt_embeds=None, negative_pooled_embeds=None, teacher_latents=None):
+                 negative_prompt_embeds=None, negative_pooled_embeds=None, teacher_latents=None,
+                 decode: bool = True):
         """Public entry: host or device tensors in -> u8 images [B,H,W,3] on device (and the
         final latents NHWC fp32 if asked).  With use_graph the whole pass is one CUDA-graph
         replay; the returned tensors are the graph's static outputs (consume before next call)."""
@@ -832,7 +882,7 @@ class LCMPipelineB200:
                                          negative_pooled_embeds, cfg_scale, 8 * h, 8 * w)
         with torch.cuda.device(self.device):
             if use_graph and record is None and teacher_latents is None:
-                g = self.graph_for(B, h, w, steps, cfg_scale)
+                g = self.graph_for(B, h, w, steps, cfg_scale, decode)
                 g.pe.copy_(pe_all, non_blocking=True)
                 if w_emb is not None:
                     g.w_emb.copy_(w_emb, non_blocking=True)
@@ -853,5 +903,5 @@ class LCMPipelineB200:
                 nz = (step_noise_nchw.to(self.device, torch.float32).contiguous()
                       if steps > 1 else None)
                 img, lat = self.run_static(pe, we, lat0, nz, steps, record, add=add, cfg_scale=cfg_scale,
-                                           teacher=teacher_latents)
+                                           teacher=teacher_latents, decode=decode)
         return (img, lat) if return_latents else img

@@ -18,7 +18,7 @@ EPI_BF16, EPI_GEGLU, EPI_F32, EPI_U8_IMAGE = 0, 1, 2, 3
 ATTN_TC, ATTN_SIMT, ATTN_SIMT_CAUSAL = 0, 1, 2
 
 EXPORTS = [
-    "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_fill_identity",
+    "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_igemm_plan_bn", "dl_fill_identity",
     "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention",
     "dl_debug_attention_trace",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
@@ -28,7 +28,7 @@ EXPORTS = [
     "dl_groupnorm_finalize", "dl_groupnorm_finalize_channels", "dl_embed_tokens", "dl_act_bf16",
     "dl_peer_allgather", "dl_igemm_f32", "dl_groupnorm_f32", "dl_layernorm_f32", "dl_attention_f32", "dl_pack_latent_f32",
     "dl_im2col_s2_f32", "dl_softmax_rows_f32", "dl_small_linear_f32",
-    "dl_png_stored_size", "dl_png_stored_workspace_bytes", "dl_png_stored",
+    "dl_png_stored_size", "dl_png_stored_workspace_bytes", "dl_png_stored", "dl_conv_tapsum",
 ]
 
 
@@ -47,6 +47,9 @@ class IgemmDesc(C.Structure):
         ("gn_rows_per_img", C.c_int),
         ("peer_out", C.c_void_p * 7), ("n_peer_out", C.c_int),
         ("in_rows", C.c_int), ("in_row0", C.c_int),
+        ("row_stats_out", C.c_void_p), ("row_stats_slots", C.c_int),
+        ("ln_stats", C.c_void_p), ("ln_slots", C.c_int), ("ln_colsum", C.c_void_p), ("ln_c", C.c_int),
+        ("ln_eps", C.c_float),
     ]
 
 
@@ -77,6 +80,7 @@ def load() -> C.CDLL:
             lib.dl_groupnorm_workspace_bytes.restype = C.c_size_t
             lib.dl_groupnorm_workspace_bytes.argtypes = [C.c_int, C.c_int]
             lib.dl_igemm.argtypes = [C.POINTER(IgemmDesc), C.c_void_p]
+            lib.dl_igemm_plan_bn.argtypes = [C.POINTER(IgemmDesc)]
             lib.dl_fill_identity.argtypes = [C.c_void_p, C.c_void_p]
             lib.dl_groupnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                          C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_int,
@@ -146,6 +150,8 @@ def load() -> C.CDLL:
                                            C.c_void_p]
             lib.dl_latent_pool8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_void_p, C.c_void_p]
+            lib.dl_conv_tapsum.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p]
             lib.dl_png_stored_size.restype = C.c_longlong
             lib.dl_png_stored_size.argtypes = [C.c_int, C.c_int]
             lib.dl_png_stored_workspace_bytes.restype = C.c_longlong
@@ -259,9 +265,12 @@ def require_cuda():
 def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None, c1=0,
           a1_stride=None, bias=None, rowadd=None, residual=None, ldr=None, ldo=None,
           mode=EPI_BF16, alpha=1.0, bn=0, tap_phase=-1, out_strides=None, in_rows=0, in_row0=0,
-          gn_partial=None, gn_cpg=0, gn_slot0=0, gn_rows_per_img=0, peer_outs=None):
+          gn_partial=None, gn_cpg=0, gn_slot0=0, gn_rows_per_img=0, peer_outs=None, row_stats=False, ln=None):
     """out[pixel, :n] = epilogue(conv/linear(a0 ‖ a1, wgt)).  a0/a1: NHWC bf16 (or [M, C] rows with
-    nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)]."""
+    nimg=1,h=1,w=M); wgt: bf16 [n, taps*(c0+c1)].
+    row_stats=True: returns fp32 [rows, slots, 2] per-row (sum, sumsq) partials of the bf16 output (the
+    LayerNorm statistics of the next GEMM).  ln=(stats, colsum, eps): LayerNorm of the A rows folded into this
+    GEMM (wgt pre-multiplied by gamma, bias = the folded bias)."""
     d = IgemmDesc()
     c0 = a0.shape[-1] if c0 is None else c0
     d.a0, d.c0 = a0.data_ptr(), c0
@@ -294,6 +303,16 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
         d.gn_partial, d.gn_cpg, d.gn_slots = gn_partial.data_ptr(), gn_cpg, gn_partial.shape[1]
         d.gn_slot0, d.gn_rows_per_img = gn_slot0, gn_rows_per_img
     m_rows = nimg * h * w
+    stats_out = None
+    if row_stats:
+        bn_plan = load().dl_igemm_plan_bn(C.byref(d))
+        slots = 2 * ((n + bn_plan - 1) // bn_plan)
+        stats_out = torch.empty(m_rows, slots, 2, device=out.device, dtype=torch.float32)
+        d.row_stats_out, d.row_stats_slots = stats_out.data_ptr(), slots
+    if ln is not None:
+        st, colsum, eps = ln
+        d.ln_stats, d.ln_slots, d.ln_colsum = st.data_ptr(), st.shape[1], colsum.data_ptr()
+        d.ln_c, d.ln_eps = c0, eps
     ncols = n // 2 if mode == EPI_GEGLU else n
     # algorithmic bytes: every operand once (activations, weights, residual) + the output
     nbytes = (2.0 * m_rows * (d.c0 + d.c1) + 2.0 * n * taps * (d.c0 + d.c1) + out.element_size() * m_rows * ncols
@@ -306,6 +325,7 @@ def igemm(a0, wgt, out, *, nimg, h, w, taps, n, c0=None, a0_stride=None, a1=None
         else:
             _check(load().dl_igemm(C.byref(d), _stream()), "igemm")
     _count()
+    return stats_out
 
 
 def groupnorm_workspace_bytes(nimg, groups=32):
@@ -580,3 +600,13 @@ def png_stored(img_u8, out=None):
            "png_stored")
     _count(2)
     return out, size
+
+
+def conv_tapsum(y, bias, out):
+    """y fp32 [n,h,w,ldy] tap-major partial products, bias fp32 [nout], out u8 or fp32 [n,h,w,nout]."""
+    n, h, w, ldy = y.shape
+    nout = out.shape[-1]
+    with _timed("conv_tapsum", 0.0, 4.0 * y.numel() + out.element_size() * out.numel()):
+        _check(load().dl_conv_tapsum(y.data_ptr(), n, h, w, ldy, nout, bias.data_ptr(), out.data_ptr(),
+                                     int(out.dtype == torch.uint8), _stream()), "conv_tapsum")
+    _count()

@@ -190,6 +190,10 @@ class StyleManager:
 
     def load(self, name: str, lora_sd) -> StyleAdapter:
         ad = build_style_adapter(name, self.unet, self.shapes, lora_sd)
+        # the adapters update the plain packed projections in place; the gamma-folded copies used by the
+        # LayerNorm fold (weights.fold_layernorm) would go stale, so a UNet that carries style adapters keeps
+        # the standalone LayerNorm kernel
+        self.unet.fold_ln = False
         for i, (path, target, _, delta) in enumerate(ad.entries):
             key = id(target)
             if key not in self._masters:

@@ -116,6 +116,23 @@ def interleave_geglu(w: torch.Tensor) -> torch.Tensor:
     return torch.stack([w[:inner], w[inner:]], dim=1).reshape(w.shape)
 
 
+def fold_layernorm(w: torch.Tensor, bias, gamma: torch.Tensor, beta: torch.Tensor, device):
+    """LayerNorm folded into the Linear that consumes it (`dl_igemm_desc.ln_*`):
+        LN(x) W^T + b = rstd (x W'^T - mean colsum(W')) + (b + W beta),   W'[j,k] = W[j,k] gamma[k].
+    w: packed fp32 [N, K] (head padding / GEGLU interleave already applied), bias fp32 [N] or None.
+    -> (W' in the packing dtype, colsum(W') fp32 of the ROUNDED W' the tensor core multiplies, folded bias
+    fp32), or (None, None, None) outside the bf16 tensor-core path."""
+    if getattr(_tls, "dtype", torch.bfloat16) != torch.bfloat16:
+        return None, None, None
+    w = w.float()
+    wf = _bf(w * gamma.float()[None, :].to(w.device), device)
+    colsum = wf.float().sum(1)
+    b = w.to(torch.bfloat16).float() @ beta.float().to(w.device)
+    if bias is not None:
+        b = b + bias.float().to(w.device)
+    return wf, _f32(colsum, device), _f32(b, device)
+
+
 class Packed(dict):
     """dict with attribute access; values are device tensors or nested Packed."""
     __getattr__ = dict.__getitem__
@@ -157,14 +174,21 @@ def pack_transformer(sd, prefix: str, heads: int, device, depth: int = 1) -> Pac
         qkv = torch.cat([pad_heads(sd[b + f"attn1.to_{n}.weight"].float(), heads) for n in "qkv"], 0)
         q["qkv_w"] = _bf(qkv, device)
         q["qkv_b"] = _f32(ones_bias(heads, c // heads, 3, 2), device)
+        q["qkv_wf"], q["qkv_cs"], q["qkv_bf"] = fold_layernorm(qkv, ones_bias(heads, c // heads, 3, 2),
+                                                               sd[b + "norm1.weight"], sd[b + "norm1.bias"], device)
         q["o1_w"], q["o1_b"] = _bf(sd[b + "attn1.to_out.0.weight"], device), _f32(sd[b + "attn1.to_out.0.bias"], device)
         q["q2_w"] = _bf(pad_heads(sd[b + "attn2.to_q.weight"].float(), heads), device)
+        q["q2_wf"], q["q2_cs"], q["q2_bf"] = fold_layernorm(pad_heads(sd[b + "attn2.to_q.weight"].float(), heads), None,
+                                                            sd[b + "norm2.weight"], sd[b + "norm2.bias"], device)
         kv = torch.cat([pad_heads(sd[b + f"attn2.to_{n}.weight"].float(), heads) for n in "kv"], 0)
         q["kv2_w"] = _bf(kv, device)
         q["kv2_b"] = _f32(ones_bias(heads, c // heads, 2, 1), device)
         q["o2_w"], q["o2_b"] = _bf(sd[b + "attn2.to_out.0.weight"], device), _f32(sd[b + "attn2.to_out.0.bias"], device)
         q["ff1_w"] = _bf(interleave_geglu(sd[b + "ff.net.0.proj.weight"].float()), device)
         q["ff1_b"] = _f32(interleave_geglu(sd[b + "ff.net.0.proj.bias"].float()), device)
+        q["ff1_wf"], q["ff1_cs"], q["ff1_bf"] = fold_layernorm(interleave_geglu(sd[b + "ff.net.0.proj.weight"].float()),
+                                                               interleave_geglu(sd[b + "ff.net.0.proj.bias"].float()),
+                                                               sd[b + "norm3.weight"], sd[b + "norm3.bias"], device)
         q["ff2_w"], q["ff2_b"] = _bf(sd[b + "ff.net.2.weight"], device), _f32(sd[b + "ff.net.2.bias"], device)
         p["blocks"].append(q)
     return p

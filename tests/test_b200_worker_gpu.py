@@ -160,10 +160,15 @@ def test_style_lora_levels_and_reset(tmp_path):
     merged = {k: (v.float() + 1.0 * deltas[k] if k in deltas else v) for k, v in unet_sd.items()}
     ref = LCMPipelineB200(merged, unet_cfg_from_json(json.load(open(os.path.join(mdir, "unet", "config.json")))),
                           vae_sd, vae_cfg_from_json(json.load(open(os.path.join(mdir, "vae", "config.json")))), "cuda:0")
+    ref.unet.fold_ln = False          # like the worker's UNet: style adapters keep the standalone LayerNorm kernel
+    assert w.pipe.unet.fold_ln is False
     lat, noise = w._draw(5, 16, 16, 2)
     pe = w._text.encode(["a cat"])
     img = ref.generate(pe, lat, torch.stack(noise), 2, torch.tensor([1.0])).cpu().numpy()[0].astype(int)
-    assert np.abs(img - lvl2).max() <= 2, np.abs(img - lvl2).max()
+    # the worker adds the delta to the fp32 copy of the PACKED (bf16) weight, the offline merge to the fp16 file weight:
+    # one extra rounding -> a few pixels move by up to a few u8 steps
+    d = np.abs(img - lvl2)
+    assert d.max() <= 4 and (d > 1).mean() < 1e-2, (d.max(), (d > 1).mean())
 
 
 def test_worker_runs_its_text_tower_on_the_device(tmp_path):
@@ -295,3 +300,22 @@ def test_two_real_workers_capture_and_serve_concurrently(tmp_path):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+
+
+def test_latent_only_jobs_match_the_image_pass(worker):
+    """`run_job_latents` / `run_batch(latents_only=True)`: the denoise loop without VAE decode or PNG (Yume-style
+    candidate scoring).  The latents are those the image pass decodes: pooled to 8x8 they equal the 512 bytes
+    `run_job_with_latents` returns for the same request."""
+    import numpy as np
+    j = job(seed=21, size="128x128", steps=2)
+    lat, seed = worker.run_job_latents(j)
+    assert seed == 21 and lat.shape == (4, 16, 16) and lat.dtype == np.float32
+    _, _, lat_bytes = worker.run_job_with_latents(j)
+    pooled = torch.nn.functional.adaptive_avg_pool2d(torch.from_numpy(lat)[None], (8, 8)).to(torch.float16)
+    ref = np.frombuffer(lat_bytes, dtype=np.float16).reshape(1, 4, 8, 8)
+    assert np.abs(pooled.numpy().astype(np.float32) - ref.astype(np.float32)).max() <= 2e-3
+    many = worker.run_batch([job(prompt=f"c{i}", seed=300 + i, size="64x64", steps=1) for i in range(5)],
+                            latents_only=True)
+    assert [s for _, s in many] == [300, 301, 302, 303, 304] and all(a.shape == (4, 8, 8) for a, _ in many)
+    solo, _ = worker.run_job_latents(job(prompt="c2", seed=302, size="64x64", steps=1))
+    assert np.abs(solo - many[2][0]).max() <= 2e-2 * np.abs(solo).max()

@@ -255,6 +255,20 @@ def test_attention_tc(B, Sq, Skv, heads, d):
 
 
 @pytest.mark.parametrize("B,Sq,Skv,heads,d", [
+    (1, 4096, 77, 8, 40), (2, 1024, 77, 8, 80), (2, 256, 77, 8, 160), (1, 300, 77, 3, 40), (2, 512, 100, 4, 64),
+    (1, 384, 128, 2, 40), (16, 4096, 77, 8, 40), (1, 2304, 77, 8, 80), (1, 9216, 77, 2, 40), (3, 256, 5, 2, 40),
+])
+def test_attention_x_short_keys(B, Sq, Skv, heads, d):
+    """attention_x.cu (cross-attention: one key tile, a CTA walks a range of query tiles of one (image, head)):
+    77 text tokens with the 80-key tile, other short key lists with the 128-key tile, query counts that are not
+    a multiple of 128, one to three 64-column chunks per head (d = 40 / 80 / 160)."""
+    e = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True)
+    assert e < 2e-2, f"rel err {e}"
+    e2 = _attn_case(L(), B, Sq, Skv, heads, d, 0, v_ones=True, qscale=6.0, seed=11)
+    assert e2 < 2e-2, f"rel err (peaked rows) {e2}"
+
+
+@pytest.mark.parametrize("B,Sq,Skv,heads,d", [
     (1, 512, 512, 2, 40), (2, 1024, 1024, 3, 40), (1, 300, 600, 2, 40), (1, 4096, 4096, 1, 40),
     (1, 768, 1000, 2, 56), (1, 512, 640, 2, 48), (2, 9216, 9216, 1, 40),
 ])
@@ -525,3 +539,48 @@ def test_softmax_rows(rows, cols):
     torch.cuda.synchronize()
     assert (out.float() - ref).abs().max().item() <= 4e-3 * ref.max().item() + 1e-6
     assert torch.allclose(out.float().sum(-1), torch.ones(rows, device=DEV), atol=2e-2)
+
+
+@pytest.mark.parametrize("M,C,N,mode", [(4096, 320, 1152, 0), (1024, 640, 768, 0), (512, 1280, 2560, 1), (300, 320, 384, 0),
+                                        (65536, 320, 2560, 1)])
+def test_layernorm_folded_into_gemms(M, C, N, mode):
+    """LayerNorm without a LayerNorm pass (dl_igemm_desc.row_stats_out / ln_*): GEMM 1 (+ residual) leaves per-row
+    (sum, sumsq) records of its bf16 output h; GEMM 2 multiplies h by gamma-scaled weights and applies mean / rstd /
+    beta in its epilogue.  Reference: LayerNorm(h) in fp32 -> Linear (-> GEGLU); also against the unfused kernels."""
+    lib = L()
+    from dreamlab_b200.weights import fold_layernorm, interleave_geglu
+    x = bf(rand(M, C, seed=1))
+    w1 = bf(rand(C, C, seed=2, scale=C ** -0.5))
+    res = bf(rand(M, C, seed=3) + 0.7)                       # a row mean well away from zero
+    h = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    rs = lib.igemm(x, w1, h, nimg=1, h=1, w=M, taps=1, n=C, bias=rand(C, seed=4), residual=res, ldr=C, ldo=C,
+                   row_stats=True)
+    torch.cuda.synchronize()
+    tot = rs.double().sum(1)                                 # [M, 2]
+    assert torch.allclose(tot[:, 0], h.double().sum(1), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(tot[:, 1], (h.double() ** 2).sum(1), rtol=1e-5, atol=1e-3)
+    gamma, beta = rand(C, seed=5) * 0.3 + 1.0, rand(C, seed=6) * 0.3
+    w2 = rand(N, C, seed=7, scale=C ** -0.5)
+    b2 = rand(N, seed=8)
+    if mode == 1:
+        w2p, b2p = interleave_geglu(w2), interleave_geglu(b2)
+    else:
+        w2p, b2p = w2, b2
+    wf, cs, bfold = fold_layernorm(w2p, b2p, gamma, beta, DEV)
+    cols = N // 2 if mode == 1 else N
+    out = torch.empty(M, cols, device=DEV, dtype=torch.bfloat16)
+    lib.igemm(h, wf, out, nimg=1, h=1, w=M, taps=1, n=N, bias=bfold, mode=mode, ldo=cols, ln=(rs, cs, 1e-5))
+    # reference in fp32 from the same bf16 h
+    ln = F.layer_norm(h.float(), (C,), gamma, beta, 1e-5)
+    y = ln @ w2.t() + b2
+    if mode == 1:
+        y = y[:, :N // 2] * F.gelu(y[:, N // 2:])
+    # the unfused product path: LayerNorm kernel (bf16 out) -> GEMM
+    n1 = torch.empty_like(h)
+    lib.layernorm(h, n1, gamma, beta, 1e-5)
+    out2 = torch.empty_like(out)
+    lib.igemm(n1, bf(w2p), out2, nimg=1, h=1, w=M, taps=1, n=N, bias=b2p, mode=mode, ldo=cols)
+    torch.cuda.synchronize()
+    e_fold, e_plain = rel_err(out, y), rel_err(out2, y)
+    assert e_fold < 1e-2, e_fold
+    assert e_fold <= 1.5 * e_plain + 1e-3, (e_fold, e_plain)      # no worse than the pass it replaces
