@@ -247,7 +247,7 @@ class B200Worker(PipelineWorker):
             int(torch.randint(0, 100_000_000, (1,)).item())
         return width, height, seed
 
-    def _draw(self, seed: int, h8: int, w8: int, steps: int):
+    def _draw(self, seed: int, h8: int, w8: int, steps: int, raw: bool = False):
         """The reference's per-request Philox stream (`backends/cuda_worker.py:212-213`,
         SURVEY.md App. A.5): latents first, then one draw per non-final step."""
         gen = torch.Generator(device=self.device)
@@ -256,8 +256,9 @@ class B200Worker(PipelineWorker):
         lat = torch.randn(shape, generator=gen, device=self.device, dtype=torch.float32)
         noise = [torch.randn(shape, generator=gen, device=self.device, dtype=torch.float32)
                  for _ in range(steps - 1)]
-        lat = lat.to(self.dtype).float()
-        noise = [z.to(self.dtype).float() for z in noise]
+        if not raw:
+            lat = lat.to(self.dtype).float()
+            noise = [z.to(self.dtype).float() for z in noise]
         return lat, noise
 
     supports_deferred = True      # run_batch(..., deferred=True) -> thunks (see WorkerPool)
@@ -277,9 +278,11 @@ class B200Worker(PipelineWorker):
             for (w, h, _), j in zip(parsed, jobs):
                 if (w, h) != (width, height) or int(j.req.num_inference_steps) != steps:
                     raise RuntimeError("run_batch: jobs must share size and num_inference_steps")
-            draws = [self._draw(seed, height // 8, width // 8, steps) for _, _, seed in parsed]
-            lat = torch.cat([d[0] for d in draws], 0)
-            noise = (torch.stack([torch.cat([d[1][i] for d in draws], 0) for i in range(steps - 1)])
+            # per-request Philox streams; the round trip through the noise dtype (CUDA_DTYPE) is applied once to
+            # the assembled batch instead of per tensor (same values, ~8 fewer launches per request)
+            draws = [self._draw(seed, height // 8, width // 8, steps, raw=True) for _, _, seed in parsed]
+            lat = torch.cat([d[0] for d in draws], 0).to(self.dtype).float()
+            noise = (torch.stack([torch.cat([d[1][i] for d in draws], 0) for i in range(steps - 1)]).to(self.dtype).float()
                      if steps > 1 else None)
             gs = torch.tensor([float(j.req.guidance_scale) for j in jobs])
             styles = {self._style_of(j.req) for j in jobs}
@@ -306,9 +309,9 @@ class B200Worker(PipelineWorker):
             if not raw and _png_mode() == "gpu":
                 # the finished PNG files come off the device (csrc/png.cu): no zlib on the host
                 png_dev, png_size = lib.png_stored(img.contiguous())
-                png_files = png_dev.cpu().numpy()
+                png_files = _to_host(png_dev)
             else:
-                img = img.cpu().numpy()
+                img = _to_host(img)
 
         def finish(i):
             seed = parsed[i][2]
@@ -382,6 +385,16 @@ def _encoders():
         n = int(os.environ.get("B200_PNG_THREADS", "0")) or min(16, os.cpu_count() or 4)
         _ENCODERS = ThreadPoolExecutor(max_workers=n, thread_name_prefix="png")
     return _ENCODERS
+
+
+def _to_host(t: torch.Tensor):
+    """Device tensor -> numpy through a PINNED staging tensor (torch's caching host allocator recycles the
+    blocks): a pageable `.cpu()` of a 12.6 MB batch runs at a fraction of the link rate.  The array keeps its
+    pinned tensor alive until the last PNG thunk that reads it is done."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()
 
 
 def _png_mode() -> str:

@@ -70,16 +70,10 @@ struct AttnParams {
 // kPoly: of every 8 score pairs, this many take their exponentials from `poly_exp2` (FMA / ALU
 // pipes) instead of MUFU.EX2 — the exp pass of the d = 40 / 64 / 80 heads is bound by the 16-lane XU
 // pipe (one MUFU per score), not by the tensor core (opt-in: DL_ATTN_POLY).
-// SW: softmax warps.  8 (default): two threads per query row, 2 CTAs / SM.  4 (opt-in, DL_ATTN_MODE=6,
-// EXPERIMENTAL — compiled and SASS-checked, not yet run on a GPU): one thread per row over a 64-key
-// tile, 192 threads, 128 TMEM columns (S 64 + O <= 64), so THREE CTAs fit an SM: the per-tile chain
-// (TMEM load -> max -> exp -> TMEM store -> PV + next QK^T) of one CTA is what bounds the kernel at
-// 2 CTAs / SM, and a third context keeps the XU pipe fed; the half-row max exchange and its named
-// barrier disappear.
-template <bool kOnes, bool kBf16Exp, int KS, int KT, int kPoly = 0, int SW = 8>
-__global__ void __launch_bounds__(64 + 32 * SW, SW == 4 ? 3 : 2)
+template <bool kOnes, bool kBf16Exp, int KS, int KT, int kPoly = 0>
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ AttnParams p) {
-  static_assert(SW == 8 || SW == 4, "8 softmax warps (two threads per row) or 4 (one thread per row)");
+  constexpr int SW = 8;                              // softmax warps: two threads per query row
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ float xch[2][2][AT_TILE];              // [tile parity][half][row] max / sum exchange
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -296,7 +290,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
     // 8 warps: two per TMEM lane quadrant; a query row is shared by two threads, each owning
     // 64 of the tile's 128 key columns (halves the serial TMEM-load -> exp chain per tile).
     const int quad = warp & 3;
-    const int ch = SW == 8 ? (warp - 2) >> 2 : 0;    // column half owned by this thread (SW = 4: whole row)
+    const int ch = (warp - 2) >> 2;                  // column half owned by this thread
     const int r = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const uint32_t o_tmem = tmem_base + lane_off + o_col;
@@ -311,8 +305,8 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j < 16 &&
                       threadIdx.x == 64;
       if (tr) p.trace[j * 16 + 4] = clock64();
-      // my columns: 64 / 48 / 32 (compile-time when KT is); one thread per row owns the whole 64-key tile
-      const int hc = SW == 8 ? (KT > 0 ? KT / 2 : (p.kt >> 1)) : (KT > 0 ? KT : p.kt);
+      // my columns: 64 / 48 / 32 (compile-time when KT is)
+      const int hc = KT > 0 ? KT / 2 : (p.kt >> 1);
       const int kbase = j * p.kt + ch * hc;
       const bool need_mask = (j * p.kt + p.kt > p.skv);         // only the last tile (warp-uniform)
       // my S columns -> registers with ONE TMEM round trip (loads in flight together); they
@@ -359,13 +353,11 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       }
       // exchange the half-row maxima; after this barrier every thread of the CTA has its S
       // values in registers, so P may overwrite the S columns right away
-      if (SW == 8) {
-        xch[j & 1][ch][r] = mx;
-        if (tr) p.trace[j * 16 + 6] = clock64();
-        named_bar_sync(1, 256);
-        if (tr) p.trace[j * 16 + 7] = clock64();
-        mx = fmaxf(mx, xch[j & 1][ch ^ 1][r]);
-      }
+      xch[j & 1][ch][r] = mx;
+      if (tr) p.trace[j * 16 + 6] = clock64();
+      named_bar_sync(1, 256);
+      if (tr) p.trace[j * 16 + 7] = clock64();
+      mx = fmaxf(mx, xch[j & 1][ch ^ 1][r]);
       // lazy running max: only move it when the tile max exceeds it by more than 2^8 — P then
       // stays <= 256 (exact in bf16/fp32 range), the O rescale becomes rare instead of
       // per-tile, and the final O / l is unchanged because l sees the same P
@@ -464,7 +456,7 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
       for (int i = 0; i < 16; ++i)
         if (i == (p.l_col & 15)) lv = __uint_as_float(oo[i]);
       l_run = lv;
-    } else if (SW == 8) {
+    } else {
       named_bar_sync(2, 256);                        // xch is free again
       xch[0][ch][r] = l_run;
       named_bar_sync(1, 256);
@@ -554,18 +546,6 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   static const int kts[3] = {128, 96, 64};
   int kv_bytes = 0;
   bool done = false;
-  //  0. (DL_ATTN_MODE=6 only, EXPERIMENTAL: not yet run on a GPU) three CTAs per SM for head dim 40:
-  //     64-key tile, 128 TMEM columns (S 64 + O 48), one softmax thread per row (SW = 4, 192 threads)
-  bool sw4 = false;
-  if (force_mode == 6 && p.l_col >= 0 && p.ksteps == 3 && p.dv <= 64 && skv >= 256) {
-    const int third_budget = (227 * 1024) / 3 - 1024;
-    kv_bytes = (p.nchunk_qk + p.nchunk_v) * 64 * 128;
-    const int st = (third_budget - overhead - q_bytes) / kv_bytes;
-    if (st >= 2) {
-      p.kt = 64; p.sbuf = 1; p.tmem_cols = 128; p.stages = st;
-      done = sw4 = true;
-    }
-  }
   for (int ki = 0; ki < 3 && !done && force_mode == 3; ++ki) {   // measured slower: opt-in only
     const int kt = kts[ki];
     kv_bytes = (p.nchunk_qk + p.nchunk_v) * kt * 128;
@@ -640,8 +620,6 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
     DL_ATTN_ATTR(true, true, 3, 128, 3);
     DL_ATTN_ATTR(true, true, 4, 128, 2);
     DL_ATTN_ATTR(true, true, 5, 128, 2);
-    DL_ATTN_ATTR(true, true, 3, 64, 0, 4);
-    DL_ATTN_ATTR(true, true, 3, 64, 2, 4);
 #undef DL_ATTN_ATTR
     if (e != cudaSuccess) { set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 1; }
     attr_set[dev & 63] = true;
@@ -656,10 +634,7 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   static int poly = -2;
   if (poly == -2) { const char* e = getenv("DL_ATTN_POLY"); poly = e ? atoi(e) : -1; }
   const bool long_keys = skv >= 256;           // short key lists (cross attention) are not exp-bound
-  if (sw4) {
-    if (poly == 0) attn_tc_kernel<true, true, 3, 64, 0, 4><<<grid, 64 + 32 * 4, smem_bytes, stream>>>(p);
-    else attn_tc_kernel<true, true, 3, 64, 2, 4><<<grid, 64 + 32 * 4, smem_bytes, stream>>>(p);
-  } else if (p.l_col < 0) {
+  if (p.l_col < 0) {
     attn_tc_kernel<false, false, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 3 && !generic && poly == 3 && long_keys) {
     attn_tc_kernel<true, true, 3, 128, 3><<<grid, AT_THREADS, smem_bytes, stream>>>(p);

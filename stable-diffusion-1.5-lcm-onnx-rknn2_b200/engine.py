@@ -724,7 +724,9 @@ class _StaticGraph:
             # an explicit capture stream on THIS device: torch.cuda.graph's default capture stream is one
             # class-wide stream created on whichever device captured first, so a second worker (another GPU,
             # same process) would capture on the wrong device
-            with torch.cuda.graph(self.graph, stream=s, capture_error_mode="thread_local"):
+            # one memory pool for all graphs of a pipeline: they replay one at a time on the worker's thread, so
+            # their intermediates may share addresses (a dozen private pools at SDXL 1024^2 is a lot of HBM)
+            with torch.cuda.graph(self.graph, pool=pipe._graph_pool(), stream=s, capture_error_mode="thread_local"):
                 self.img, self.final = pipe.run_static(*args, **kw)
             self.launches = lib.launch_count - n0        # native kernel launches per replay
 
@@ -787,7 +789,15 @@ class LCMPipelineB200:
             return None, lat
         return self.vae.decode(lat, tiling=self.vae_tiling), lat
 
-    max_graphs = 12       # captured geometries kept per pipeline (each owns its activation pool)
+    max_graphs = 12       # captured geometries kept per pipeline
+    # batch sizes a CUDA graph is captured for: a request batch is padded up to the next one (micro-batching
+    # produces every B in 1..16; one graph per exact B would thrash the LRU and re-capture constantly)
+    batch_buckets = (1, 2, 4, 8, 16)
+
+    def _graph_pool(self):
+        if getattr(self, "_pool", None) is None:
+            self._pool = torch.cuda.graph_pool_handle()
+        return self._pool
 
     def graph_for(self, B, h, w, steps, cfg_scale=None, decode=True) -> _StaticGraph:
         key = (B, h, w, steps, cfg_scale, decode)
@@ -876,6 +886,27 @@ class LCMPipelineB200:
         replay; the returned tensors are the graph's static outputs (consume before next call)."""
         B, _, h, w = latents_nchw.shape
         steps = int(num_inference_steps)
+        if use_graph and record is None and teacher_latents is None:
+            Bp = next((b for b in self.batch_buckets if b >= B), B)
+            if Bp != B:
+                # pad to the bucket by repeating the last request (images are independent: per-image GroupNorm,
+                # per-image attention), run the bucket's graph, return the first B results
+                def pad(t, dim=0):
+                    if t is None or not torch.is_tensor(t) or t.dim() == 0:
+                        return t
+                    idx = [slice(None)] * t.dim()
+                    idx[dim] = slice(t.shape[dim] - 1, t.shape[dim])
+                    return torch.cat([t] + [t[tuple(idx)]] * (Bp - B), dim)
+                gs = torch.as_tensor(guidance_scale, dtype=torch.float32).reshape(-1)
+                out = self.generate(pad(prompt_embeds), pad(latents_nchw),
+                                    pad(step_noise_nchw, 1) if steps > 1 else step_noise_nchw, steps,
+                                    pad(gs) if gs.numel() > 1 else guidance_scale, return_latents=True, use_graph=True,
+                                    pooled_embeds=pad(pooled_embeds), time_ids=pad(time_ids),
+                                    negative_prompt_embeds=pad(negative_prompt_embeds),
+                                    negative_pooled_embeds=pad(negative_pooled_embeds), decode=decode)
+                img, lat = out
+                img = img[:B] if img is not None else None
+                return (img, lat[:B]) if return_latents else img
         w_emb = self._w_emb(B, guidance_scale)
         cfg_scale = self.cfg_scale_for(guidance_scale)
         pe_all, add = self._conditioning(prompt_embeds, pooled_embeds, time_ids, negative_prompt_embeds,

@@ -146,6 +146,25 @@ def test_batch_invariance():
     assert d.max().item() <= 1, d.max().item()
 
 
+def test_graph_batch_buckets_pad_and_share_one_pool():
+    """Micro-batching produces every batch size in 1..16: graphs are captured per bucket (1/2/4/8/16), a batch
+    is padded up to its bucket and the first B results returned — equal to the eager pass of the same B requests —
+    and all graphs of a pipeline share one memory pool."""
+    from oracle.unet import UNetConfig
+    from oracle.vae import VAEConfig
+    from oracle.pipeline import synthetic_inputs
+    _, _, pipe = _build(UNetConfig.tiny(), VAEConfig.tiny())
+    pe, lat, noise = synthetic_inputs(7, 128, 128, 3, ctx_dim=64)
+    for B in (3, 5, 7, 2):
+        eager = pipe.generate(pe[:B], lat[:B], noise[:, :B], 3, 1.0).clone()
+        graph = pipe.generate(pe[:B], lat[:B], noise[:, :B], 3, 1.0, use_graph=True).clone()
+        torch.cuda.synchronize()
+        assert graph.shape == eager.shape
+        assert (graph.int() - eager.int()).abs().max().item() <= 1, B          # the batch-invariance bar
+    assert sorted(k[0] for k in pipe._graphs) == [2, 4, 8]                      # 3 -> 4, 5 and 7 -> 8, 2 -> 2
+    assert pipe._graph_pool() is pipe._graph_pool()
+
+
 def test_sd15_lcm_768_8step_vs_committed_golden():
     """BASELINE config C3 geometry (768x768, 8 steps; B=1 here): larger attention sequences
     (S = 9216 / 2304 / 576 / 144, partial tiles everywhere) and the 768^2 VAE decode (untiled:
