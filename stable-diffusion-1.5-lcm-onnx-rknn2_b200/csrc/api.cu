@@ -1,6 +1,5 @@
 // Host-side plumbing of the C-ABI: error text, driver entry points, tensor-map encoding.
 #include <stdarg.h>
-#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -17,12 +16,6 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
-
-bool pdl_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("DL_PDL"); v = (e && atoi(e) == 0) ? 0 : 1; }
-  return v != 0;
-}
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

@@ -125,8 +125,6 @@ attn_tc_kernel(const __grid_constant__ AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();                                   // PDL: prologue done, global memory from here on
-  pdl_wait();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -637,23 +635,23 @@ static int attn_tc_launch(const void* q, long long ldq, const void* k, long long
   if (poly == -2) { const char* e = getenv("DL_ATTN_POLY"); poly = e ? atoi(e) : -1; }
   const bool long_keys = skv >= 256;           // short key lists (cross attention) are not exp-bound
   if (p.l_col < 0) {
-    launch_pdl(attn_tc_kernel<false, false, 0, 0>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<false, false, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 3 && !generic && poly == 3 && long_keys) {
-    launch_pdl(attn_tc_kernel<true, true, 3, 128, 3>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 3, 128, 3><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 3 && !generic && (poly >= 2 || poly == -1) && long_keys) {
-    launch_pdl(attn_tc_kernel<true, true, 3, 128, 2>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 3, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 4 && !generic && poly >= 2 && long_keys) {
-    launch_pdl(attn_tc_kernel<true, true, 4, 128, 2>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 4, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 5 && !generic && poly >= 2 && long_keys) {
-    launch_pdl(attn_tc_kernel<true, true, 5, 128, 2>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 5, 128, 2><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 3 && !generic) {       // SD1.5 head dim 40
-    launch_pdl(attn_tc_kernel<true, true, 3, 128>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 3, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 4 && !generic) {       // SDXL head dim 64
-    launch_pdl(attn_tc_kernel<true, true, 4, 128>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 4, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else if (p.kt == 128 && p.ksteps == 5 && !generic) {       // SD1.5 head dim 80
-    launch_pdl(attn_tc_kernel<true, true, 5, 128>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 5, 128><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   } else {
-    launch_pdl(attn_tc_kernel<true, true, 0, 0>, grid, dim3(AT_THREADS), smem_bytes, stream, p);
+    attn_tc_kernel<true, true, 0, 0><<<grid, AT_THREADS, smem_bytes, stream>>>(p);
   }
   return check_launch("attention(tc)");
 }

@@ -126,8 +126,6 @@ attn_pp_kernel(const __grid_constant__ AttnPPParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();                                   // PDL: prologue done, global memory from here on
-  pdl_wait();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -445,7 +443,7 @@ int attn_pp_launch(const void* q, long long ldq, const void* k, long long ldk, c
   const int ks = d16 / 16;
   const int pl = poly <= 0 ? 0 : (poly >= 3 ? 3 : 2);
 #define DL_PP_LAUNCH(KS_, PL_, NQ_) \
-  launch_pdl(attn_pp_kernel<KS_, PL_, NQ_>, grid, dim3(64 + 128 * NQ_), smem_bytes, stream, p)
+  attn_pp_kernel<KS_, PL_, NQ_><<<grid, 64 + 128 * NQ_, smem_bytes, stream>>>(p)
 #define DL_PP_PICK(KS_, NQ_)                                                                   \
   do {                                                                                          \
     if (pl == 0) DL_PP_LAUNCH(KS_, 0, NQ_); else if (pl == 2) DL_PP_LAUNCH(KS_, 2, NQ_);        \

@@ -91,8 +91,6 @@ attn_x_kernel(const __grid_constant__ AttnXParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t O_COL = 128u;
-  pdl_trigger();                                   // PDL: prologue done, global memory from here on
-  pdl_wait();
 
   if (warp == 0) {
     // ============================ TMA producer ============================
@@ -308,8 +306,8 @@ int attn_x_launch(const void* q, long long ldq, const void* k, long long ldk, co
     attr_set[dev & 63] = true;
   }
   dim3 grid(chunks, heads, batch);
-  if (p.kt == 80) launch_pdl(attn_x_kernel<80>, grid, dim3(AX_THREADS), smem_bytes, stream, p);
-  else launch_pdl(attn_x_kernel<128>, grid, dim3(AX_THREADS), smem_bytes, stream, p);
+  if (p.kt == 80) attn_x_kernel<80><<<grid, AX_THREADS, smem_bytes, stream>>>(p);
+  else attn_x_kernel<128><<<grid, AX_THREADS, smem_bytes, stream>>>(p);
   return check_launch("attention(x)");
 }
 

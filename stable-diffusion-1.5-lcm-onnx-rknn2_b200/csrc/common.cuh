@@ -317,16 +317,6 @@ __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// ---- programmatic dependent launch (PDL) ----
-// Every hot kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization (`launch_pdl` below): the next
-// kernel of the stream is scheduled while this one is still running, executes its prologue (barrier init, TMEM
-// allocation, tensor-map prefetch, index math) and then blocks in `pdl_wait()` until the previous grid has completed
-// and flushed its memory.  At B = 1 the pass is ~1800 launches of ~10 us: the launch / drain bubble between kernels
-// was a third of the latency.  Rule: a kernel launched through launch_pdl MUST call pdl_wait() before its first
-// global-memory access (reads of the producer's output AND writes to buffers an earlier kernel may still read).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
 // ---- small numeric helpers ----
 // packed bf16 in, packed bf16 out: saves the fp32 -> bf16 conversion of the results (in sm_100a SASS it is
 // still two MUFU.EX2.BF16, one per half, + a PRMT — not two exponentials per XU op)
@@ -395,24 +385,6 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
-}
-
-// host: kernel launch with the PDL attribute (DL_PDL=0 in the environment: plain stream order)
-bool pdl_enabled();
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                              Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 #endif  // __CUDACC__

@@ -11,8 +11,6 @@ namespace dl {
 // ---- Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) ---------------------------------------
 __global__ void sinusoid_kernel(const float* __restrict__ t, int batch, int dim,
                                 float* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
@@ -33,8 +31,6 @@ __global__ void small_linear_kernel(const float* __restrict__ x, int m, int k,
                                     const __nv_bfloat16* __restrict__ w,
                                     const float* __restrict__ bias, const float* __restrict__ add,
                                     int n, int silu_in, int silu_out, float* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = warp * NR;
@@ -114,8 +110,6 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int nimg, int h, 
 // ---- im2col for conv3x3 stride 2 pad 1 (Downsample2D): cols[(n,yo,xo), tap*c + ch] ----------
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int nimg, int h, int w, int V,
                                  uint4* __restrict__ cols, int in_rows, int in_row0) {
-  pdl_trigger();
-  pdl_wait();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)nimg * ho * wo * 9 * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -142,8 +136,6 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int nimg, int h, i
 __global__ void pack_latent_kernel(const float* __restrict__ x, long long npix, int cin, int cpad,
                                    float scale, const float* __restrict__ mat,
                                    const float* __restrict__ vec, __nv_bfloat16* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const long long total = npix * cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -165,8 +157,6 @@ __global__ void pack_latent_kernel(const float* __restrict__ x, long long npix, 
 // row softmax: fp32 scores [rows, cols] -> bf16 probabilities (VAE mid-block attention, d=512)
 __global__ void softmax_rows_kernel(const float* __restrict__ s, long long rows, int cols,
                                     __nv_bfloat16* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* sr = s + row * cols;
@@ -201,8 +191,6 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, long long rows,
 
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int nimg, int c, int hw,
                                     float* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const long long total = (long long)nimg * c * hw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -230,8 +218,6 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int nimg, int c
 __global__ void lcm_step_kernel(const float4* __restrict__ eps, const float4* __restrict__ x,
                                 const float4* __restrict__ noise, float4* __restrict__ x_next,
                                 float4* __restrict__ denoised, long long n4, dl_lcm_coeffs k) {
-  pdl_trigger();
-  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 e = eps[i], xv = x[i];
@@ -355,8 +341,6 @@ __global__ void image_crop_u8_kernel(const float* __restrict__ src, int nimg, in
 // ---- classifier-free guidance: out = u + gs * (t - u), un-contracted like the reference ------
 __global__ void cfg_combine_kernel(const float4* __restrict__ u, const float4* __restrict__ t, float gs,
                                    float4* __restrict__ out, long long n4) {
-  pdl_trigger();
-  pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     const float4 a = u[i], b = t[i];
@@ -395,8 +379,6 @@ __global__ void latent_pool8_kernel(const float* __restrict__ lat, int nimg, int
 template <bool U8>
 __global__ void conv_tapsum_kernel(const float* __restrict__ yp, int nimg, int h, int w, int ldy, int nout,
                                    const float* __restrict__ bias, void* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const long long total = (long long)nimg * h * w;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -447,7 +429,7 @@ using namespace dl;
 extern "C" int dl_timestep_sinusoid(const float* t, int batch, int dim, float* out, void* stream_) {
   DL_CHECK_ARG(t && out && dim % 2 == 0 && batch > 0, "timestep_sinusoid: bad args");
   const int total = batch * dim / 2;
-  launch_pdl(sinusoid_kernel, dim3((total + 127) / 128), dim3(128), 0, STREAM, t, batch, dim, out);
+  sinusoid_kernel<<<(total + 127) / 128, 128, 0, STREAM>>>(t, batch, dim, out);
   return check_launch("timestep_sinusoid");
 }
 
@@ -466,10 +448,12 @@ extern "C" int dl_small_linear(const float* x, int m, int k, const void* w, cons
   for (int m0 = 0; m0 < m; m0 += 16) {
     const int mm = (m - m0) < 16 ? (m - m0) : 16;
     if (nr == 4)
-      launch_pdl(small_linear_kernel<16, 4>, dim3(blocks), dim3(threads), 0, STREAM, x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
+      small_linear_kernel<16, 4><<<blocks, threads, 0, STREAM>>>(
+          x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
           silu_out, out + (size_t)m0 * n);
     else
-      launch_pdl(small_linear_kernel<16, 1>, dim3(blocks), dim3(threads), 0, STREAM, x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
+      small_linear_kernel<16, 1><<<blocks, threads, 0, STREAM>>>(
+          x + (size_t)m0 * k, mm, k, wb, bias, add ? add + (size_t)m0 * n : nullptr, n, silu_in,
           silu_out, out + (size_t)m0 * n);
   }
   return check_launch("small_linear");
@@ -486,7 +470,8 @@ extern "C" int dl_upsample2x(const void* x, int nimg, int h, int w, int c, void*
 extern "C" int dl_im2col_s2(const void* x, int nimg, int h, int w, int c, void* cols, void* stream_) {
   DL_CHECK_ARG(x && cols && c % 8 == 0 && h % 2 == 0 && w % 2 == 0, "im2col_s2: bad args");
   const long long total = (long long)nimg * (h / 2) * (w / 2) * 9 * (c / 8);
-  launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(cols), h, 0);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(cols), h, 0);
   return check_launch("im2col_s2");
 }
 
@@ -495,14 +480,16 @@ extern "C" int dl_im2col_s2_halo(const void* x, int nimg, int in_rows, int in_ro
   DL_CHECK_ARG(x && cols && c % 8 == 0 && h % 2 == 0 && w % 2 == 0 && in_rows >= h && in_row0 >= 0,
                "im2col_s2_halo: bad args");
   const long long total = (long long)nimg * (h / 2) * (w / 2) * 9 * (c / 8);
-  launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(cols), in_rows, in_row0);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const uint4*>(x), nimg, h, w, c / 8, reinterpret_cast<uint4*>(cols), in_rows, in_row0);
   return check_launch("im2col_s2_halo");
 }
 
 extern "C" int dl_pack_latent(const float* x, long long npix, int cin, int cpad, float scale,
                               const float* mat, const float* vec, void* out, void* stream_) {
   DL_CHECK_ARG(x && out && cin <= cpad, "pack_latent: bad args");
-  launch_pdl(pack_latent_kernel, dim3(grid_for(npix * cpad, 256)), dim3(256), 0, STREAM, x, npix, cin, cpad, scale, mat, vec, reinterpret_cast<__nv_bfloat16*>(out));
+  pack_latent_kernel<<<grid_for(npix * cpad, 256), 256, 0, STREAM>>>(
+      x, npix, cin, cpad, scale, mat, vec, reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("pack_latent");
 }
 
@@ -511,8 +498,6 @@ namespace dl {
 // three, float4 loads, packed 8-byte bf16 stores
 __global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* __restrict__ s, long long rows, int cols,
                                                                __nv_bfloat16* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   __shared__ float red[8];
   const long long row = blockIdx.x;
   const float4* sr = reinterpret_cast<const float4*>(s + row * cols);
@@ -559,17 +544,17 @@ extern "C" int dl_softmax_rows(const float* scores, long long rows, int cols, vo
                                void* stream_) {
   DL_CHECK_ARG(scores && out && rows > 0 && cols > 0, "softmax_rows: bad args");
   if (cols % 4 == 0 && cols <= 4096)
-    launch_pdl(softmax_rows_reg_kernel, dim3((unsigned)rows), dim3(256), 0, STREAM, scores, rows, cols,
+    softmax_rows_reg_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(scores, rows, cols,
                                                                reinterpret_cast<__nv_bfloat16*>(out));
   else
-    launch_pdl(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), 0, STREAM, scores, rows, cols,
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, STREAM>>>(scores, rows, cols,
                                                            reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("softmax_rows");
 }
 
 extern "C" int dl_nchw_to_nhwc_f32(const float* x, int nimg, int c, int hw, float* out, void* stream_) {
   DL_CHECK_ARG(x && out, "nchw_to_nhwc: null pointer");
-  launch_pdl(nchw_to_nhwc_kernel, dim3(grid_for((long long)nimg * c * hw, 256)), dim3(256), 0, STREAM, x, nimg, c, hw, out);
+  nchw_to_nhwc_kernel<<<grid_for((long long)nimg * c * hw, 256), 256, 0, STREAM>>>(x, nimg, c, hw, out);
   return check_launch("nchw_to_nhwc");
 }
 extern "C" int dl_nhwc_to_nchw_f32(const float* x, int nimg, int c, int hw, float* out, void* stream_) {
@@ -582,7 +567,8 @@ extern "C" int dl_lcm_step(const float* eps, const float* x, const float* noise,
                            float* denoised, long long n, const dl_lcm_coeffs* k, void* stream_) {
   DL_CHECK_ARG(eps && x && x_next && denoised && k, "lcm_step: null pointer");
   DL_CHECK_ARG(n % 4 == 0, "lcm_step: n must be a multiple of 4");
-  launch_pdl(lcm_step_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, STREAM, reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(x),
+  lcm_step_kernel<<<grid_for(n / 4, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(eps), reinterpret_cast<const float4*>(x),
       reinterpret_cast<const float4*>(noise), reinterpret_cast<float4*>(x_next),
       reinterpret_cast<float4*>(denoised), n / 4, *k);
   return check_launch("lcm_step");
@@ -631,9 +617,9 @@ extern "C" int dl_conv_tapsum(const float* y, int nimg, int h, int w, int ldy, i
   DL_CHECK_ARG(nout >= 1 && nout <= 4 && ldy >= 9 * nout, "conv_tapsum: nout in [1,4], ldy >= 9*nout (got %d, %d)", nout, ldy);
   const long long total = (long long)nimg * h * w;
   if (out_u8)
-    launch_pdl(conv_tapsum_kernel<true>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, y, nimg, h, w, ldy, nout, bias, out);
+    conv_tapsum_kernel<true><<<grid_for(total, 256), 256, 0, STREAM>>>(y, nimg, h, w, ldy, nout, bias, out);
   else
-    launch_pdl(conv_tapsum_kernel<false>, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, y, nimg, h, w, ldy, nout, bias, out);
+    conv_tapsum_kernel<false><<<grid_for(total, 256), 256, 0, STREAM>>>(y, nimg, h, w, ldy, nout, bias, out);
   return check_launch("conv_tapsum");
 }
 
@@ -641,7 +627,8 @@ extern "C" int dl_cfg_combine(const float* eps_uncond, const float* eps_text, fl
                               float* out, long long n, void* stream_) {
   DL_CHECK_ARG(eps_uncond && eps_text && out, "cfg_combine: null pointer");
   DL_CHECK_ARG(n % 4 == 0, "cfg_combine: n must be a multiple of 4");
-  launch_pdl(cfg_combine_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, STREAM, reinterpret_cast<const float4*>(eps_uncond), reinterpret_cast<const float4*>(eps_text),
+  cfg_combine_kernel<<<grid_for(n / 4, 256), 256, 0, STREAM>>>(
+      reinterpret_cast<const float4*>(eps_uncond), reinterpret_cast<const float4*>(eps_text),
       guidance_scale, reinterpret_cast<float4*>(out), n / 4);
   return check_launch("cfg_combine");
 }

@@ -170,9 +170,6 @@ igemm_kernel(const __grid_constant__ IgemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // PDL: the prologue above ran under the previous kernel's tail; from here on global memory is touched
-  pdl_trigger();
-  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -830,9 +827,8 @@ int igemm_launch(const dl_igemm_desc* d, cudaStream_t stream) {
   }
   const int num_tiles = ((p.m_tiles + p.msub - 1) / p.msub) * p.n_tiles;
   const int grid = num_tiles < sms ? num_tiles : sms;
-  cudaError_t le = p.msub == 2 ? launch_pdl(igemm_kernel<2>, dim3(grid), dim3(IGEMM_THREADS), smem_bytes, stream, p)
-                               : launch_pdl(igemm_kernel<1>, dim3(grid), dim3(IGEMM_THREADS), smem_bytes, stream, p);
-  if (le != cudaSuccess) { set_error("igemm: launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return 2; }
+  if (p.msub == 2) igemm_kernel<2><<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
+  else igemm_kernel<1><<<grid, IGEMM_THREADS, smem_bytes, stream>>>(p);
   return check_launch("igemm");
 }
 

@@ -434,8 +434,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
                                                         int C, float eps, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta,
                                                         __nv_bfloat16* __restrict__ out) {
-  pdl_trigger();
-  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -616,8 +614,6 @@ __global__ void __launch_bounds__(GNX_THREADS) gn_stats_kernel(const GnSplitPara
 }
 
 __global__ void __launch_bounds__(GNX_THREADS) gn_apply_kernel(const GnSplitParams p) {
-  pdl_trigger();
-  pdl_wait();
   __shared__ float s_mean[GN_MAX_GROUPS];
   __shared__ float s_rstd[GN_MAX_GROUPS];
   const int C = p.c0 + p.c1;
@@ -670,8 +666,6 @@ __global__ void __launch_bounds__(GNX_THREADS) gn_apply_kernel(const GnSplitPara
 // (sum, sumsq) per (image, M tile, group) from the producing conv's epilogue -> (mean, M2)
 __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restrict__ partial, int slots,
                                                           int groups, double count, float* __restrict__ stats) {
-  pdl_trigger();
-  pdl_wait();
   __shared__ double sh[2][128];
   const int img = blockIdx.x / groups, g = blockIdx.x % groups;
   double s = 0.0, q = 0.0;
@@ -701,8 +695,6 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float* __restric
 __global__ void __launch_bounds__(128) gn_finalize_chan_kernel(const float* __restrict__ part0, int slots0, int c0,
                                                                const float* __restrict__ part1, int slots1, int c1,
                                                                int groups, double count, float* __restrict__ stats) {
-  pdl_trigger();
-  pdl_wait();
   __shared__ double sh[2][128];
   const int img = blockIdx.x / groups, g = blockIdx.x % groups;
   const int cpg = (c0 + c1) / groups;
@@ -766,8 +758,8 @@ extern "C" int dl_groupnorm_finalize(const float* partial, int nimg, int slots, 
                                      float* stats, void* stream_) {
   using namespace dl;
   DL_CHECK_ARG(partial && stats && nimg > 0 && slots > 0 && groups > 0 && count > 0, "groupnorm_finalize: bad args");
-  launch_pdl(gn_finalize_kernel, dim3(nimg * groups), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream_), partial, slots,
-             groups, (double)count, stats);
+  gn_finalize_kernel<<<nimg * groups, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(partial, slots, groups,
+                                                                                       (double)count, stats);
   return check_launch("groupnorm_finalize");
 }
 
@@ -779,8 +771,8 @@ extern "C" int dl_groupnorm_finalize_channels(const float* part0, int slots0, in
                "groupnorm_finalize_channels: bad args");
   DL_CHECK_ARG(c1 == 0 || (part1 && slots1 > 0), "groupnorm_finalize_channels: c1 > 0 needs part1 / slots1");
   DL_CHECK_ARG((c0 + c1) % groups == 0, "groupnorm_finalize_channels: C=%d not divisible by groups=%d", c0 + c1, groups);
-  launch_pdl(gn_finalize_chan_kernel, dim3(nimg * groups), dim3(128), 0, reinterpret_cast<cudaStream_t>(stream_), part0,
-             slots0, c0, part1, c1 > 0 ? slots1 : 0, c1, groups, (double)count, stats);
+  gn_finalize_chan_kernel<<<nimg * groups, 128, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(
+      part0, slots0, c0, part1, c1 > 0 ? slots1 : 0, c1, groups, (double)count, stats);
   return check_launch("groupnorm_finalize_channels");
 }
 
@@ -817,7 +809,7 @@ extern "C" int dl_groupnorm_apply(const void* x0, int c0, const void* x1, int c1
   p.apply_silu = apply_silu;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.out_img_stride = out_img_stride > 0 ? out_img_stride : dense;
-  launch_pdl(gn_apply_kernel, dim3(p.slabs, nimg), dim3(GNX_THREADS), 0, reinterpret_cast<cudaStream_t>(stream_), p);
+  gn_apply_kernel<<<dim3(p.slabs, nimg), GNX_THREADS, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(p);
   return check_launch("groupnorm_apply");
 }
 
@@ -935,9 +927,8 @@ extern "C" int dl_layernorm(const void* x, long long rows, int c, float eps, con
   if (blocks > cap) blocks = cap;
   const __nv_bfloat16* xi = reinterpret_cast<const __nv_bfloat16*>(x);
   __nv_bfloat16* xo = reinterpret_cast<__nv_bfloat16*>(out);
-  const dim3 lg((unsigned)blocks), lb(wpb * 32);
-  if (c <= 512) launch_pdl(layernorm_kernel<2>, lg, lb, 0, stream, xi, (long long)rows, c, eps, gamma, beta, xo);
-  else if (c <= 768) launch_pdl(layernorm_kernel<3>, lg, lb, 0, stream, xi, (long long)rows, c, eps, gamma, beta, xo);
-  else launch_pdl(layernorm_kernel<5>, lg, lb, 0, stream, xi, (long long)rows, c, eps, gamma, beta, xo);
+  if (c <= 512) layernorm_kernel<2><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
+  else if (c <= 768) layernorm_kernel<3><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
+  else layernorm_kernel<5><<<(unsigned)blocks, wpb * 32, 0, stream>>>(xi, rows, c, eps, gamma, beta, xo);
   return check_launch("layernorm");
 }
