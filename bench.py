@@ -510,7 +510,18 @@ def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
     pe_d, lat_d, noise_d, pooled_d = (t.to(dev) for t in (pe, lat, noise, pooled))
     img_h = torch.empty(1, size, size, 3, dtype=torch.uint8).pin_memory()
     peer = os.environ.get("B200_C5_EXCHANGE", "peer") == "peer"
-    if world > 1:
+    group = args.c5_group if args.c5_group and args.c5_group < world else world
+    n_groups = world // group
+    if world > 1 and group != world:
+        # throughput layout: the ranks form n_groups independent groups, each sharding ITS OWN image (group = 2:
+        # the two CFG halves of one image per GPU pair, one noise-prediction exchange per step, no strips)
+        import torch.distributed as dist
+        if group != 2 or world % 2:
+            raise RuntimeError("--c5-group supports groups of 2 ranks (the CFG pair)")
+        groups = [dist.new_group(list(range(i * group, (i + 1) * group))) for i in range(n_groups)]
+        mine = groups[rank // group]
+        den = pp.PatchParallelDenoiser(pipe, pp.PeerComm(mine) if peer else pp.DistComm(mine))
+    elif world > 1:
         den = pp.dist_denoiser(pipe, peer=peer)
 
         def step(host: bool):
@@ -544,7 +555,7 @@ def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
     clocks = sampler.stop() if rank == 0 else None
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = max_over_ranks(sum(step_ms))
-    value = args.steps / (total_ms / 1e3)
+    value = n_groups * args.steps / (total_ms / 1e3)
     for _ in range(2):
         step(True)
     barrier()
@@ -554,7 +565,7 @@ def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
         step(True)
     e1.record()
     barrier()
-    e2e_v = args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+    e2e_v = n_groups * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
     # launches of one eager pass on this rank (the graph replays exactly these)
     n0 = lib.launch_count
     if world > 1:
@@ -569,9 +580,12 @@ def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
         print(json.dumps({
             "metric": c["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong" if n_groups == 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_text(c), "l2": "flushed between timed iterations", "cuda_graph": True,
+                       "images_in_flight": n_groups,
                        "parallelism": ("1 GPU" if world == 1 else
+                                       f"{n_groups} independent groups of {group} ranks, one image each (CFG halves on the "
+                                       f"two GPUs of a pair, one exchange per step)" if n_groups > 1 else
                                        f"CFG halves x row strips over {world} ranks, exchanges: "
                                        f"{'NVLink peer-memory kernels' if peer else 'ncclAllGather'}; VAE decode as row strips")},
             "ms_per_unet_step": total_ms / args.steps / nsteps,
@@ -634,6 +648,8 @@ def main():
     ap.add_argument("--lcm-steps", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pool-e2e", action="store_true", help="skip the WorkerPool/PNG leg (kernel work only)")
+    ap.add_argument("--c5-group", type=int, default=0,
+                    help="config c5: ranks per image (default: all ranks shard ONE image); 2 = one image per GPU pair")
     ap.add_argument("--pool-workers", type=int, default=0,
                     help="one process, WorkerPool with this many GPU workers; prints the e2e line only")
     args = ap.parse_args()
