@@ -9,6 +9,9 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 DEV = "cuda"
+# the torch references below (F.conv2d, matmul, SDPA in fp32) must be real fp32: no TF32 in cuDNN / cuBLAS
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def L():
