@@ -285,6 +285,8 @@ def run_b200(args, c):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    from dreamlab_b200 import lib as _lib
+    _lib.wait_for_driver()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
@@ -629,11 +631,14 @@ def run_b200_c5(args, c, rank, local, world, dev, barrier, max_over_ranks):
 # ------------------------------------------------------------------------------------------------
 def run_pool(args, c):
     import torch
+    from dreamlab_b200 import lib as _lib
+    _lib.wait_for_driver()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     import __graft_entry__ as g
     g.build()
     n = args.pool_workers
+    ngpu = min(n, torch.cuda.device_count())      # more workers than GPUs: worker k runs on cuda:(k % GPUs)
     os.environ["B200_PNG"] = os.environ.get("B200_PNG", "").strip().lower() or "gpu"
     root, name = bench_model_dir(c, 0, lambda: None)
     pool = make_pool(c, root, name, n)
@@ -643,11 +648,11 @@ def run_pool(args, c):
     pool.shutdown()
     v = n_req / dt
     print(json.dumps({
-        "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": 2,
+        "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": 2,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_text(c), "parallelism": f"ONE process, WorkerPool with {n} B200Worker threads "
-                   f"(worker k on cuda:k), shared FIFO, micro-batches of {B}, PNG on encoder threads / GPU",
+                   f"on {ngpu} GPU(s) (worker k on cuda:(k % GPUs)), shared FIFO, micro-batches of {B}, PNG on encoder threads / GPU",
                    "png": os.environ.get("B200_PNG", "pil"), "host_cores": os.cpu_count()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": n * (B * 77 * 768 * 4 + B * 4),
                 "d2h_bytes_per_step": n * B * c["size"] * c["size"] * 3, "png_bytes_mean": png_bytes,

@@ -162,6 +162,14 @@ int dl_attention(const void* q, long long ldq, const void* k, long long ldk, con
                  long long ldv, int dh_stride, void* out, long long ldo, int batch, int sq,
                  int skv, int heads, int d, float scale, int impl, int v_ones, void* stream);
 
+/* Wide-head flash attention (one head, head dim d a multiple of 128 up to 512): the AutoencoderKL mid-block
+ * attention (diffusers UNetMidBlock2D -> Attention, reached from reference `backends/rknnlcm.py:618` vae.decode and
+ * `backends/cuda_worker.py` pipe.vae).  The head dim is split over two CTAs per query tile (a 128 x 512 fp32 output is
+ * all of TMEM); nothing of size sq x skv touches HBM.  q/k/v/out bf16 rows; sq % 128 == 0, skv % 64 == 0.      */
+int dl_attention_wide(const void* q, long long ldq, const void* k, long long ldk, const void* v,
+                      long long ldv, void* out, long long ldo, int batch, int sq, int skv, int d,
+                      float scale, void* stream);
+
 /* debug aid: CTA (0,0,0) of the tcgen05 attention kernel writes per-tile clock stamps of its MMA
  * and softmax warps into this device buffer of 256 int64 (NULL switches tracing off).          */
 int dl_debug_attention_trace(void* device_buf_i64_256);

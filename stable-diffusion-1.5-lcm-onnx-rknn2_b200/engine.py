@@ -488,14 +488,21 @@ class VAEDecoderB200:
         self.fuse_gn_stats = os.environ.get("DL_VAE_GN_FUSE", "1") not in ("0", "false")
         self.conv_out_tapsum = (os.environ.get("DL_VAE_CONV_OUT_TAPSUM", "1") not in ("0", "false")
                                 and self.dt == BF16 and self.P["conv_out_w"].shape[0] == 3)
+        # flash attention for the mid block (csrc/attention_wide.cu); DL_VAE_FLASH=0 keeps the unfused GEMM form
+        self.flash_attention = os.environ.get("DL_VAE_FLASH", "1") not in ("0", "false") and self.dt == BF16
         if self.conv_out_tapsum:
             # conv_out weights regrouped tap-major for the 1x1-GEMM + tap-sum form: row t*3 + oc = w[oc, tap t, :]
             cl = self.P["conv_out_w"].shape[1] // 9
             w27 = self.P["conv_out_w"].view(3, 9, cl).permute(1, 0, 2).reshape(27, cl)
             self.P["conv_out_w27"] = torch.cat([w27, w27.new_zeros(5, cl)], 0).contiguous()
 
+    def _flash_ok(self, sq, skv, C):
+        return self.flash_attention and sq % 128 == 0 and skv % 64 == 0 and C % 128 == 0 and C <= 512
+
     def _mid_attention(self, ctx, x, a: Packed):
-        """heads=1, d=C (512): QK^T and PV through the tcgen05 GEMM, fp32 scores, per image."""
+        """heads=1, d=C (512).  Token counts the wide flash kernel tiles (multiples of 128: every full decode) go
+        through it; otherwise QK^T and PV through the tcgen05 GEMM with fp32 scores per image, or the CUDA-core
+        flash kernel for ragged tiles."""
         B, H, W, C = x.shape
         S = H * W
         hn = groupnorm(ctx, x, a["norm_w"], a["norm_b"], eps=1e-6, silu=False, groups=self.groups)
@@ -504,6 +511,13 @@ class VAEDecoderB200:
             return self._mid_attention_strips(ctx, x, hn2, a)
         qk = linear(ctx, hn2, a["qk_w"], a["qk_b"], 2 * C)                 # [B*S, 2C]
         o = ctx.empty(B * S, C)
+        if self._flash_ok(S, S, C):
+            # b_v is folded into the out-proj bias (softmax rows sum to 1), as in the other branches
+            v = linear(ctx, hn2, a["v_w"], None, C)
+            lib.attention_wide(qk, qk[:, C:], v, o, batch=B, sq=S, skv=S, d=C, ldq=2 * C, ldk=2 * C, ldv=C, ldo=C,
+                               scale=1.0 / math.sqrt(C))
+            out = linear(ctx, o, a["o_w"], a["o_b"], C, residual=x.view(B * S, C), norm_rows_per_img=S)
+            return _carry_gn(out, out.view(B, H, W, C))
         if S % 64 or self.dt != BF16:
             # fp32 precision mode, and ragged tiles of a tiled decode (token count not a multiple of the 64-deep GEMM K
             # chunk, e.g. a 29 x 29 corner tile): the CUDA-core flash kernel takes any length.
@@ -543,7 +557,10 @@ class VAEDecoderB200:
         q = linear(ctx, hn2, a["qk_w"][:C], a["qk_b"][:C], C)               # [B*S, C]
         k = linear(ctx, hn_all, a["qk_w"][C:], a["qk_b"][C:], C)            # [B*Sa, C]
         o = ctx.empty(B * S, C)
-        if Sa % 64:                       # ragged key count: the CUDA-core flash kernel takes any length
+        if self._flash_ok(S, Sa, C):
+            v = linear(ctx, hn_all, a["v_w"], None, C)
+            lib.attention_wide(q, k, v, o, batch=B, sq=S, skv=Sa, d=C, ldq=C, ldk=C, ldv=C, ldo=C, scale=scale)
+        elif Sa % 64:                     # ragged key count: the CUDA-core flash kernel takes any length
             v = linear(ctx, hn_all, a["v_w"], None, C)
             lib.attention(q, k, v, o, batch=B, sq=S, skv=Sa, heads=1, d=C, dh_stride=C,
                           ldq=C, ldk=C, ldv=C, ldo=C, scale=scale, impl=lib.ATTN_SIMT)

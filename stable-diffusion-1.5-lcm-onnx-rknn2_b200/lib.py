@@ -19,7 +19,7 @@ ATTN_TC, ATTN_SIMT, ATTN_SIMT_CAUSAL = 0, 1, 2
 
 EXPORTS = [
     "dl_abi_version", "dl_last_error", "dl_device_sm_count", "dl_igemm", "dl_igemm_plan_bn", "dl_fill_identity",
-    "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention",
+    "dl_groupnorm_workspace_bytes", "dl_groupnorm", "dl_layernorm", "dl_attention", "dl_attention_wide",
     "dl_debug_attention_trace",
     "dl_timestep_sinusoid", "dl_small_linear", "dl_upsample2x", "dl_im2col_s2", "dl_pack_latent",
     "dl_nchw_to_nhwc_f32", "dl_nhwc_to_nchw_f32", "dl_lcm_step", "dl_latent_pool8", "dl_softmax_rows",
@@ -101,6 +101,9 @@ def load() -> C.CDLL:
                                               C.c_int, C.c_void_p, C.c_void_p]
             lib.dl_layernorm.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dl_attention_wide.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p,
+                                              C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_float, C.c_void_p]
             lib.dl_attention.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
                                          C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong,
                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -254,7 +257,30 @@ class _timed:
         return False
 
 
+def wait_for_driver(timeout_s: float = 20.0) -> None:
+    """On a box without persistence mode the driver tears the GPU down when its last client exits; a process that
+    starts inside that window gets a failing cuInit ("CUDA driver initialization failed"), and torch caches the
+    resulting device count of 0 for the life of the process.  So before torch first touches CUDA: when a GPU device
+    node exists, retry cuInit through the driver API until it succeeds (or the timeout passes; the caller's own
+    check then fails loudly).  No GPU node (the CPU-only build container): returns at once."""
+    import glob
+    import time
+    if not glob.glob("/dev/nvidia[0-9]*"):
+        return
+    try:
+        cu = C.CDLL("libcuda.so.1")
+    except OSError:
+        return
+    t0 = time.monotonic()
+    while True:
+        rc = cu.cuInit(0)
+        if rc == 0 or rc == 100 or time.monotonic() - t0 > timeout_s:     # 100: CUDA_ERROR_NO_DEVICE
+            return
+        time.sleep(0.5)
+
+
 def require_cuda():
+    wait_for_driver()
     if not torch.cuda.is_available():
         raise RuntimeError("dreamlab_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
 
@@ -423,6 +449,15 @@ def attention(q, k, v, out, *, batch, sq, skv, heads, d, dh_stride, ldq, ldk, ld
         _check(load().dl_attention(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, dh_stride,
                                    out.data_ptr(), ldo, batch, sq, skv, heads, d, scale, impl,
                                    int(v_ones), _stream()), "attention")
+    _count()
+
+
+def attention_wide(q, k, v, out, *, batch, sq, skv, d, ldq, ldk, ldv, ldo, scale):
+    """One-head flash attention for head dims up to 512 (the VAE mid block); bf16 only."""
+    with _timed("attention_wide", 4.0 * batch * sq * skv * d,
+                tag=f"B={batch} Sq={sq} Skv={skv} d={d}"):
+        _check(load().dl_attention_wide(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo,
+                                        batch, sq, skv, d, scale, _stream()), "attention_wide")
     _count()
 
 

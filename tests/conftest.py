@@ -12,8 +12,27 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
 
 
+def _wait_for_driver(timeout_s=20.0):
+    """A process started while the driver is still tearing the GPU down after the previous one (no persistence mode)
+    gets a failing cuInit, torch caches "no device" and every gpu test would be SKIPPED silently: retry cuInit first
+    when a GPU device node exists (same helper as dreamlab_b200.lib.wait_for_driver, kept import-free here)."""
+    import ctypes
+    import glob
+    import time
+    if not glob.glob("/dev/nvidia[0-9]*"):
+        return
+    try:
+        cu = ctypes.CDLL("libcuda.so.1")
+    except OSError:
+        return
+    t0 = time.monotonic()
+    while cu.cuInit(0) not in (0, 100) and time.monotonic() - t0 < timeout_s:
+        time.sleep(0.5)
+
+
 def pytest_collection_modifyitems(config, items):
     import torch
+    _wait_for_driver()
     if torch.cuda.is_available():
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")

@@ -67,3 +67,15 @@ def test_product_never_imports_oracle():
                 if f.endswith(".py"):
                     txt = open(os.path.join(dp, f)).read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_wait_for_driver_returns_at_once_without_a_gpu_node(monkeypatch):
+    """lib.wait_for_driver() only retries cuInit when a GPU device node exists; in the CPU container it must not
+    delay the loud 'no CUDA device' failure of the product path."""
+    import glob
+    import time
+    from dreamlab_b200 import lib
+    monkeypatch.setattr(glob, "glob", lambda pat: [])
+    t0 = time.monotonic()
+    lib.wait_for_driver(timeout_s=30.0)
+    assert time.monotonic() - t0 < 1.0

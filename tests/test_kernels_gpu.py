@@ -301,6 +301,34 @@ def _attention_pp_case(B, Sq, Skv, heads, d, poly):
         assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("B,Sq,Skv,d", [
+    (2, 1024, 1024, 512), (1, 4096, 4096, 512), (1, 256, 448, 256), (3, 128, 64, 128), (1, 512, 2048, 384),
+])
+@pytest.mark.parametrize("qscale", [1.0, 5.0])
+def test_attention_wide_vae_head(B, Sq, Skv, d, qscale):
+    """attention_wide.cu (one head, head dim up to 512, the output columns split over two CTAs per query tile)
+    against an fp32 softmax(QK^T / sqrt(d)) V of the same bf16 inputs; q and k are read out of one fused [.., 2d]
+    projection buffer as the VAE mid block passes them; peaked rows exercise the running-max rescale of O."""
+    lib = L()
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + Sq + d)
+    qk = (torch.randn(B * max(Sq, Skv), 2 * d, device="cuda", generator=g) * qscale).to(torch.bfloat16)
+    v = torch.randn(B * Skv, d, device="cuda", generator=g).to(torch.bfloat16)
+    q = qk[:B * Sq, :d]
+    k = qk[:B * Skv, d:]
+    out = torch.full((B * Sq, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(d)
+    lib.attention_wide(q, k, v, out, batch=B, sq=Sq, skv=Skv, d=d, ldq=2 * d, ldk=2 * d, ldv=d, ldo=d, scale=scale)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Sq, d)
+    kf = k.float().reshape(B, Skv, d)
+    vf = v.float().reshape(B, Skv, d)
+    ref = torch.softmax(qf @ kf.transpose(1, 2) * scale, dim=-1) @ vf
+    got = out.float().reshape(B, Sq, d)
+    assert torch.isfinite(got).all()
+    e = ((got - ref).norm() / ref.norm()).item()
+    assert e < 2e-2, f"rel err {e}"
+
+
 # ------------------------------------------------------------------ elementwise / scheduler
 def test_upsample_im2col_pack():
     lib = L()
