@@ -469,8 +469,9 @@ def run_b200(args, c):
                # per step (= one batch of B requests): the prompt conditioning enters from the host
                # (77 x 768 fp32 per request), latents / step noise are drawn on the device from the request's
                # seed exactly as the reference's CUDA worker does (`cuda_worker.py:212-213`); u8 images leave
-               "h2d_bytes_per_step": B * 77 * D * 4 + B * 4,
-               "d2h_bytes_per_step": B * size * size * 3,
+               # ... both counted over all ranks, like `value`
+               "h2d_bytes_per_step": world * (B * 77 * D * 4 + B * 4),
+               "d2h_bytes_per_step": world * B * size * size * 3,
                "path": "GenerationJob -> WorkerPool.submit_job -> B200Worker.run_batch -> PNG bytes",
                "png": png_mode, "png_bytes_mean": png_bytes,
                "requests": n_req * world, "timed": "wall clock, first submit to last PNG, max over ranks",
@@ -500,10 +501,11 @@ def run_b200(args, c):
                        "cuda_graph": True, "parallelism": f"replicas x{world} (no collective)"},
             "p50_latency_ms_per_batch": statistics.median(step_ms),
             "p50_latency_ms_single_image": lat_b1,
-            "e2e": e2e if e2e is not None else {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": h2d_engine,
-                                                "d2h_bytes_per_step": img_h.numel(), "path": "engine (pool e2e skipped)"},
-            "e2e_engine": {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": h2d_engine,
-                           "d2h_bytes_per_step": img_h.numel(),
+            "e2e": e2e if e2e is not None else {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": world * h2d_engine,
+                                                "d2h_bytes_per_step": world * img_h.numel(),
+                                                "path": "engine (pool e2e skipped)"},
+            "e2e_engine": {"value": e2e_engine, "unit": UNIT, "h2d_bytes_per_step": world * h2d_engine,
+                           "d2h_bytes_per_step": world * img_h.numel(),
                            "path": "pinned host tensors -> LCMPipelineB200.generate (CUDA graph) -> pinned host u8"},
             "gpu_launches": launches_per_step * args.steps * world,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
