@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import io
 import json
+import collections
 import os
 from typing import List, Sequence, Tuple
 
@@ -305,27 +306,47 @@ class B200Worker(PipelineWorker):
                 pooled = torch.empty(len(jobs), 4, 8, 8, device=self.device, dtype=torch.float16)
                 lib.latent_pool8(final, pooled)
                 pooled = pooled.cpu().numpy()
-            png_files, png_size = None, 0
-            if not raw and _png_mode() == "gpu":
+            png_size = 0
+            gpu_png = not raw and _png_mode() == "gpu"
+            if gpu_png:
                 # the finished PNG files come off the device (csrc/png.cu): no zlib on the host
                 png_dev, png_size = lib.png_stored(img.contiguous())
-                png_files = _to_host(png_dev)
+                host, done = _to_host_async(png_dev)
             else:
-                img = _to_host(img)
+                host, done = _to_host_async(img)
+            self._admit(done)
 
         def finish(i):
+            done.synchronize()                      # this batch's GPU work and its copy to `host` have finished
             seed = parsed[i][2]
+            arr = host.numpy()
             if raw:
-                return (img[i], seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (img[i], seed)
-            png = png_files[i, :png_size].tobytes() if png_files is not None else _encode_png(img[i])
+                return (arr[i], seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (arr[i], seed)
+            png = arr[i, :png_size].tobytes() if gpu_png else _encode_png(arr[i])
             return (png, seed, pooled[i:i + 1].tobytes(order="C")) if with_latents else (png, seed)
 
         if deferred:
-            import functools
-            return [functools.partial(finish, i) for i in range(len(jobs))]
+            return [_Deferred(finish, i, done) for i in range(len(jobs))]
         if len(jobs) == 1:
             return [finish(0)]
         return list(_encoders().map(finish, range(len(jobs))))      # PIL releases the GIL in zlib
+
+    def _admit(self, done) -> None:
+        """Bound how far this thread runs ahead of the GPU: with `deferred=True` run_batch returns as soon as a
+        batch is enqueued, and the host work of batch k+1 (request parsing, token ids, draws, launches) overlaps
+        batch k on the device.  At most B200_BATCHES_IN_FLIGHT (default 2) batches are outstanding — their pinned
+        result buffers are what would pile up otherwise."""
+        q = self.__dict__.setdefault("_in_flight", collections.deque())
+        q.append(done)
+        limit = max(1, int(os.environ.get("B200_BATCHES_IN_FLIGHT", "2")))
+        while len(q) > limit:
+            q.popleft().synchronize()
+
+    def drain(self) -> None:
+        """Wait for every batch this worker has enqueued (the pool calls it before it drops a worker)."""
+        q = self.__dict__.get("_in_flight")
+        while q:
+            q.popleft().synchronize()
 
     def run_job(self, job) -> Tuple[bytes, int]:
         return self.run_batch([job])[0]
@@ -387,14 +408,33 @@ def _encoders():
     return _ENCODERS
 
 
-def _to_host(t: torch.Tensor):
-    """Device tensor -> numpy through a PINNED staging tensor (torch's caching host allocator recycles the
-    blocks): a pageable `.cpu()` of a 12.6 MB batch runs at a fraction of the link rate.  The array keeps its
-    pinned tensor alive until the last PNG thunk that reads it is done."""
+class _Deferred:
+    """One request's result, still on its way: `()` -> the result tuple (blocks until the batch's GPU work is done,
+    then encodes / slices this request's bytes); `wait()` only blocks — the pool parks ONE waiter per batch on it and
+    fans the per-request calls out to the encoder threads afterwards, instead of blocking a thread per request."""
+    __slots__ = ("_finish", "_i", "_done")
+
+    def __init__(self, finish, i, done):
+        self._finish, self._i, self._done = finish, i, done
+
+    def wait(self):
+        self._done.synchronize()
+
+    def __call__(self):
+        return self._finish(self._i)
+
+
+def _to_host_async(t: torch.Tensor):
+    """Device tensor -> (pinned host tensor, CUDA event): the copy is only ENQUEUED behind the work that produces
+    `t`; whoever reads the host tensor waits on the event first (the PNG thunks do, on the encoder threads), so the
+    worker's thread is free to enqueue the next batch while this one is still on the GPU.  Pinned staging: torch's
+    caching host allocator recycles the blocks, and a pageable `.cpu()` of a 12.6 MB batch runs at a fraction of the
+    link rate.  The thunks keep the pinned tensor alive until the last one that reads it is done."""
     host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     host.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    return host.numpy()
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(t.device))
+    return host, ev
 
 
 def _png_mode() -> str:
@@ -470,12 +510,14 @@ def _side_tokenizer(checkpoint_path: str, name: str):
 def _hash_tokens(prompts: List[str], eos: int = 49407, bos: int = 49406) -> torch.Tensor:
     """Deterministic stand-in token ids when the model dir ships no tokenizer files (offline
     fixtures): good for synthetic load, meaningless for real prompts."""
-    ids = torch.full((len(prompts), 77), eos, dtype=torch.long)
+    import numpy as np
+    ids = np.full((len(prompts), 77), eos, dtype=np.int64)
+    ids[:, 0] = bos
+    j = np.arange(75, dtype=np.int64)
     for i, p in enumerate(prompts):
-        ids[i, 0] = bos
-        for j, b in enumerate(p.encode("utf-8")[:75]):
-            ids[i, 1 + j] = (b * 193 + j * 7919) % bos
-    return ids
+        b = np.frombuffer(p.encode("utf-8")[:75], dtype=np.uint8).astype(np.int64)
+        ids[i, 1:1 + b.size] = (b * 193 + j[:b.size] * 7919) % bos
+    return torch.from_numpy(ids)
 
 
 def _seeded_embeds(prompts: List[str], dims, device):
@@ -519,7 +561,7 @@ class _TextEncoder:
                                  return_tensors="pt").input_ids
         else:
             ids = _hash_tokens(prompts)
-        return self.model.forward(ids)["last_hidden_state"].float()
+        return self.model.forward_graphed(ids)["last_hidden_state"].float()
 
 
 class _SDXLTextEncoder:
@@ -562,7 +604,7 @@ class _SDXLTextEncoder:
                           return_tensors="pt").input_ids
             else:
                 ids = _hash_tokens(prompts, eos=m.cfg.vocab_size - 1, bos=m.cfg.vocab_size - 2)
-            out = m.forward(ids, want_hidden=-2)
+            out = m.forward_graphed(ids, want_hidden=-2)
             hs.append(out["hidden"].float())
             pooled = out.get("text_embeds", out["pooler_output"]).float()   # the last tower's pooled embedding
         return torch.cat(hs, -1), pooled

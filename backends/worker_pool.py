@@ -236,6 +236,14 @@ class WorkerPool:
             return
         if self._current_mode:
             self._registry.unregister_model(self._current_mode)
+        for w in self._workers:
+            # a worker that returns from run_batch(deferred=True) before its GPU work is done finishes it first
+            drain = getattr(type(w), "drain", None)
+            if callable(drain):
+                try:
+                    drain(w)
+                except Exception as e:                       # noqa: BLE001 - unloading must go on
+                    logger.warning("[WorkerPool] drain failed: %s", e)
         self._workers = []
         import gc
         gc.collect()
@@ -286,9 +294,12 @@ class WorkerPool:
                 # GPU pass here, PNG encoding on the encoder threads: this thread moves on to the
                 # next batch while the images of this one are still being compressed
                 thunks = worker.run_batch(batch, deferred=True)
-                from backends.b200_worker import _encoders
-                for j, th in zip(batch, thunks):
-                    _encoders().submit(_resolve, j, th)
+                if callable(getattr(thunks[0], "wait", None)):
+                    # the batch is only enqueued on the GPU: one waiter thread sleeps on it, this thread goes on
+                    # to the next batch (whose host work then overlaps this one's kernels)
+                    _waiters().submit(_resolve_batch, batch, thunks)
+                else:
+                    _resolve_batch(batch, thunks)
             elif len(batch) > 1:
                 results = worker.run_batch(batch)
                 for j, r in zip(batch, results):
@@ -377,6 +388,39 @@ class WorkerPool:
             if t.is_alive():
                 t.join(timeout=5.0)
         self._unload_current_worker()
+
+
+_WAITERS = None
+_WAITERS_LOCK = threading.Lock()
+
+
+def _waiters():
+    """Threads that sleep until a batch's GPU work is done (one per batch in flight; they hold no GIL while waiting)."""
+    global _WAITERS
+    with _WAITERS_LOCK:
+        if _WAITERS is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _WAITERS = ThreadPoolExecutor(max_workers=int(os.environ.get("B200_WAITER_THREADS", "32")),
+                                          thread_name_prefix="batch-wait")
+        return _WAITERS
+
+
+def _resolve_batch(batch, thunks):
+    """Waits for the batch (when its results are deferred past the GPU work), then hands one task per request to
+    the encoder threads."""
+    from backends.b200_worker import _encoders
+    try:
+        wait = getattr(thunks[0], "wait", None)
+        if callable(wait):
+            wait()
+    except Exception as e:                                  # noqa: BLE001 - forwarded to the callers
+        logger.error("[WorkerPool] Batch failed on the device: %s", e, exc_info=True)
+        for j in batch:
+            if not j.fut.done():
+                j.fut.set_exception(e)
+        return
+    for j, th in zip(batch, thunks):
+        _encoders().submit(_resolve, j, th)
 
 
 def _resolve(job, thunk):

@@ -235,6 +235,7 @@ def bench_model_dir(c, rank, barrier):
     if rank == 0 and not os.path.exists(done):
         if c["arch"] == "sd15":
             syn.write_model_dir(path)
+            syn.write_text_encoder(path)        # CLIP ViT-L/14 text tower (random init): prompts go through it on the device
         else:
             syn.write_model_dir(path, syn.sdxl_unet_cfg(), syn.sdxl_vae_cfg())
         open(done, "w").close()
@@ -464,15 +465,16 @@ def run_b200(args, c):
                        "note": "same pool, the reference's img.save(buf, format='PNG') on the host encoder threads"}
             os.environ["B200_PNG"] = png_mode
         pool.shutdown()
-        D = 768
         e2e = {"value": world * n_req / dt, "unit": UNIT,
-               # per step (= one batch of B requests): the prompt conditioning enters from the host
-               # (77 x 768 fp32 per request), latents / step noise are drawn on the device from the request's
-               # seed exactly as the reference's CUDA worker does (`cuda_worker.py:212-213`); u8 images leave
-               # ... both counted over all ranks, like `value`
-               "h2d_bytes_per_step": world * (B * 77 * D * 4 + B * 4),
+               # per step (= one batch of B requests) over all ranks, like `value`: what enters from the host is the
+               # request itself — 77 int64 token ids per prompt (hashed stand-in ids: no vocabulary offline) and the
+               # seed; the CLIP text tower runs on the device, latents / step noise are drawn on the device from the
+               # request's seed exactly as the reference's CUDA worker does (`cuda_worker.py:212-213`); what leaves is
+               # the PNG file (device-side writer) or the u8 image (PIL encoder threads)
+               "h2d_bytes_per_step": world * (B * 77 * 8 + B * 8),
                "d2h_bytes_per_step": world * B * size * size * 3,
-               "path": "GenerationJob -> WorkerPool.submit_job -> B200Worker.run_batch -> PNG bytes",
+               "path": "GenerationJob(prompt, seed) -> WorkerPool.submit_job -> B200Worker.run_batch (token ids -> CLIP-L "
+                       "text tower on the device -> LCM loop -> VAE) -> PNG bytes",
                "png": png_mode, "png_bytes_mean": png_bytes,
                "requests": n_req * world, "timed": "wall clock, first submit to last PNG, max over ranks",
                "host_cores": os.cpu_count()}
@@ -656,9 +658,10 @@ def run_pool(args, c):
         "config": {"workload": workload_text(c), "parallelism": f"ONE process, WorkerPool with {n} B200Worker threads "
                    f"on {ngpu} GPU(s) (worker k on cuda:(k % GPUs)), shared FIFO, micro-batches of {B}, PNG on encoder threads / GPU",
                    "png": os.environ.get("B200_PNG", "pil"), "host_cores": os.cpu_count()},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": n * (B * 77 * 768 * 4 + B * 4),
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": n * (B * 77 * 8 + B * 8),
                 "d2h_bytes_per_step": n * B * c["size"] * c["size"] * 3, "png_bytes_mean": png_bytes,
-                "path": "GenerationJob -> WorkerPool.submit_job -> B200Worker.run_batch -> PNG bytes",
+                "path": "GenerationJob(prompt, seed) -> WorkerPool.submit_job -> B200Worker.run_batch (token ids -> "
+                        "CLIP-L text tower on the device -> LCM loop -> VAE) -> PNG bytes",
                 "requests": n_req, "timed": "wall clock, first submit to last PNG"},
         "gpu_launches": None,
     }))

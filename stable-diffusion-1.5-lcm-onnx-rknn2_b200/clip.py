@@ -15,6 +15,7 @@ the residual on the tensor core), `dl_attention` (causal CUDA-core flash kernel:
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -66,8 +67,45 @@ class CLIPTextB200:
             L["fc1_w"], L["fc1_b"] = _bf(sd[b + "mlp.fc1.weight"], dev), _f32(sd[b + "mlp.fc1.bias"], dev)
             L["fc2_w"], L["fc2_b"] = _bf(sd[b + "mlp.fc2.weight"], dev), _f32(sd[b + "mlp.fc2.bias"], dev)
             self.layers.append(L)
+        self._graphs = {}
         self.fln_w, self.fln_b = _f32(sd[p + "final_layer_norm.weight"], dev), _f32(sd[p + "final_layer_norm.bias"], dev)
         self.proj = _bf(sd["text_projection.weight"], dev) if "text_projection.weight" in sd else None
+
+    GRAPH_BUCKETS = (1, 2, 4, 8, 16, 32)
+
+    @torch.no_grad()
+    def forward_graphed(self, input_ids: torch.Tensor, want_hidden: Optional[int] = None):
+        """forward() as ONE CUDA-graph replay per (batch bucket, T, want_hidden): the tower is ~150 small launches,
+        5-6 ms of interpreter time per batch in front of a 118 ms UNet/VAE replay when issued eagerly.  The batch is
+        padded to its bucket (the pad rows keep whatever ids the buffer held); batches beyond the largest bucket,
+        or B200_CLIP_GRAPH=0, run eagerly.  The returned tensors are views of the graph's STATIC outputs: convert
+        or copy them before the next call (the workers' `.float()` does)."""
+        B, T = input_ids.shape
+        bucket = next((b for b in self.GRAPH_BUCKETS if b >= B), None)
+        if bucket is None or os.environ.get("B200_CLIP_GRAPH", "1") in ("0", "false"):
+            return self.forward(input_ids, want_hidden)
+        key = (bucket, T, want_hidden)
+        g = self._graphs.get(key)
+        with torch.cuda.device(self.device):
+            if g is None:
+                from .engine import CAPTURE_LOCK
+                ids = torch.zeros(bucket, T, device=self.device, dtype=torch.int64)
+                ids[:B].copy_(input_ids)
+                with CAPTURE_LOCK:
+                    s = torch.cuda.Stream(device=self.device)
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(s):
+                        self.forward(ids, want_hidden)                     # warm-up: lazy per-device init
+                    torch.cuda.current_stream(self.device).wait_stream(s)
+                    torch.cuda.synchronize(self.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=s, capture_error_mode="thread_local"):
+                        out = self.forward(ids, want_hidden)
+                g = self._graphs[key] = (graph, ids, out)
+            graph, ids, out = g
+            ids[:B].copy_(input_ids)
+            graph.replay()
+            return {k: v[:B] for k, v in out.items()}
 
     def _lin(self, x, w, b, n, residual=None):
         M = x.shape[0]

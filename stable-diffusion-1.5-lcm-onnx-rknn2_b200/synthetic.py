@@ -197,6 +197,51 @@ def synthetic_inputs(batch: int, height: int, width: int, steps: int, ctx_dim: i
     return pe, torch.cat(lat, 0), torch.cat(noise, 1)
 
 
+def clip_text_shapes(hidden: int = 768, layers: int = 12, inter: int = 3072, vocab: int = 49408,
+                     positions: int = 77) -> Dict[str, Tuple[int, ...]]:
+    """State-dict layout of transformers' CLIPTextModel (defaults: CLIP ViT-L/14's text tower, 123 M parameters)."""
+    s: Dict[str, Tuple[int, ...]] = {}
+    p = "text_model."
+    s[p + "embeddings.token_embedding.weight"] = (vocab, hidden)
+    s[p + "embeddings.position_embedding.weight"] = (positions, hidden)
+    for i in range(layers):
+        b = f"{p}encoder.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            s[b + f"self_attn.{n}.weight"] = (hidden, hidden)
+            s[b + f"self_attn.{n}.bias"] = (hidden,)
+        for n in ("layer_norm1", "layer_norm2"):
+            s[b + n + ".weight"] = (hidden,)
+            s[b + n + ".bias"] = (hidden,)
+        s[b + "mlp.fc1.weight"] = (inter, hidden)
+        s[b + "mlp.fc1.bias"] = (inter,)
+        s[b + "mlp.fc2.weight"] = (hidden, inter)
+        s[b + "mlp.fc2.bias"] = (hidden,)
+    s[p + "final_layer_norm.weight"] = (hidden,)
+    s[p + "final_layer_norm.bias"] = (hidden,)
+    return s
+
+
+def write_text_encoder(model_dir: str, hidden: int = 768, layers: int = 12, heads: int = 12, inter: int = 3072,
+                       seed: int = 2, dtype=torch.float16) -> None:
+    """`text_encoder/` (transformers layout, random init) under a model dir written by write_model_dir: with it the
+    worker runs the prompt through the on-device CLIP tower, as a real checkpoint would.  No tokenizer files are
+    written (there is no vocabulary offline): the worker falls back to its hashed stand-in token ids."""
+    from safetensors.torch import save_file
+    te = os.path.join(model_dir, "text_encoder")
+    os.makedirs(te, exist_ok=True)
+    with open(os.path.join(te, "config.json"), "w") as f:
+        json.dump({"_class_name": "CLIPTextModel", "architectures": ["CLIPTextModel"], "model_type": "clip_text_model",
+                   "vocab_size": 49408, "hidden_size": hidden, "intermediate_size": inter, "num_hidden_layers": layers,
+                   "num_attention_heads": heads, "max_position_embeddings": 77, "hidden_act": "quick_gelu",
+                   "layer_norm_eps": 1e-5, "eos_token_id": 49407, "bos_token_id": 49406, "pad_token_id": 1}, f)
+    sd = random_state_dict(clip_text_shapes(hidden, layers, inter), seed, dtype)
+    # embeddings at the scale of a trained tower (transformers initialises them N(0, 0.02))
+    for k in list(sd):
+        if "embedding" in k:
+            sd[k] = (sd[k].float() * (0.02 * (3.0 * sd[k].shape[1]) ** 0.5)).to(dtype)
+    save_file(sd, os.path.join(te, "model.safetensors"))
+
+
 def write_model_dir(path: str, unet_cfg=None, vae_cfg=None, seed: int = 0, dtype=torch.float16):
     """A diffusers-layout directory (model_index.json, unet/, vae/) with random-init weights —
     what `MODEL_ROOT/MODEL` points at for offline tests of the b200 worker."""

@@ -208,6 +208,15 @@ def test_worker_runs_its_text_tower_on_the_device(tmp_path):
         ref = clip(_hash_tokens(prompts)).last_hidden_state
     err = ((got - ref).abs().max() / ref.abs().max()).item()
     assert err <= 2e-2, err
+    # the tower runs as one CUDA-graph replay per batch bucket (static ids in, static states out): a second call
+    # through the same graph, a padded bucket (3 prompts in the 4-bucket) and the eager path all agree
+    assert len(w._text.model._graphs) == 1
+    three = ["x", prompts[1], "third prompt"]
+    g3 = w._text.encode(three).cpu()
+    assert torch.equal(w._text.encode(prompts).cpu(), got) and len(w._text.model._graphs) == 2
+    eager = w._text.model.forward(_hash_tokens(three))["last_hidden_state"].float().cpu()
+    assert torch.equal(g3, eager)
+    assert torch.equal(g3[1], got[1])                                  # a prompt's embedding does not depend on its batch
     a, b = w.run_job(job(prompt=prompts[0], seed=3)), w.run_job(job(prompt=prompts[1], seed=3))
     assert a[0][:4] == b"\x89PNG" and a[0] != b[0]                   # the prompt conditions the image
     assert w.run_job(job(prompt=prompts[0], seed=3))[0] == a[0]
@@ -319,3 +328,23 @@ def test_latent_only_jobs_match_the_image_pass(worker):
     assert [s for _, s in many] == [300, 301, 302, 303, 304] and all(a.shape == (4, 8, 8) for a, _ in many)
     solo, _ = worker.run_job_latents(job(prompt="c2", seed=302, size="64x64", steps=1))
     assert np.abs(solo - many[2][0]).max() <= 2e-2 * np.abs(solo).max()
+
+
+@pytest.mark.parametrize("png", ["pil", "gpu"])
+def test_deferred_batches_overlap_and_match_the_synchronous_results(worker, png, monkeypatch):
+    """run_batch(deferred=True) returns while the batch is still on the GPU (the result copy is only enqueued; each
+    thunk waits on the batch's event): four batches are enqueued back to back — at most B200_BATCHES_IN_FLIGHT
+    outstanding — and resolved afterwards in reverse order; every result equals the synchronous run_batch of the same
+    jobs (static graph buffers, pinned staging and PNG buffers of neighbouring batches do not alias)."""
+    monkeypatch.setenv("B200_PNG", png)
+    batches = [[job(prompt=f"p{b}-{i}", seed=100 * b + i) for i in range(3 + b % 2)] for b in range(4)]
+    ref = [worker.run_batch(bt) for bt in batches]
+    pending = [worker.run_batch(bt, deferred=True) for bt in batches]
+    assert len(worker._in_flight) <= 2
+    assert all(callable(getattr(t, "wait", None)) for th in pending for t in th)
+    got = [None] * len(batches)
+    for b in reversed(range(len(batches))):
+        got[b] = [t() for t in pending[b]]
+    assert got == ref
+    worker.drain()
+    assert len(worker._in_flight) == 0

@@ -53,3 +53,35 @@ def test_write_model_dir_roundtrip(tmp_path):
     assert set(sd) == set(S.unet_shapes(cfg))
     vj, vsd = _load_component(p + "/vae")
     assert vae_cfg_from_json(vj).sample_size == 128 and set(vsd) == set(S.vae_decoder_shapes(VAEConfig.tiny()))
+
+
+def test_synthetic_text_encoder_has_the_transformers_layout(tmp_path):
+    """write_text_encoder (the CLIP tower bench.py ships in its model dir so that the e2e leg runs prompt -> token ids
+    -> on-device text tower): every key and shape is what transformers' CLIPTextModel expects, embeddings at the
+    N(0, 0.02) scale transformers initialises them with."""
+    import json
+    import os
+    from safetensors.torch import load_file
+    from transformers import CLIPTextConfig, CLIPTextModel
+    from dreamlab_b200 import synthetic as syn
+    syn.write_text_encoder(str(tmp_path), layers=2)
+    te = os.path.join(str(tmp_path), "text_encoder")
+    cj = json.load(open(os.path.join(te, "config.json")))
+    cfg = CLIPTextConfig(**{k: v for k, v in cj.items() if not k.startswith("_") and k not in ("architectures", "model_type")})
+    sd = load_file(os.path.join(te, "model.safetensors"))
+    r = CLIPTextModel(cfg).load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
+    assert r.missing_keys == [] and r.unexpected_keys == []
+    assert abs(float(sd["text_model.embeddings.token_embedding.weight"].float().std()) - 0.02) < 2e-3
+
+
+def test_hashed_stand_in_token_ids():
+    """_hash_tokens (no tokenizer files in the model dir): BOS, one id per UTF-8 byte (at most 75), EOS padding; ids
+    inside the vocabulary; a function of the prompt alone."""
+    from backends.b200_worker import _hash_tokens
+    ids = _hash_tokens(["", "ab", "x" * 200, "ü"])
+    assert ids.shape == (4, 77) and ids.dtype == torch.long
+    assert (ids[:, 0] == 49406).all() and (ids[0, 1:] == 49407).all()
+    assert ids[1, 1] == (ord("a") * 193) % 49406 and ids[1, 2] == (ord("b") * 193 + 7919) % 49406 and ids[1, 3] == 49407
+    assert (ids[2, 1:76] != 49407).all() and ids[2, 76] == 49407 and int(ids.max()) <= 49407 and int(ids.min()) >= 0
+    assert ids[3, 1] == (0xC3 * 193) % 49406 and ids[3, 2] == (0xBC * 193 + 7919) % 49406
+    assert torch.equal(_hash_tokens(["ab"])[0], ids[1])

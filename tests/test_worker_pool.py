@@ -285,3 +285,53 @@ def test_workers_are_created_concurrently(pool_factory):
     t0 = time.perf_counter()
     pool = pool_factory(worker_factory=factory, num_workers=4, max_batch=4)
     assert time.perf_counter() - t0 < 0.6 and [w.worker_id for w in pool._workers] == [0, 1, 2, 3]
+
+
+def test_deferred_results_with_a_wait_are_parked_on_one_waiter_per_batch(pool_factory):
+    """A worker whose deferred results are still on the device hands out thunks with `wait()`: the pool parks ONE
+    waiter thread per batch on it (not one encoder thread per request), the worker thread is back for the next batch
+    at once, and every future still resolves; an error raised by the wait reaches every request of that batch."""
+    gate = threading.Event()
+    waits, order = [], []
+
+    class Thunk:
+        def __init__(self, tag, fail):
+            self.tag, self.fail = tag, fail
+
+        def wait(self):
+            waits.append(self.tag)
+            gate.wait(10)
+            if self.fail:
+                raise RuntimeError("device fault")
+
+        def __call__(self):
+            return (b"png-" + self.tag.encode(), 0)
+
+    class W(FakeWorker):
+        supports_deferred = True
+
+        def run_batch(self, jobs, with_latents=False, deferred=False):
+            order.append([j.req.prompt for j in jobs])
+            fail = jobs[0].req.prompt.startswith("bad")
+            th = [Thunk(j.req.prompt, fail) for j in jobs]
+            return th if deferred else [t() for t in th]
+
+    pool = pool_factory(worker_factory=lambda worker_id=0: W(worker_id), num_workers=1, max_batch=4)
+    try:
+        futs = [pool.submit_job(GenerationJob(req=req(f"a{i}"))) for i in range(4)]
+        t0 = time.monotonic()
+        while len(order) < 1 and time.monotonic() - t0 < 5:
+            time.sleep(0.01)
+        futs += [pool.submit_job(GenerationJob(req=req(f"bad{i}"))) for i in range(2)]
+        t0 = time.monotonic()
+        while sum(map(len, order)) < 6 and time.monotonic() - t0 < 5:   # later batches are taken while the first still "runs"
+            time.sleep(0.01)
+        assert len(order) >= 2 and not any(f.done() for f in futs)
+        gate.set()
+        assert sorted(f.result(timeout=10)[0] for f in futs[:4]) == [b"png-a0", b"png-a1", b"png-a2", b"png-a3"]
+        for f in futs[4:]:
+            with pytest.raises(RuntimeError, match="device fault"):
+                f.result(timeout=10)
+        assert len(waits) == len(order) < 6                        # one wait per batch, not per request
+    finally:
+        gate.set()
