@@ -18,6 +18,7 @@ import io
 import json
 import collections
 import os
+import time
 from typing import List, Sequence, Tuple
 
 import torch
@@ -272,7 +273,12 @@ class B200Worker(PipelineWorker):
         called: the pool runs them on encoder threads while this worker's thread already drives
         the next batch on the GPU (PIL's ~20 ms per 512^2 image would otherwise cap a worker at
         ~50 img/s)."""
+        timing = _BATCH_TIMING is not None
         with torch.cuda.device(self.device):
+            if timing:
+                t_in = time.perf_counter()
+                ev0 = torch.cuda.Event(enable_timing=True)
+                ev0.record()
             parsed = [self._parse(j.req) for j in jobs]
             width, height = parsed[0][0], parsed[0][1]
             steps = int(jobs[0].req.num_inference_steps)
@@ -314,6 +320,12 @@ class B200Worker(PipelineWorker):
                 host, done = _to_host_async(png_dev)
             else:
                 host, done = _to_host_async(img)
+            if timing:
+                # debug aid (B200_BATCH_TIMING=1): host time to enqueue the batch, device time from its first to its
+                # last command, and when both happened — enough to tell an idle GPU from a slow one
+                ev1 = torch.cuda.Event(enable_timing=True)
+                ev1.record()
+                _BATCH_TIMING.append((self.worker_id, len(jobs), t_in, time.perf_counter(), ev0, ev1))
             self._admit(done)
 
         def finish(i):
@@ -406,6 +418,26 @@ def _encoders():
         n = int(os.environ.get("B200_PNG_THREADS", "0")) or min(16, os.cpu_count() or 4)
         _ENCODERS = ThreadPoolExecutor(max_workers=n, thread_name_prefix="png")
     return _ENCODERS
+
+
+# B200_BATCH_TIMING=1: run_batch appends (worker, batch size, t_enter, t_enqueued, first event, last event)
+_BATCH_TIMING = [] if os.environ.get("B200_BATCH_TIMING", "0") not in ("0", "", "false") else None
+
+
+def batch_timing_summary():
+    """-> per-worker medians of the B200_BATCH_TIMING records (call after the work has finished)."""
+    import statistics
+    out = {}
+    for wid in sorted({r[0] for r in _BATCH_TIMING or []}):
+        rows = [r for r in _BATCH_TIMING if r[0] == wid]
+        gpu = [r[4].elapsed_time(r[5]) for r in rows]
+        host = [(r[3] - r[2]) * 1e3 for r in rows]
+        period = [(b[2] - a[2]) * 1e3 for a, b in zip(rows, rows[1:])]
+        out[wid] = {"batches": len(rows), "device_ms_median": statistics.median(gpu),
+                    "device_ms_max": max(gpu), "host_enqueue_ms_median": statistics.median(host),
+                    "host_enqueue_ms_max": max(host),
+                    "period_ms_median": statistics.median(period) if period else None}
+    return out
 
 
 class _Deferred:

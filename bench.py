@@ -265,10 +265,12 @@ def pool_requests(pool, c, n, seed0):
         guidance_scale=c["gs"], seed=seed0 + i))) for i in range(n)]
 
 
-def pool_e2e(pool, c, n_requests, warm_requests):
+def pool_e2e(pool, c, n_requests, warm_requests, before_timed=None):
     """-> (seconds for n_requests, mean PNG bytes).  Requests in (host objects), PNG bytes out."""
     for f in pool_requests(pool, c, warm_requests, 0):          # graph capture, encoder threads, allocator
         f.result(timeout=1200)
+    if before_timed is not None:
+        before_timed()
     t0 = time.perf_counter()
     outs = [f.result(timeout=1200) for f in pool_requests(pool, c, n_requests, 100000)]
     dt = time.perf_counter() - t0
@@ -648,9 +650,16 @@ def run_pool(args, c):
     pool = make_pool(c, root, name, n)
     B = c["batch"]
     n_req = n * B * args.steps
-    dt, png_bytes = pool_e2e(pool, c, n_req, 2 * n * B)
+    # clocks / throttle reasons of EVERY GPU during the timed region: eight GPUs running back to back in one box
+    # is also a box-level power question
+    samplers = [ClockSampler(i) for i in range(ngpu)]
+    dt, png_bytes = pool_e2e(pool, c, n_req, 2 * n * B, before_timed=lambda: [sp.start() for sp in samplers])
+    clocks = [sp.stop() for sp in samplers]
     pool.shutdown()
     v = n_req / dt
+    if os.environ.get("B200_BATCH_TIMING", "0") not in ("0", "", "false"):
+        from backends.b200_worker import batch_timing_summary
+        print(json.dumps({"batch_timing": batch_timing_summary()}), file=sys.stderr)
     print(json.dumps({
         "metric": c["metric"], "value": v, "unit": UNIT, "n_gpus": ngpu, "steps": args.steps, "warmup": 2,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -664,6 +673,9 @@ def run_pool(args, c):
                         "CLIP-L text tower on the device -> LCM loop -> VAE) -> PNG bytes",
                 "requests": n_req, "timed": "wall clock, first submit to last PNG"},
         "gpu_launches": None,
+        "clocks": {"per_gpu_sm_mhz": [k["sm_mhz"] for k in clocks], "sm_max_mhz": clocks[0]["sm_max_mhz"],
+                   "reasons": sorted({r for k in clocks for r in k["reasons"]}),
+                   "samples": [k.get("samples") for k in clocks]},
     }))
 
 

@@ -103,7 +103,9 @@ class CLIPTextB200:
                         out = self.forward(ids, want_hidden)
                 g = self._graphs[key] = (graph, ids, out)
             graph, ids, out = g
-            ids[:B].copy_(input_ids)
+            # pinned staging + async copy: a pageable host-to-device copy would first wait for the stream to drain
+            src = input_ids.pin_memory() if input_ids.device.type == "cpu" and not input_ids.is_pinned() else input_ids
+            ids[:B].copy_(src, non_blocking=True)
             graph.replay()
             return {k: v[:B] for k, v in out.items()}
 

@@ -707,6 +707,12 @@ import threading as _threading
 CAPTURE_LOCK = _threading.Lock()
 
 
+def _pinned(x: torch.Tensor) -> torch.Tensor:
+    """Host tensors -> page-locked staging (torch's caching host allocator; it keeps the block until the async copy
+    that reads it has run); device tensors pass through."""
+    return x.pin_memory() if x.device.type == "cpu" and not x.is_pinned() else x
+
+
 class _StaticGraph:
     """One captured CUDA graph of the whole hot path for a fixed (B, h, w, steps[, gs])."""
 
@@ -931,15 +937,18 @@ class LCMPipelineB200:
         with torch.cuda.device(self.device):
             if use_graph and record is None and teacher_latents is None:
                 g = self.graph_for(B, h, w, steps, cfg_scale, decode)
-                g.pe.copy_(pe_all, non_blocking=True)
+                # host inputs go through pinned staging: a copy from PAGEABLE host memory first waits for the stream to
+                # drain (CUDA's documented behaviour), i.e. for the previous batch — the thread could then not enqueue
+                # this batch behind it
+                g.pe.copy_(_pinned(pe_all), non_blocking=True)
                 if w_emb is not None:
-                    g.w_emb.copy_(w_emb, non_blocking=True)
+                    g.w_emb.copy_(_pinned(w_emb), non_blocking=True)
                 if add is not None:
-                    g.add[0].copy_(add[0], non_blocking=True)
-                    g.add[1].copy_(add[1], non_blocking=True)
-                g.lat.copy_(latents_nchw, non_blocking=True)
+                    g.add[0].copy_(_pinned(add[0]), non_blocking=True)
+                    g.add[1].copy_(_pinned(add[1]), non_blocking=True)
+                g.lat.copy_(_pinned(latents_nchw), non_blocking=True)
                 if steps > 1:
-                    g.noise.copy_(step_noise_nchw, non_blocking=True)
+                    g.noise.copy_(_pinned(step_noise_nchw), non_blocking=True)
                 g.graph.replay()
                 img, lat = g.img, g.final
             else:
