@@ -85,3 +85,28 @@ def test_hashed_stand_in_token_ids():
     assert (ids[2, 1:76] != 49407).all() and ids[2, 76] == 49407 and int(ids.max()) <= 49407 and int(ids.min()) >= 0
     assert ids[3, 1] == (0xC3 * 193) % 49406 and ids[3, 2] == (0xBC * 193 + 7919) % 49406
     assert torch.equal(_hash_tokens(["ab"])[0], ids[1])
+
+
+def test_layernorm_fold_identity_on_the_host():
+    """weights.fold_layernorm: LN(x) W^T + b == rstd * (x W'^T - mean * colsum(W')) + (b + W beta) with
+    W' = W * gamma — the identity the GEMM epilogue applies (dl_igemm_desc.ln_*), checked in fp64 on the host with
+    the bf16-rounded W' and its column sums exactly as the packer hands them to the kernel."""
+    from dreamlab_b200.weights import fold_layernorm
+    g = torch.Generator().manual_seed(3)
+    M, K, N, eps = 37, 320, 96, 1e-5
+    x = torch.randn(M, K, generator=g) * 2 + 0.5
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    bias, gamma, beta = torch.randn(N, generator=g), 1 + 0.2 * torch.randn(K, generator=g), 0.3 * torch.randn(K, generator=g)
+    wf, colsum, bf = fold_layernorm(w, bias, gamma, beta, "cpu")
+    assert wf.dtype == torch.bfloat16 and colsum.dtype == torch.float32 and bf.dtype == torch.float32
+    xd = x.double()
+    mean, var = xd.mean(1, keepdim=True), xd.var(1, unbiased=False, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    folded = rstd * (xd @ wf.double().t() - mean * colsum.double()[None, :]) + bf.double()[None, :]
+    # the same weights the kernel multiplies (bf16 W'), un-folded: LayerNorm without affine, then W' and the folded bias
+    direct = ((xd - mean) * rstd) @ wf.double().t() + bf.double()[None, :]
+    assert torch.allclose(folded, direct, rtol=0, atol=1e-5)        # colsum is kept in fp32
+    # and against torch's LayerNorm -> Linear in fp32: only the bf16 rounding of W' (and of W in the beta term) apart
+    ref = torch.nn.functional.linear(torch.nn.functional.layer_norm(x, (K,), gamma, beta, eps), w, bias)
+    err = (folded.float() - ref).abs().max() / ref.abs().max()
+    assert err < 1e-2, float(err)
