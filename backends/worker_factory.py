@@ -5,7 +5,7 @@ Keeps the reference's entry points (`backends/worker_factory.py:17-100`):
 `MODEL_ROOT`/`MODEL` (768/1024 -> sd15, 1280/2048 -> sdxl, anything else raises) and
 `create_cuda_worker(worker_id)`.  The only behavioural change: SD1.5-class models now get the
 B200-native `B200Worker` instead of `DiffusersCudaWorker`, SDXL-class models `B200SDXLWorker`
-instead of `DiffusersSDXLCudaWorker`.  There is no switch back to a diffusers worker and no other
+instead of `DiffusersSDXLCudaWorker` (`backends/cuda_worker.py` keeps the reference's two names, bound to them).  There is no switch back to a diffusers worker and no other
 backend: this package is the B200 path only.
 """
 from __future__ import annotations
@@ -81,14 +81,22 @@ def detect_worker_type() -> str:
         raise RuntimeError(f"Model detection failed: {e}")
 
 
+def _worker_class(worker_type: str):
+    """The class behind a worker type, looked up at call time under both of its names: the reference's
+    (`backends.cuda_worker.DiffusersCudaWorker` / `DiffusersSDXLCudaWorker`) and this package's
+    (`backends.b200_worker.B200Worker` / `B200SDXLWorker`).  A caller that rebound the reference name (its own tests
+    do, `tests/test_worker_factory.py:133-159`) gets what it installed."""
+    import backends.b200_worker as bw
+    import backends.cuda_worker as cw
+    ref_name, name = (("DiffusersSDXLCudaWorker", "B200SDXLWorker") if worker_type == "sdxl"
+                      else ("DiffusersCudaWorker", "B200Worker"))
+    cls = getattr(cw, ref_name)
+    return cls if cls is not cw._ORIGINALS[ref_name] else getattr(bw, name)
+
+
 def create_cuda_worker(worker_id: int) -> "PipelineWorker":
     worker_type = detect_worker_type()
-    if worker_type == "sdxl":
-        from backends.b200_worker import B200SDXLWorker
-        worker = B200SDXLWorker(worker_id=worker_id)
-        logger.info("[WorkerFactory] Created B200SDXLWorker (worker %d)", worker_id)
-        return worker
-    from backends.b200_worker import B200Worker
-    worker = B200Worker(worker_id=worker_id)
-    logger.info("[WorkerFactory] Created B200Worker (worker %d)", worker_id)
+    cls = _worker_class(worker_type)
+    worker = cls(worker_id=worker_id)
+    logger.info("[WorkerFactory] Created %s (worker %d)", getattr(cls, "__name__", cls), worker_id)
     return worker
