@@ -87,11 +87,17 @@ def _worker_class(worker_type: str):
     (`backends.b200_worker.B200Worker` / `B200SDXLWorker`).  A caller that rebound the reference name (its own tests
     do, `tests/test_worker_factory.py:133-159`) gets what it installed."""
     import backends.b200_worker as bw
-    import backends.cuda_worker as cw
     ref_name, name = (("DiffusersSDXLCudaWorker", "B200SDXLWorker") if worker_type == "sdxl"
                       else ("DiffusersCudaWorker", "B200Worker"))
+    try:
+        import backends.cuda_worker as cw
+    except ImportError:                       # the reference's own cuda_worker.py without diffusers installed
+        return getattr(bw, name)
+    originals = getattr(cw, "_ORIGINALS", None)
+    if originals is None:                     # the reference's own cuda_worker.py: its diffusers workers are not ours
+        return getattr(bw, name)
     cls = getattr(cw, ref_name)
-    return cls if cls is not cw._ORIGINALS[ref_name] else getattr(bw, name)
+    return cls if cls is not originals[ref_name] else getattr(bw, name)
 
 
 def create_cuda_worker(worker_id: int) -> "PipelineWorker":
